@@ -744,3 +744,660 @@ RO_API int ro_solve_varying_focal(const double *x1h, const double *x2h, const do
     align3(X, Y, m->q, m->t);
     return 1;
 }
+
+/* ------------------------------------------------------------------------- */
+/* L2: refine_monodepth_relpose so@0x261030 (+ shared so@0x2592e0, varying so@0x260fa0):
+ * lm_impl<MonoDepth*JacobianAccumulator> (bundle.cc / jacobian_impl.h).
+ * cost = sum_k [ w_s*rho(r_sampson^2) + rho(s_r*|pi(R (d1+u) p1 + t) - x2|^2) [z>0]
+ *                                      + rho(s_r*|pi(R^T (sigma (d2+v) p2 - t)) - x1|^2) [z>0] ]
+ * (SURVEY.md §8a row L2).  Parameters: rotation tangent (3, R <- R*exp([w]x)), t (3),
+ * scale, then (shift1, shift2) | f | (f1, f2).                                   */
+static double loss_eval(int type, double thr, double r2) {
+    const double t2 = thr * thr;
+    switch (type) {
+    case RO_LOSS_TRIVIAL: return r2;
+    case RO_LOSS_TRUNCATED: return r2 < t2 ? r2 : t2;
+    case RO_LOSS_HUBER: { double r = sqrt(r2); return r <= thr ? r2 : thr * (2.0 * r - thr); }
+    case RO_LOSS_CAUCHY: return t2 * log1p(r2 / t2);
+    case RO_LOSS_TRUNCATED_CAUCHY: return r2 > t2 ? t2 * log1p(1.0) : t2 * log1p(r2 / t2);
+    default: return r2 < t2 ? r2 : t2;
+    }
+}
+static double loss_weight(int type, double thr, double r2) {
+    const double t2 = thr * thr;
+    switch (type) {
+    case RO_LOSS_TRIVIAL: return 1.0;
+    case RO_LOSS_TRUNCATED: return r2 < t2 ? 1.0 : 0.0;
+    case RO_LOSS_HUBER: { double r = sqrt(r2); return r <= thr ? 1.0 : thr / r; }
+    case RO_LOSS_CAUCHY: return 1.0 / (1.0 + r2 / t2);
+    case RO_LOSS_TRUNCATED_CAUCHY: return r2 > t2 ? 0.0 : 1.0 / (1.0 + r2 / t2);
+    default: return r2 < t2 ? 1.0 : 0.0;
+    }
+}
+
+static int n_params(int variant) {
+    return variant == RO_CALIB ? 7 : (variant == RO_SHARED ? 8 : 9);
+}
+
+typedef struct {
+    double rs;          /* sampson residual */
+    double r12[2];      /* reprojection 1->2 */
+    double r21[2];      /* reprojection 2->1 */
+    int v12, v21;       /* positive-depth flags */
+    double Js[9], J12[2][9], J21[2][9];
+} pt_terms;
+
+typedef struct {
+    int variant;
+    double R[9], E[9];
+    ro_model m;
+} lm_ctx;
+
+static void lm_ctx_init(lm_ctx *c, int variant, const ro_model *m) {
+    c->variant = variant;
+    c->m = *m;
+    quat_to_rotmat(m->q, c->R);
+    ro_essential_from_motion(m->q, m->t, c->E);
+}
+
+static void point_terms(const lm_ctx *c, const double x1[2], const double x2[2], double d1, double d2,
+                        int want_jac, pt_terms *o) {
+    const int variant = c->variant;
+    const double *R = c->R, *E = c->E;
+    const ro_model *m = &c->m;
+    const double f1 = m->f1, f2 = m->f2;
+    const double p1[3] = {x1[0] / f1, x1[1] / f1, 1.0};
+    const double p2[3] = {x2[0] / f2, x2[1] / f2, 1.0};
+    const int np = n_params(variant);
+    if (want_jac) memset(o->Js, 0, sizeof(o->Js) + sizeof(o->J12) + sizeof(o->J21));
+    /* --- Sampson --- */
+    double Ep1[3], Etp2[3];
+    matvec3(E, p1, Ep1);
+    matTvec3(E, p2, Etp2);
+    const double C = dot3(p2, Ep1);
+    const double A = Ep1[0] * Ep1[0] + Ep1[1] * Ep1[1];
+    const double B = Etp2[0] * Etp2[0] + Etp2[1] * Etp2[1];
+    const double if1sq = 1.0 / (f1 * f1), if2sq = 1.0 / (f2 * f2);
+    const double den = A * if2sq + B * if1sq;
+    const double inv = 1.0 / sqrt(den);
+    o->rs = C * inv;
+    if (want_jac) {
+        const double k = 0.5 * C * inv * inv * inv;
+        double Rp1[3];
+        matvec3(R, p1, Rp1);
+        for (int i = 0; i < 3; ++i) {
+            double e[3] = {0, 0, 0}; e[i] = 1.0;
+            double exp1[3], dEp1[3], dEtp2[3], tmp[3];
+            /* rotation */
+            cross3(e, p1, exp1);
+            matvec3(E, exp1, dEp1);
+            cross3(e, Etp2, tmp);
+            dEtp2[0] = -tmp[0]; dEtp2[1] = -tmp[1];
+            double dC = dot3(Etp2, exp1);
+            double dden = 2.0 * (Ep1[0] * dEp1[0] + Ep1[1] * dEp1[1]) * if2sq +
+                          2.0 * (Etp2[0] * dEtp2[0] + Etp2[1] * dEtp2[1]) * if1sq;
+            o->Js[i] = dC * inv - k * dden;
+            /* translation */
+            cross3(e, Rp1, dEp1);
+            cross3(e, p2, tmp);
+            double rt[3];
+            matTvec3(R, tmp, rt);
+            dEtp2[0] = -rt[0]; dEtp2[1] = -rt[1];
+            dC = dot3(p2, dEp1);
+            dden = 2.0 * (Ep1[0] * dEp1[0] + Ep1[1] * dEp1[1]) * if2sq +
+                   2.0 * (Etp2[0] * dEtp2[0] + Etp2[1] * dEtp2[1]) * if1sq;
+            o->Js[3 + i] = dC * inv - k * dden;
+        }
+        if (variant == RO_SHARED || variant == RO_VARYING) {
+            const double dp1[3] = {-p1[0] / f1, -p1[1] / f1, 0.0};
+            const double dp2[3] = {-p2[0] / f2, -p2[1] / f2, 0.0};
+            double dEp1[3], dEtp2[3];
+            matvec3(E, dp1, dEp1);
+            matTvec3(E, dp2, dEtp2);
+            double dC1 = dot3(Etp2, dp1);
+            double dden1 = 2.0 * (Ep1[0] * dEp1[0] + Ep1[1] * dEp1[1]) * if2sq - 2.0 * B * if1sq / f1;
+            double dC2 = dot3(Ep1, dp2);
+            double dden2 = 2.0 * (Etp2[0] * dEtp2[0] + Etp2[1] * dEtp2[1]) * if1sq - 2.0 * A * if2sq / f2;
+            double j1 = dC1 * inv - k * dden1, j2 = dC2 * inv - k * dden2;
+            if (variant == RO_SHARED) o->Js[7] = j1 + j2;
+            else { o->Js[7] = j1; o->Js[8] = j2; }
+        }
+    }
+    /* --- reprojection 1 -> 2 --- */
+    {
+        const double a = d1 + m->shift1;
+        const double P[3] = {a * p1[0], a * p1[1], a * p1[2]};
+        double Z[3];
+        matvec3(R, P, Z);
+        Z[0] += m->t[0]; Z[1] += m->t[1]; Z[2] += m->t[2];
+        o->v12 = Z[2] > 0.0;
+        const double iz = 1.0 / Z[2];
+        const double u0 = Z[0] * iz, u1 = Z[1] * iz;
+        o->r12[0] = f2 * u0 - x2[0];
+        o->r12[1] = f2 * u1 - x2[1];
+        if (want_jac && o->v12) {
+            const double g = f2 * iz;
+#define PROJ_JAC(dZ, col)                                   \
+    do {                                                    \
+        o->J12[0][col] = g * ((dZ)[0] - u0 * (dZ)[2]);      \
+        o->J12[1][col] = g * ((dZ)[1] - u1 * (dZ)[2]);      \
+    } while (0)
+            for (int i = 0; i < 3; ++i) {
+                double e[3] = {0, 0, 0}; e[i] = 1.0;
+                double exP[3], dZ[3];
+                cross3(e, P, exP);
+                matvec3(R, exP, dZ);
+                PROJ_JAC(dZ, i);
+                PROJ_JAC(e, 3 + i);
+            }
+            if (variant == RO_CALIB_SHIFT) {
+                double dZ[3];
+                matvec3(R, p1, dZ);
+                PROJ_JAC(dZ, 7);
+            }
+            if (variant == RO_SHARED || variant == RO_VARYING) {
+                const double dP[3] = {-a * p1[0] / f1, -a * p1[1] / f1, 0.0};
+                double dZ[3];
+                matvec3(R, dP, dZ);
+                PROJ_JAC(dZ, 7);
+                int c2 = variant == RO_SHARED ? 7 : 8;
+                o->J12[0][c2] += u0;
+                o->J12[1][c2] += u1;
+            }
+#undef PROJ_JAC
+        }
+    }
+    /* --- reprojection 2 -> 1 --- */
+    {
+        const double bb = d2 + m->shift2;
+        const double b = m->scale * bb;
+        const double Q[3] = {b * p2[0] - m->t[0], b * p2[1] - m->t[1], b * p2[2] - m->t[2]};
+        double Y[3];
+        matTvec3(R, Q, Y);
+        o->v21 = Y[2] > 0.0;
+        const double iz = 1.0 / Y[2];
+        const double u0 = Y[0] * iz, u1 = Y[1] * iz;
+        o->r21[0] = f1 * u0 - x1[0];
+        o->r21[1] = f1 * u1 - x1[1];
+        if (want_jac && o->v21) {
+            const double g = f1 * iz;
+#define PROJ_JAC(dY, col)                                   \
+    do {                                                    \
+        o->J21[0][col] = g * ((dY)[0] - u0 * (dY)[2]);      \
+        o->J21[1][col] = g * ((dY)[1] - u1 * (dY)[2]);      \
+    } while (0)
+            for (int i = 0; i < 3; ++i) {
+                double e[3] = {0, 0, 0}; e[i] = 1.0;
+                double dY[3];
+                cross3(Y, e, dY);
+                PROJ_JAC(dY, i);
+                double dT[3] = {-R[3 * i], -R[3 * i + 1], -R[3 * i + 2]};
+                PROJ_JAC(dT, 3 + i);
+            }
+            {
+                const double dQ[3] = {bb * p2[0], bb * p2[1], bb * p2[2]};
+                double dY[3];
+                matTvec3(R, dQ, dY);
+                PROJ_JAC(dY, 6);
+            }
+            if (variant == RO_CALIB_SHIFT) {
+                const double dQ[3] = {m->scale * p2[0], m->scale * p2[1], m->scale * p2[2]};
+                double dY[3];
+                matTvec3(R, dQ, dY);
+                PROJ_JAC(dY, 8);
+            }
+            if (variant == RO_SHARED || variant == RO_VARYING) {
+                const double dQ[3] = {-b * p2[0] / f2, -b * p2[1] / f2, 0.0};
+                double dY[3];
+                matTvec3(R, dQ, dY);
+                int c2 = variant == RO_SHARED ? 7 : 8;
+                o->J21[0][c2] += g * (dY[0] - u0 * dY[2]);
+                o->J21[1][c2] += g * (dY[1] - u1 * dY[2]);
+                o->J21[0][7] += u0;
+                o->J21[1][7] += u1;
+            }
+#undef PROJ_JAC
+        }
+    }
+    (void)np;
+}
+
+RO_API double ro_cost(int variant, const double *x1, const double *x2, const double *d1, const double *d2,
+                      size_t n, const ro_model *m, double scale_reproj, double weight_sampson, int loss_type,
+                      double loss_scale) {
+    lm_ctx c;
+    lm_ctx_init(&c, variant, m);
+    double cost = 0.0;
+    pt_terms o;
+    for (size_t k = 0; k < n; ++k) {
+        point_terms(&c, x1 + 2 * k, x2 + 2 * k, d1[k], d2[k], 0, &o);
+        if (weight_sampson > 0.0) cost += weight_sampson * loss_eval(loss_type, loss_scale, o.rs * o.rs);
+        if (scale_reproj > 0.0) {
+            if (o.v12) cost += loss_eval(loss_type, loss_scale, scale_reproj * (o.r12[0] * o.r12[0] + o.r12[1] * o.r12[1]));
+            if (o.v21) cost += loss_eval(loss_type, loss_scale, scale_reproj * (o.r21[0] * o.r21[0] + o.r21[1] * o.r21[1]));
+        }
+    }
+    return cost;
+}
+
+/* JtJ: 9x9 row-major (only the leading np x np block is used), Jtr: 9 */
+RO_API void ro_accumulate(int variant, const double *x1, const double *x2, const double *d1, const double *d2,
+                          size_t n, const ro_model *m, double scale_reproj, double weight_sampson,
+                          int loss_type, double loss_scale, double *JtJ, double *Jtr) {
+    lm_ctx c;
+    lm_ctx_init(&c, variant, m);
+    const int np = n_params(variant);
+    memset(JtJ, 0, 81 * sizeof(double));
+    memset(Jtr, 0, 9 * sizeof(double));
+    pt_terms o;
+    for (size_t k = 0; k < n; ++k) {
+        point_terms(&c, x1 + 2 * k, x2 + 2 * k, d1[k], d2[k], 1, &o);
+        if (weight_sampson > 0.0) {
+            double w = weight_sampson * loss_weight(loss_type, loss_scale, o.rs * o.rs);
+            if (w != 0.0)
+                for (int i = 0; i < np; ++i) {
+                    Jtr[i] += w * o.Js[i] * o.rs;
+                    for (int j = 0; j <= i; ++j) JtJ[9 * i + j] += w * o.Js[i] * o.Js[j];
+                }
+        }
+        if (scale_reproj > 0.0) {
+            if (o.v12) {
+                double r2 = scale_reproj * (o.r12[0] * o.r12[0] + o.r12[1] * o.r12[1]);
+                double w = scale_reproj * loss_weight(loss_type, loss_scale, r2);
+                if (w != 0.0)
+                    for (int i = 0; i < np; ++i) {
+                        Jtr[i] += w * (o.J12[0][i] * o.r12[0] + o.J12[1][i] * o.r12[1]);
+                        for (int j = 0; j <= i; ++j)
+                            JtJ[9 * i + j] += w * (o.J12[0][i] * o.J12[0][j] + o.J12[1][i] * o.J12[1][j]);
+                    }
+            }
+            if (o.v21) {
+                double r2 = scale_reproj * (o.r21[0] * o.r21[0] + o.r21[1] * o.r21[1]);
+                double w = scale_reproj * loss_weight(loss_type, loss_scale, r2);
+                if (w != 0.0)
+                    for (int i = 0; i < np; ++i) {
+                        Jtr[i] += w * (o.J21[0][i] * o.r21[0] + o.J21[1][i] * o.r21[1]);
+                        for (int j = 0; j <= i; ++j)
+                            JtJ[9 * i + j] += w * (o.J21[0][i] * o.J21[0][j] + o.J21[1][i] * o.J21[1][j]);
+                    }
+            }
+        }
+    }
+    for (int i = 0; i < np; ++i)
+        for (int j = i + 1; j < np; ++j) JtJ[9 * i + j] = JtJ[9 * j + i];
+}
+
+/* Cholesky (lower) solve of A x = b on the leading np x np block; NaN on failure (as Eigen LLT). */
+static void llt_solve(const double *A9, const double *b, int np, double *x) {
+    double L[81];
+    memset(L, 0, sizeof(L));
+    for (int j = 0; j < np; ++j) {
+        double s = A9[9 * j + j];
+        for (int k = 0; k < j; ++k) s -= L[9 * j + k] * L[9 * j + k];
+        double d = sqrt(s);
+        L[9 * j + j] = d;
+        for (int i = j + 1; i < np; ++i) {
+            double v = A9[9 * i + j];
+            for (int k = 0; k < j; ++k) v -= L[9 * i + k] * L[9 * j + k];
+            L[9 * i + j] = v / d;
+        }
+    }
+    double y[9];
+    for (int i = 0; i < np; ++i) {
+        double v = b[i];
+        for (int k = 0; k < i; ++k) v -= L[9 * i + k] * y[k];
+        y[i] = v / L[9 * i + i];
+    }
+    for (int i = np - 1; i >= 0; --i) {
+        double v = y[i];
+        for (int k = i + 1; k < np; ++k) v -= L[9 * k + i] * x[k];
+        x[i] = v / L[9 * i + i];
+    }
+}
+
+static void model_step(int variant, const ro_model *m, const double *dp, ro_model *out) {
+    *out = *m;
+    double dq[4], qn[4];
+    quat_exp(dp, dq);
+    quat_multiply(m->q, dq, qn);
+    memcpy(out->q, qn, 32);
+    out->t[0] += dp[3]; out->t[1] += dp[4]; out->t[2] += dp[5];
+    out->scale += dp[6];
+    if (variant == RO_CALIB_SHIFT) { out->shift1 += dp[7]; out->shift2 += dp[8]; }
+    if (variant == RO_SHARED) { out->f1 += dp[7]; out->f2 = out->f1; }
+    if (variant == RO_VARYING) { out->f1 += dp[7]; out->f2 += dp[8]; }
+}
+
+RO_API void ro_refine(int variant, const double *x1, const double *x2, const double *d1, const double *d2,
+                      size_t n, ro_model *m, double scale_reproj, double weight_sampson,
+                      const ro_bundle_opt *opt, ro_bundle_stats *stats) {
+    const int np = n_params(variant);
+    double JtJ[81], Jtr[9], sol[9];
+    ro_bundle_stats st;
+    st.cost = ro_cost(variant, x1, x2, d1, d2, n, m, scale_reproj, weight_sampson, opt->loss_type, opt->loss_scale);
+    st.initial_cost = st.cost;
+    st.grad_norm = -1;
+    st.step_norm = -1;
+    st.invalid_steps = 0;
+    st.lambda = opt->initial_lambda;
+    int recompute = 1;
+    for (st.iterations = 0; st.iterations < opt->max_iterations; ++st.iterations) {
+        if (recompute) {
+            ro_accumulate(variant, x1, x2, d1, d2, n, m, scale_reproj, weight_sampson, opt->loss_type,
+                          opt->loss_scale, JtJ, Jtr);
+            double g = 0;
+            for (int i = 0; i < np; ++i) g += Jtr[i] * Jtr[i];
+            st.grad_norm = sqrt(g);
+            if (st.grad_norm < opt->gradient_tol) break;
+        }
+        for (int k = 0; k < np; ++k) JtJ[9 * k + k] += st.lambda;
+        llt_solve(JtJ, Jtr, np, sol);
+        double sn = 0;
+        for (int i = 0; i < np; ++i) { sol[i] = -sol[i]; sn += sol[i] * sol[i]; }
+        st.step_norm = sqrt(sn);
+        if (st.step_norm < opt->step_tol) break;
+        ro_model mn;
+        model_step(variant, m, sol, &mn);
+        double cost_new = ro_cost(variant, x1, x2, d1, d2, n, &mn, scale_reproj, weight_sampson,
+                                  opt->loss_type, opt->loss_scale);
+        if (cost_new < st.cost) {
+            *m = mn;
+            st.lambda = fmax(opt->min_lambda, st.lambda / 10);
+            st.cost = cost_new;
+            recompute = 1;
+        } else {
+            st.invalid_steps++;
+            for (int k = 0; k < np; ++k) JtJ[9 * k + k] -= st.lambda;
+            st.lambda = fmin(opt->max_lambda, st.lambda * 10);
+            recompute = 0;
+        }
+    }
+    if (stats) *stats = st;
+}
+
+/* ------------------------------------------------------------------------- */
+/* R1: ransac<Est,Model> so@0x22f030 + score_models<> so@0x22ebc0 (ransac_impl.h),
+ * estimators of robust/estimators/relative_pose.cc.            */
+RO_API int ro_solve_shared_focal(const double *x1h, const double *x2h, const double *d1, const double *d2,
+                                 ro_model *out);
+
+typedef struct {
+    int variant;
+    size_t n;
+    const double *x1, *x2, *d1, *d2;
+    const ro_ransac_opt *opt;
+    uint64_t rng;
+    double sq_thr, scale_reproj;
+    ro_bundle_opt lo;
+} estimator;
+
+static int est_generate(estimator *e, ro_model *models) {
+    size_t s[3];
+    ro_draw_sample(3, e->n, &e->rng, s);
+    double x1h[9], x2h[9], d1[3], d2[3];
+    for (int i = 0; i < 3; ++i) {
+        x1h[3 * i] = e->x1[2 * s[i]]; x1h[3 * i + 1] = e->x1[2 * s[i] + 1]; x1h[3 * i + 2] = 1.0;
+        x2h[3 * i] = e->x2[2 * s[i]]; x2h[3 * i + 1] = e->x2[2 * s[i] + 1]; x2h[3 * i + 2] = 1.0;
+        d1[i] = e->d1[s[i]];
+        d2[i] = e->d2[s[i]];
+    }
+    switch (e->variant) {
+    case RO_CALIB: return ro_solve_calib_scale(x1h, x2h, d1, d2, models);
+    case RO_CALIB_SHIFT: return ro_solve_calib_shift(x1h, x2h, d1, d2, models);
+    case RO_SHARED: return ro_solve_shared_focal(x1h, x2h, d1, d2, models);
+    default: return ro_solve_varying_focal(x1h, x2h, d1, d2, models);
+    }
+}
+
+static double est_score(const estimator *e, const ro_model *m, size_t *count) {
+    if (e->variant == RO_CALIB || e->variant == RO_CALIB_SHIFT)
+        return ro_msac_score_pose(m->q, m->t, e->x1, e->x2, e->n, e->sq_thr, count);
+    double F[9];
+    ro_fundamental_from_model(m, F);
+    return ro_msac_score_F(F, e->x1, e->x2, e->n, e->sq_thr, count);
+}
+
+static void est_refine(const estimator *e, ro_model *m) {
+    ro_refine(e->variant, e->x1, e->x2, e->d1, e->d2, e->n, m, e->scale_reproj, e->opt->weight_sampson,
+              &e->lo, NULL);
+}
+
+RO_API void ro_ransac(int variant, const double *x1, const double *x2, const double *d1, const double *d2,
+                      size_t n, const ro_ransac_opt *opt, ro_model *best, ro_ransac_stats *stats,
+                      char *inliers) {
+    estimator e;
+    e.variant = variant; e.n = n; e.x1 = x1; e.x2 = x2; e.d1 = d1; e.d2 = d2; e.opt = opt;
+    e.rng = opt->seed;
+    e.sq_thr = opt->max_epipolar_error * opt->max_epipolar_error;
+    e.scale_reproj = opt->max_reproj_error > 0.0
+                         ? (opt->max_epipolar_error * opt->max_epipolar_error) /
+                               (opt->max_reproj_error * opt->max_reproj_error)
+                         : 0.0;
+    e.lo.max_iterations = 25; e.lo.loss_type = RO_LOSS_TRUNCATED;
+    /* VaryingFocalMonodepthPoseEstimator::refine_model so@0x4fb0a0 never copies the threshold into its
+     * BundleOptions: loss_scale stays at the struct default 1.0 (so@0x5232a0); the calibrated (so@0x4fa550)
+     * and shared-focal (so@0x4fad60) estimators use opt.max_epipolar_error.  Reproduced as is. */
+    e.lo.loss_scale = variant == RO_VARYING ? 1.0 : opt->max_epipolar_error;
+    e.lo.gradient_tol = 1e-10; e.lo.step_tol = 1e-8; e.lo.initial_lambda = 1e-3;
+    e.lo.min_lambda = 1e-10; e.lo.max_lambda = 1e10;
+
+    model_init(best);
+    stats->refinements = 0; stats->iterations = 0; stats->num_inliers = 0;
+    stats->inlier_ratio = 0.0; stats->model_score = DBL_MAX;
+    if (inliers) memset(inliers, 0, n);
+    if (n < 3) return;
+
+    size_t best_minimal_inliers = 0;
+    double best_minimal_score = DBL_MAX;
+    double dyn_max_iter = (double)opt->max_iterations;
+    const double log_prob_missing = log(1.0 - opt->success_prob);
+    ro_model models[8];
+    size_t cnt = 0;
+    for (stats->iterations = 0; stats->iterations < opt->max_iterations; stats->iterations++) {
+        if (stats->iterations > opt->min_iterations && (double)stats->iterations > dyn_max_iter) break;
+        int nm = est_generate(&e, models);
+        int best_idx = -1;
+        for (int i = 0; i < nm; ++i) {
+            double score = est_score(&e, &models[i], &cnt);
+            int more = cnt > best_minimal_inliers;
+            int better = score < best_minimal_score;
+            if (more || better) {
+                if (more) best_minimal_inliers = cnt;
+                if (better) best_minimal_score = score;
+                best_idx = i;
+                if (score < stats->model_score) {
+                    stats->model_score = score;
+                    *best = models[i];
+                    stats->num_inliers = (int64_t)cnt;
+                }
+            }
+        }
+        if (best_idx == -1) continue;
+        ro_model refined = models[best_idx];
+        est_refine(&e, &refined);
+        stats->refinements++;
+        double rs = est_score(&e, &refined, &cnt);
+        if (rs < stats->model_score) {
+            stats->model_score = rs;
+            stats->num_inliers = (int64_t)cnt;
+            *best = refined;
+        }
+        stats->inlier_ratio = (double)stats->num_inliers / (double)n;
+        if (stats->inlier_ratio >= 0.9999) dyn_max_iter = (double)opt->min_iterations;
+        else if (stats->inlier_ratio <= 0.0001) dyn_max_iter = (double)opt->max_iterations;
+        else {
+            const double prob_outlier = 1.0 - pow(stats->inlier_ratio, 3.0);
+            dyn_max_iter = ceil(log_prob_missing / log(prob_outlier) * opt->dyn_num_trials_mult);
+        }
+    }
+    ro_model refined = *best;
+    est_refine(&e, &refined);
+    stats->refinements++;
+    double rs = est_score(&e, &refined, &cnt);
+    if (rs < stats->model_score) {
+        stats->model_score = rs;
+        stats->num_inliers = (int64_t)cnt;
+        *best = refined;
+    }
+    stats->inlier_ratio = (double)stats->num_inliers / (double)n;
+    if (inliers) {
+        if (variant == RO_CALIB || variant == RO_CALIB_SHIFT)
+            ro_get_inliers_pose(best->q, best->t, x1, x2, n, e.sq_thr, inliers);
+        else {
+            double F[9];
+            ro_fundamental_from_model(best, F);
+            ro_get_inliers_F(F, x1, x2, n, e.sq_thr, inliers);
+        }
+    }
+}
+
+/* P1/P2: estimate_monodepth_relative_pose so@0x224170, estimate_shared_focal_… so@0x223300,
+ * estimate_varying_focal_… so@0x223a40 (robust.cc).  cam = (fx, fy, cx, cy) for the
+ * calibrated variants (SIMPLE_PINHOLE: fx = fy); x in pixels.  Focal variants take
+ * principal-point-centred pixels and ignore cam1/cam2.                              */
+RO_API void ro_estimate(int variant, const double *x1, const double *x2, const double *d1, const double *d2,
+                        size_t n, const double *cam1, const double *cam2, const ro_ransac_opt *ropt,
+                        const ro_bundle_opt *bopt, ro_model *best, ro_ransac_stats *stats, char *inliers) {
+    double *a = (double *)malloc(sizeof(double) * (4 * n + 4));
+    double *b = a + 2 * n;
+    ro_ransac_opt ro = *ropt;
+    ro_bundle_opt bo = *bopt;
+    double nscale = 1.0;
+    if (variant == RO_CALIB || variant == RO_CALIB_SHIFT) {
+        for (size_t k = 0; k < n; ++k) {
+            a[2 * k] = (x1[2 * k] - cam1[2]) / cam1[0];
+            a[2 * k + 1] = (x1[2 * k + 1] - cam1[3]) / cam1[1];
+            b[2 * k] = (x2[2 * k] - cam2[2]) / cam2[0];
+            b[2 * k + 1] = (x2[2 * k + 1] - cam2[3]) / cam2[1];
+        }
+        const double fo1 = 0.5 * (cam1[0] + cam1[1]), fo2 = 0.5 * (cam2[0] + cam2[1]);
+        const double k = 0.5 * (1.0 / fo1 + 1.0 / fo2);
+        ro.max_epipolar_error = ropt->max_epipolar_error * k;
+        ro.max_reproj_error = ropt->max_reproj_error * k;
+        bo.loss_scale = 0.5 * ro.max_epipolar_error;
+    } else {
+        /* normalize_points so@0x4f6ae0: shared scale, no centroid */
+        double s = 0.0;
+        for (size_t k = 0; k < n; ++k) {
+            s += sqrt(x1[2 * k] * x1[2 * k] + x1[2 * k + 1] * x1[2 * k + 1]);
+            s += sqrt(x2[2 * k] * x2[2 * k] + x2[2 * k + 1] * x2[2 * k + 1]);
+        }
+        nscale = s / (sqrt(2.0) * (double)n);
+        for (size_t k = 0; k < 2 * n; ++k) { a[k] = x1[k] / nscale; b[k] = x2[k] / nscale; }
+        ro.max_epipolar_error = ropt->max_epipolar_error / nscale;
+        ro.max_reproj_error = ropt->max_reproj_error / nscale;
+        bo.loss_scale = bopt->loss_scale / nscale;
+    }
+    ro_ransac(variant, a, b, d1, d2, n, &ro, best, stats, inliers);
+    if (stats->num_inliers > 3) {
+        size_t m = 0;
+        double *ia = (double *)malloc(sizeof(double) * (6 * n));
+        double *ib = ia + 2 * n, *id1 = ia + 4 * n, *id2 = ia + 5 * n;
+        for (size_t k = 0; k < n; ++k)
+            if (inliers[k]) {
+                ia[2 * m] = a[2 * k]; ia[2 * m + 1] = a[2 * k + 1];
+                ib[2 * m] = b[2 * k]; ib[2 * m + 1] = b[2 * k + 1];
+                id1[m] = d1[k]; id2[m] = d2[k];
+                ++m;
+            }
+        const double sr = ro.max_reproj_error > 0.0
+                              ? (ro.max_epipolar_error * ro.max_epipolar_error) /
+                                    (ro.max_reproj_error * ro.max_reproj_error)
+                              : 0.0;
+        ro_refine(variant, ia, ib, id1, id2, m, best, sr, ropt->weight_sampson, &bo, NULL);
+        free(ia);
+    }
+    if (variant == RO_SHARED || variant == RO_VARYING) {
+        best->f1 *= nscale;
+        best->f2 *= nscale;
+    }
+    free(a);
+}
+
+/* ------------------------------------------------------------------------- */
+/* S3: relpose_monodepth_3pt_shared_focal so@0x18fdf0.  Unknowns f, scale and the depth
+ * of the third point in camera 2: points 0,1 align in 3-D,
+ * point 2 only reprojects.  With g = 1/f^2, nu = depth_2/scale and
+ *   S1 = g*A1_01 + B1_01,  S2 = g*A2_01 + B2_01,  scale^2 = S1/S2,
+ * the difference of the (0,2) and (1,2) distance equations is linear in nu
+ * (nu = N/(2 S1 L)), and substituting into the (0,2) equation leaves a quintic in g
+ * whose constant term vanishes identically (g = 0 <=> f = inf), i.e. a quartic:
+ * <= 4 solutions, as the binary's 4x4 action matrix.  Valid iff g > 0 and nu > 0.
+ * The binary orders its solutions by its eigen-solver; here they come in the order of
+ * solve_quartic_real (documented deviation; affects only same-iteration RANSAC ties). */
+typedef struct { double c[8]; int deg; } poly;
+static poly pmake(int deg, const double *c) { poly p; memset(&p, 0, sizeof p); p.deg = deg; for (int i = 0; i <= deg; ++i) p.c[i] = c[i]; return p; }
+static poly plin(double c1, double c0) { double c[2] = {c0, c1}; return pmake(1, c); } /* c1*g + c0 */
+static poly pmul(poly a, poly b) {
+    poly r; memset(&r, 0, sizeof r); r.deg = a.deg + b.deg;
+    for (int i = 0; i <= a.deg; ++i) for (int j = 0; j <= b.deg; ++j) r.c[i + j] += a.c[i] * b.c[j];
+    return r;
+}
+static poly padd(poly a, double sa, poly b, double sb) {
+    poly r; memset(&r, 0, sizeof r); r.deg = a.deg > b.deg ? a.deg : b.deg;
+    for (int i = 0; i <= r.deg; ++i) r.c[i] = sa * (i <= a.deg ? a.c[i] : 0.0) + sb * (i <= b.deg ? b.c[i] : 0.0);
+    return r;
+}
+static double peval(poly p, double x) { double v = 0; for (int i = p.deg; i >= 0; --i) v = v * x + p.c[i]; return v; }
+
+RO_API int ro_solve_shared_focal(const double *x1h, const double *x2h, const double *d1, const double *d2,
+                                 ro_model *out) {
+    double A1[3], B1[3]; /* pairs 01, 02, 12 */
+    static const int PI[3] = {0, 0, 1}, PJ[3] = {1, 2, 2};
+    for (int r = 0; r < 3; ++r) {
+        int i = PI[r], j = PJ[r];
+        double vx = d1[i] * x1h[3 * i] - d1[j] * x1h[3 * j], vy = d1[i] * x1h[3 * i + 1] - d1[j] * x1h[3 * j + 1];
+        A1[r] = vx * vx + vy * vy;
+        B1[r] = (d1[i] - d1[j]) * (d1[i] - d1[j]);
+    }
+    double vx = d2[0] * x2h[0] - d2[1] * x2h[3], vy = d2[0] * x2h[1] - d2[1] * x2h[4];
+    const double A2 = vx * vx + vy * vy, B2 = (d2[0] - d2[1]) * (d2[0] - d2[1]);
+    const double n2 = x2h[6] * x2h[6] + x2h[7] * x2h[7];
+    const double c02 = d2[0] * (x2h[0] * x2h[6] + x2h[1] * x2h[7]);
+    const double c12 = d2[1] * (x2h[3] * x2h[6] + x2h[4] * x2h[7]);
+    const double m0 = d2[0] * d2[0] * (x2h[0] * x2h[0] + x2h[1] * x2h[1]);
+    const double m1 = d2[1] * d2[1] * (x2h[3] * x2h[3] + x2h[4] * x2h[4]);
+    poly S1 = plin(A1[0], B1[0]), S2 = plin(A2, B2);
+    poly T02 = plin(A1[1], B1[1]), T12 = plin(A1[2], B1[2]);
+    poly L = plin(c02 - c12, d2[0] - d2[1]);
+    poly N = padd(pmul(S1, plin(m0 - m1, d2[0] * d2[0] - d2[1] * d2[1])), 1.0, pmul(S2, padd(T02, 1.0, T12, -1.0)), -1.0);
+    poly LL = pmul(L, L);
+    poly lhs = pmul(pmul(pmul(S2, T02), S1), LL);                       /* *4 */
+    poly r1 = pmul(pmul(N, N), plin(n2, 1.0));
+    poly r2 = pmul(pmul(pmul(S1, N), L), plin(c02, d2[0]));             /* *4 */
+    poly r3 = pmul(pmul(pmul(S1, S1), LL), plin(m0, d2[0] * d2[0]));    /* *4 */
+    poly P = padd(padd(lhs, 4.0, r1, -1.0), 1.0, padd(r2, 4.0, r3, -4.0), 1.0);
+    /* P.c[0] == 0 analytically: quartic P.c[5] g^4 + ... + P.c[1] */
+    double roots[4];
+    int nr = ro_solve_quartic_real(P.c[4] / P.c[5], P.c[3] / P.c[5], P.c[2] / P.c[5], P.c[1] / P.c[5], roots);
+    int n = 0;
+    for (int ir = 0; ir < nr; ++ir) {
+        double g = roots[ir];
+        /* Newton polish on the quartic */
+        for (int it = 0; it < 3; ++it) {
+            double v = (((P.c[5] * g + P.c[4]) * g + P.c[3]) * g + P.c[2]) * g + P.c[1];
+            double dv = ((4.0 * P.c[5] * g + 3.0 * P.c[4]) * g + 2.0 * P.c[3]) * g + P.c[2];
+            if (dv == 0.0) break;
+            g -= v / dv;
+        }
+        if (!(g > 0.0)) continue;
+        const double s1 = peval(S1, g), s2 = peval(S2, g);
+        const double sc2 = s1 / s2;
+        if (!(sc2 > 0.0)) continue;
+        const double nu = peval(N, g) / (2.0 * s1 * peval(L, g));
+        if (!(nu > 0.0)) continue;
+        const double w = sqrt(g), f = 1.0 / w, scale = sqrt(sc2);
+        ro_model *m = &out[n];
+        model_init(m);
+        m->scale = scale; m->f1 = f; m->f2 = f;
+        double X[3][3], Y[3][3];
+        for (int i = 0; i < 3; ++i) {
+            X[i][0] = d1[i] * x1h[3 * i] * w; X[i][1] = d1[i] * x1h[3 * i + 1] * w; X[i][2] = d1[i];
+            double dep = scale * (i < 2 ? d2[i] : nu);
+            Y[i][0] = dep * x2h[3 * i] * w; Y[i][1] = dep * x2h[3 * i + 1] * w; Y[i][2] = dep;
+        }
+        align3(X, Y, m->q, m->t);
+        ++n;
+    }
+    return n;
+}
