@@ -1,0 +1,173 @@
+/*
+ * repose_b200.h — C ABI of the B200-native batched RePoseD relative-pose estimator.
+ *
+ * This is the drop-in boundary for the hot path behind
+ *   poselib.estimate_monodepth_relative_pose                 (whl:_core.pyi:446-475, so@0x224170)
+ *   poselib.estimate_monodepth_shared_focal_relative_pose    (whl:_core.pyi:477-488, so@0x223300)
+ *   poselib.estimate_monodepth_varying_focal_relative_pose   (whl:_core.pyi:490-501, so@0x223a40)
+ * of PoseLib 2.0.5 + PR #152 as used by kocurvik/mdrp (/root/reference/make_pair.py:111,
+ * make_video.py:284, README.md:86-96).  The reference binds these through pybind11 one
+ * pair per call; this library takes a ragged BATCH of pairs per call (a single pair is a
+ * batch of one).  Plain pointers and sizes only; no exceptions cross the boundary: every
+ * function returns 0 on success or a negative rp_status, and rp_last_error() explains.
+ *
+ * There is no CPU execution path: every entry point needs a CUDA device (sm_100a).
+ */
+#ifndef REPOSE_B200_H
+#define REPOSE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RP_API __attribute__((visibility("default")))
+
+typedef struct rp_ctx rp_ctx;
+
+enum rp_status {
+    RP_OK = 0,
+    RP_ERR_INVALID = -1,   /* bad argument (null pointer, negative size, unknown variant) */
+    RP_ERR_CUDA = -2,      /* CUDA runtime error; text in rp_last_error */
+    RP_ERR_NO_DEVICE = -3, /* no CUDA device / wrong architecture */
+    RP_ERR_OVERFLOW = -4   /* an internal fixed-capacity list overflowed */
+};
+
+/* estimator variants (which minimal solver / Jacobian accumulator is used) */
+enum rp_variant {
+    RP_CALIB = 0,       /* calibrated, scale only:   P3P + scale (generate_models so@0x4fe090), 7 params */
+    RP_CALIB_SHIFT = 1, /* calibrated, scale+shifts: relpose_monodepth_3pt so@0x155ca0, 9 params        */
+    RP_SHARED = 2,      /* shared unknown focal:     relpose_monodepth_3pt_shared_focal so@0x18fdf0, 8   */
+    RP_VARYING = 3      /* two unknown focals:       relpose_monodepth_3pt_varying_focal so@0x19bcd0, 9  */
+};
+
+/* BundleOptions.loss_type */
+enum rp_loss {
+    RP_LOSS_TRIVIAL = 0, RP_LOSS_TRUNCATED = 1, RP_LOSS_HUBER = 2, RP_LOSS_CAUCHY = 3,
+    RP_LOSS_TRUNCATED_CAUCHY = 4
+};
+
+/* MonoDepthTwoViewGeometry / MonoDepthImagePair (whl:_core.pyi:171-204): 12 doubles.
+ * X2 = scale*(d2+shift2)*K2^-1 x2 = R(q)*(d1+shift1)*K1^-1 x1 + t ; q is w-first.
+ * f1,f2 are 1 for the calibrated variants. */
+typedef struct {
+    double q[4];
+    double t[3];
+    double scale, shift1, shift2;
+    double f1, f2;
+} rp_model;
+
+/* RansacStats */
+typedef struct {
+    int64_t refinements, iterations, num_inliers;
+    double inlier_ratio, model_score;
+} rp_stats;
+
+/* RansacOptions + BundleOptions (whl:METADATA:71-107), the keys the monodepth path reads */
+typedef struct {
+    int64_t max_iterations, min_iterations;
+    double dyn_num_trials_mult, success_prob;
+    double max_reproj_error, max_epipolar_error;
+    uint64_t seed;
+    int32_t estimate_shift; /* monodepth_estimate_shift (calibrated variants) */
+    int32_t reserved0;
+    double weight_sampson;  /* monodepth_weight_sampson */
+    /* final refinement (bundle_opt) */
+    int64_t bundle_max_iterations;
+    int32_t loss_type;
+    int32_t reserved1;
+    double loss_scale, gradient_tol, step_tol, initial_lambda, min_lambda, max_lambda;
+} rp_options;
+
+/* LM options for the stage entry point rp_refine_batch (BundleOptions) */
+typedef struct {
+    int64_t max_iterations;
+    int32_t loss_type;
+    int32_t reserved;
+    double loss_scale, gradient_tol, step_tol, initial_lambda, min_lambda, max_lambda;
+} rp_bundle_options;
+
+/* BundleStats */
+typedef struct {
+    int64_t iterations;
+    double initial_cost, cost, lambda;
+    int64_t invalid_steps;
+    double step_norm, grad_norm;
+} rp_bundle_stats;
+
+/* ---- lifetime ------------------------------------------------------------------ */
+RP_API int rp_create(int device, rp_ctx **out);
+RP_API void rp_destroy(rp_ctx *ctx);
+RP_API const char *rp_last_error(const rp_ctx *ctx); /* ctx may be NULL: last creation error */
+RP_API void rp_default_options(rp_options *opt);     /* PoseLib defaults (RansacOptions(), BundleOptions()) */
+/* number of kernels this library launched on ctx since creation (bench "gpu_launches") */
+RP_API int64_t rp_launch_count(const rp_ctx *ctx);
+
+/* ---- the hot path: batched estimators -------------------------------------------
+ * n_pairs image pairs, pair p owning correspondences [offsets[p], offsets[p+1]).
+ * x1,x2: [offsets[n_pairs], 2] pixel coordinates (row-major), d1,d2: [offsets[n_pairs]].
+ * variant RP_CALIB / RP_CALIB_SHIFT (replaces estimate_monodepth_relative_pose):
+ *     cams: [n_pairs, 8] = (fx1, fy1, cx1, cy1, fx2, fy2, cx2, cy2) pinhole intrinsics;
+ *     opt->estimate_shift selects RP_CALIB_SHIFT when variant is RP_CALIB.
+ * variant RP_SHARED / RP_VARYING (replace the two focal estimators): x already
+ *     principal-point-centred, cams ignored (may be NULL).
+ * Outputs: models [n_pairs], stats [n_pairs], masks [offsets[n_pairs]] (0/1 bytes, the
+ * `inliers` list of the reference's info dict).
+ * _host: all pointers are HOST memory (pinned or pageable); copies are inside the call.
+ * _dev : all pointers are DEVICE memory on ctx's device; `stream` is a cudaStream_t
+ *        (NULL = default stream); the call is synchronous with respect to the host. */
+RP_API int rp_estimate_batch_host(rp_ctx *ctx, int variant, int64_t n_pairs, const int64_t *offsets,
+                                  const double *x1, const double *x2, const double *d1, const double *d2,
+                                  const double *cams, const rp_options *opt, rp_model *models,
+                                  rp_stats *stats, uint8_t *masks);
+RP_API int rp_estimate_batch_dev(rp_ctx *ctx, int variant, int64_t n_pairs, const int64_t *offsets,
+                                 const double *x1, const double *x2, const double *d1, const double *d2,
+                                 const double *cams, const rp_options *opt, rp_model *models,
+                                 rp_stats *stats, uint8_t *masks, void *stream);
+
+/* ---- stage entry points (parity tests; all pointers HOST memory) -----------------
+ * Each mirrors one exported stage of the reference binary. */
+
+/* R2: RandomSampler::generate_sample so@0x4f8970 — `iters` consecutive 3-samples out of n
+ * points from `seed`; samples: [iters,3] int32. */
+RP_API int rp_sample_batch(rp_ctx *ctx, int64_t n, uint64_t seed, int64_t iters, int32_t *samples);
+
+/* S1-S4: minimal solvers on n_problems independent triplets.  x1h,x2h: [n,3,3] homogeneous
+ * (x,y,1) points, d1,d2: [n,3].  models: [n,4], counts: [n] (solutions per problem). */
+RP_API int rp_solve_batch(rp_ctx *ctx, int variant, int64_t n_problems, const double *x1h, const double *x2h,
+                          const double *d1, const double *d2, rp_model *models, int32_t *counts);
+
+/* SC/SF/I1: compute_sampson_msac_score so@0x4f61d0 / so@0x4f65d0 for n_models models against
+ * ONE pair's n_points normalised correspondences x1,x2: [n_points,2].  RP_CALIB*: pose scorer
+ * (Sampson + cheirality); RP_SHARED/RP_VARYING: F = diag(1,1,f2) E diag(1,1,f1), Sampson only.
+ * scores,counts: [n_models]; masks (optional, may be NULL): [n_models, n_points] get_inliers bytes. */
+RP_API int rp_score_batch(rp_ctx *ctx, int variant, int64_t n_models, const rp_model *models, int64_t n_points,
+                          const double *x1, const double *x2, double sq_threshold, double *scores,
+                          int64_t *counts, uint8_t *masks);
+
+/* L2: refine_monodepth_relpose so@0x261030 (+ shared so@0x2592e0, varying so@0x260fa0) for
+ * n_models start models against ONE pair's correspondences (all points, uniform weights;
+ * `mask` optional [n_points] selects a subset, as the final refinement does). */
+RP_API int rp_refine_batch(rp_ctx *ctx, int variant, int64_t n_models, rp_model *models, int64_t n_points,
+                           const double *x1, const double *x2, const double *d1, const double *d2,
+                           const uint8_t *mask, double scale_reproj, double weight_sampson,
+                           const rp_bundle_options *opt, rp_bundle_stats *stats);
+
+/* ---- measurement helpers ---------------------------------------------------------
+ * Pipe micro-benchmarks for the roofline denominators SURVEY.md §8d asks for (the driver's
+ * MEASURED_PEAKS.json has only HBM and bf16): sustained FP64 and FP32 FMA throughput of
+ * this device, in TFLOP/s (2 flops per FMA). */
+RP_API int rp_measure_pipes(rp_ctx *ctx, double *fp64_tflops, double *fp32_tflops);
+
+/* per-stage device time of the last rp_estimate_batch_* call on ctx, milliseconds:
+ * [0] prepare, [1] sample, [2] solve, [3] score(minimal), [4] scan, [5] LO refine,
+ * [6] LO score+merge, [7] final refine, [8] total device, [9] H2D, [10] D2H;
+ * counters: [0] hypotheses scored, [1] point-scores, [2] LO problems, [3] LM iterations */
+RP_API int rp_last_timing(const rp_ctx *ctx, double *ms11, int64_t *counters4);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REPOSE_B200_H */
