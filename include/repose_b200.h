@@ -116,8 +116,10 @@ RP_API int64_t rp_launch_count(const rp_ctx *ctx);
  * Outputs: models [n_pairs], stats [n_pairs], masks [offsets[n_pairs]] (0/1 bytes, the
  * `inliers` list of the reference's info dict).
  * _host: all pointers are HOST memory (pinned or pageable); copies are inside the call.
- * _dev : all pointers are DEVICE memory on ctx's device; `stream` is a cudaStream_t
- *        (NULL = default stream); the call is synchronous with respect to the host. */
+ * _dev : x1,x2,d1,d2,cams,models,stats,masks are DEVICE memory on ctx's device (inputs already
+ *        resident in HBM); `offsets` and `opt` stay HOST memory (the host plans the chunks from
+ *        them); `stream` is a cudaStream_t (NULL = default stream); the call returns after the
+ *        stream has finished. */
 RP_API int rp_estimate_batch_host(rp_ctx *ctx, int variant, int64_t n_pairs, const int64_t *offsets,
                                   const double *x1, const double *x2, const double *d1, const double *d2,
                                   const double *cams, const rp_options *opt, rp_model *models,

@@ -1,0 +1,792 @@
+// repose_b200.cu — host orchestration + C ABI (include/repose_b200.h) of the batched RePoseD
+// estimator.  Everything numeric happens in the kernels of rp_kernels.cuh; this file plans the
+// chunks, owns the HBM workspace and replays the reference's call order:
+//   estimate_* (so@0x224170 / 0x223300 / 0x223a40) -> ransac_* -> ransac<> -> final refinement.
+// There is no host fallback: without a CUDA device rp_create fails.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "rp_kernels.cuh"
+
+using namespace rp;
+
+namespace {
+
+std::string g_create_error;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        const size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T *as() const { return (T *)p; }
+};
+
+enum { B_OFFS, B_PAIRS, B_PTS64, B_PTS32, B_BEAR, B_SAMPLES, B_MODELS, B_HYPITER, B_SCORE, B_COUNT, B_SEGCNT,
+       B_ITEMPFX, B_SCALARS, B_EVENTS, B_NEVENTS, B_LOMODELS, B_LOOFEV, B_LOCOUNT, B_PROBLIST, B_LOSCORE,
+       B_LOCNT, B_LOITEMPFX, B_BEST, B_FINSTART, B_FINSCORE, B_FINCNT, B_ONES, B_ONEPFX, B_ENABLE, B_STATS,
+       B_MASK, B_IN_X1, B_IN_X2, B_IN_D1, B_IN_D2, B_IN_CAMS, B_TMP0, B_TMP1, B_TMP2, B_NBUF };
+
+// device scalars living in B_SCALARS
+struct Scalars {
+    int n_items, n_lo_items, n_one_items, n_prob, n_pairs_scalar, overflow, pad0, pad1;
+    unsigned long long point_scores, lm_iters;
+    long long n_hyp;
+};
+
+constexpr int N_EVENTS = 12;
+
+}  // namespace
+
+struct rp_ctx {
+    int device = 0;
+    int sms = 148;
+    std::string err;
+    int64_t launches = 0;
+    cudaStream_t stream = nullptr;
+    DevBuf buf[B_NBUF];
+    cudaEvent_t ev[N_EVENTS];
+    double last_ms[11] = {0};
+    int64_t last_cnt[4] = {0};
+    size_t workspace_budget = (size_t)12 << 30;
+    int occ_score[4] = {0}, occ_lm[4] = {0};
+};
+
+namespace {
+
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess) {                                                                     \
+            char b_[512];                                                                            \
+            snprintf(b_, sizeof b_, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,             \
+                     cudaGetErrorString(e_));                                                        \
+            ctx->err = b_;                                                                           \
+            return RP_ERR_CUDA;                                                                      \
+        }                                                                                            \
+    } while (0)
+
+#define LAUNCHED()                                                                                   \
+    do {                                                                                             \
+        ctx->launches++;                                                                             \
+        CK(cudaGetLastError());                                                                      \
+    } while (0)
+
+inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+int fail(rp_ctx *ctx, int code, const char *msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+template <class K>
+int occupancy_grid(rp_ctx *ctx, K kernel, int threads) {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, 0) != cudaSuccess || nb < 1) nb = 1;
+    return nb * ctx->sms;
+}
+
+// ---- kernel launch helpers ---------------------------------------------------------------------
+int launch_score(rp_ctx *ctx, bool pose, bool mask, const ScoreArgs &a, cudaStream_t st) {
+    int grid;
+    if (pose) {
+        if (mask) { grid = occupancy_grid(ctx, score_kernel<true, true>, SCORE_THREADS); score_kernel<true, true><<<grid, SCORE_THREADS, 0, st>>>(a); }
+        else { grid = occupancy_grid(ctx, score_kernel<true, false>, SCORE_THREADS); score_kernel<true, false><<<grid, SCORE_THREADS, 0, st>>>(a); }
+    } else {
+        if (mask) { grid = occupancy_grid(ctx, score_kernel<false, true>, SCORE_THREADS); score_kernel<false, true><<<grid, SCORE_THREADS, 0, st>>>(a); }
+        else { grid = occupancy_grid(ctx, score_kernel<false, false>, SCORE_THREADS); score_kernel<false, false><<<grid, SCORE_THREADS, 0, st>>>(a); }
+    }
+    LAUNCHED();
+    return RP_OK;
+}
+
+int launch_lm(rp_ctx *ctx, int variant, const LMArgs &a, cudaStream_t st) {
+    int grid;
+    switch (variant) {
+    case RP_CALIB:
+        grid = occupancy_grid(ctx, lm_kernel<RP_CALIB, 7>, LM_THREADS);
+        lm_kernel<RP_CALIB, 7><<<grid, LM_THREADS, 0, st>>>(a);
+        break;
+    case RP_CALIB_SHIFT:
+        grid = occupancy_grid(ctx, lm_kernel<RP_CALIB_SHIFT, 9>, LM_THREADS);
+        lm_kernel<RP_CALIB_SHIFT, 9><<<grid, LM_THREADS, 0, st>>>(a);
+        break;
+    case RP_SHARED:
+        grid = occupancy_grid(ctx, lm_kernel<RP_SHARED, 8>, LM_THREADS);
+        lm_kernel<RP_SHARED, 8><<<grid, LM_THREADS, 0, st>>>(a);
+        break;
+    default:
+        grid = occupancy_grid(ctx, lm_kernel<RP_VARYING, 9>, LM_THREADS);
+        lm_kernel<RP_VARYING, 9><<<grid, LM_THREADS, 0, st>>>(a);
+        break;
+    }
+    LAUNCHED();
+    return RP_OK;
+}
+
+int launch_solve(rp_ctx *ctx, int variant, const SolveArgs &a, int n_pairs, cudaStream_t st) {
+    dim3 grid(a.nseg, n_pairs);
+    switch (variant) {
+    case RP_CALIB: solve_kernel<RP_CALIB><<<grid, SOLVE_THREADS, 0, st>>>(a); break;
+    case RP_CALIB_SHIFT: solve_kernel<RP_CALIB_SHIFT><<<grid, SOLVE_THREADS, 0, st>>>(a); break;
+    case RP_SHARED: solve_kernel<RP_SHARED><<<grid, SOLVE_THREADS, 0, st>>>(a); break;
+    default: solve_kernel<RP_VARYING><<<grid, SOLVE_THREADS, 0, st>>>(a); break;
+    }
+    LAUNCHED();
+    return RP_OK;
+}
+
+__global__ void valid_ones_kernel(int n_pairs, const PairParams *pairs, int *ones) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_pairs) ones[i] = pairs[i].valid ? 1 : 0;
+}
+
+// stage helper: already-normalised correspondences of ONE pair -> pts64 / pts32 / bearings + bounds
+__global__ void stage_points_kernel(int n, const double *x1, const double *x2, double sq_thr, Pt64 *pts64,
+                                    float4 *pts32, Bear *bear, PairParams *pair) {
+    const int lane = threadIdx.x;
+    double Mmax = 0.0, mmax = 0.0;
+    for (int k = lane; k < n; k += 32) {
+        Pt64 p;
+        p.x1_0 = x1[2 * k]; p.x1_1 = x1[2 * k + 1]; p.x2_0 = x2[2 * k]; p.x2_1 = x2[2 * k + 1];
+        pts64[k] = p;
+        pts32[k] = make_float4((float)p.x1_0, (float)p.x1_1, (float)p.x2_0, (float)p.x2_1);
+        const V3 b1 = bearing(p.x1_0, p.x1_1), b2 = bearing(p.x2_0, p.x2_1);
+        Bear b;
+        b.b1x = b1.x; b.b1y = b1.y; b.b1z = b1.z; b.b2x = b2.x; b.b2y = b2.y; b.b2z = b2.z;
+        bear[k] = b;
+        const double m1 = fabs(p.x1_0) + fabs(p.x1_1) + 1.0, m2 = fabs(p.x2_0) + fabs(p.x2_1) + 1.0;
+        Mmax = fmax(Mmax, m1 * m2);
+        mmax = fmax(mmax, fmax(m1, m2));
+    }
+    Mmax = warp_max(Mmax);
+    mmax = warp_max(mmax);
+    if (lane == 0) {
+        PairParams pp;
+        pp.off = 0; pp.n = n; pp.valid = 1;
+        pp.sq_thr = sq_thr;
+        pp.thr = sqrt(sq_thr) * (1.0 + 1e-15);  // only feeds the (conservative) FP32 filter bound
+        pp.scale_reproj = 0.0; pp.lo_loss_scale = pp.thr; pp.final_loss_scale = pp.thr; pp.nscale = 1.0;
+        pp.Mmax = Mmax * 1.000001; pp.mmax = mmax * 1.000001;
+        *pair = pp;
+    }
+}
+
+// ---- one chunk of pairs, everything on device ----------------------------------------------------
+struct ChunkIO {
+    int n_pairs;
+    long long n_points;
+    const long long *h_offsets_rel;  // host, [n_pairs+1], relative to the chunk
+    const double *x1, *x2, *d1, *d2, *cams;  // device, chunk-local
+    Model *models_out;               // device [n_pairs]
+    rp_stats *stats_out;             // device [n_pairs]
+    unsigned char *masks_out;        // device [n_points]
+};
+
+int run_chunk(rp_ctx *ctx, int variant, const rp_options &opt, const ChunkIO &io, cudaStream_t st) {
+    const int P = io.n_pairs;
+    const long long N = io.n_points;
+    const bool pose = variant == RP_CALIB || variant == RP_CALIB_SHIFT;
+    const int iters = (int)opt.max_iterations;
+    const int nseg = std::max(1, cdiv(iters, SEG));
+    const size_t slots_pp = (size_t)nseg * 4 * SEG;
+    const size_t slots = slots_pp * (size_t)P;
+
+    DevBuf *B = ctx->buf;
+    CK(B[B_OFFS].reserve(sizeof(long long) * (P + 1)));
+    CK(B[B_PAIRS].reserve(sizeof(PairParams) * P));
+    CK(B[B_PTS64].reserve(sizeof(Pt64) * std::max<long long>(N, 1)));
+    CK(B[B_PTS32].reserve(sizeof(float4) * std::max<long long>(N, 1)));
+    CK(B[B_BEAR].reserve(sizeof(Bear) * std::max<long long>(N, 1)));
+    CK(B[B_SAMPLES].reserve(sizeof(int) * 3 * (size_t)P * std::max(iters, 1)));
+    CK(B[B_MODELS].reserve(sizeof(Model) * slots));
+    CK(B[B_HYPITER].reserve(sizeof(int) * slots));
+    CK(B[B_SCORE].reserve(sizeof(double) * slots));
+    CK(B[B_COUNT].reserve(sizeof(int) * slots));
+    CK(B[B_SEGCNT].reserve(sizeof(int) * (size_t)P * nseg));
+    CK(B[B_ITEMPFX].reserve(sizeof(int) * ((size_t)P * nseg + 1)));
+    CK(B[B_SCALARS].reserve(sizeof(Scalars)));
+    CK(B[B_EVENTS].reserve(sizeof(int) * (size_t)P * EV));
+    CK(B[B_NEVENTS].reserve(sizeof(int) * P));
+    CK(B[B_LOMODELS].reserve(sizeof(Model) * (size_t)P * EV));
+    CK(B[B_LOOFEV].reserve(sizeof(int) * (size_t)P * EV));
+    CK(B[B_LOCOUNT].reserve(sizeof(int) * P));
+    CK(B[B_PROBLIST].reserve(sizeof(int) * (size_t)P * EV));
+    CK(B[B_LOSCORE].reserve(sizeof(double) * (size_t)P * EV));
+    CK(B[B_LOCNT].reserve(sizeof(int) * (size_t)P * EV));
+    CK(B[B_LOITEMPFX].reserve(sizeof(int) * (P + 1)));
+    CK(B[B_BEST].reserve(sizeof(Model) * P));
+    CK(B[B_FINSTART].reserve(sizeof(Model) * P));
+    CK(B[B_FINSCORE].reserve(sizeof(double) * P));
+    CK(B[B_FINCNT].reserve(sizeof(int) * P));
+    CK(B[B_ONES].reserve(sizeof(int) * P));
+    CK(B[B_ONEPFX].reserve(sizeof(int) * (P + 1)));
+    CK(B[B_ENABLE].reserve(sizeof(int) * P));
+    CK(B[B_STATS].reserve(sizeof(rp_stats) * P));
+
+    Scalars *sc = B[B_SCALARS].as<Scalars>();
+    PairParams *pairs = B[B_PAIRS].as<PairParams>();
+    Pt64 *pts64 = B[B_PTS64].as<Pt64>();
+    float4 *pts32 = B[B_PTS32].as<float4>();
+    Bear *bear = B[B_BEAR].as<Bear>();
+    int *samples = B[B_SAMPLES].as<int>();
+    Model *models = B[B_MODELS].as<Model>();
+    int *hyp_iter = B[B_HYPITER].as<int>();
+    double *score = B[B_SCORE].as<double>();
+    int *count = B[B_COUNT].as<int>();
+    int *seg_count = B[B_SEGCNT].as<int>();
+    int *item_prefix = B[B_ITEMPFX].as<int>();
+
+    Scalars h_sc;
+    memset(&h_sc, 0, sizeof h_sc);
+    h_sc.n_pairs_scalar = P;
+    CK(cudaMemcpyAsync(sc, &h_sc, sizeof h_sc, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(B[B_OFFS].p, io.h_offsets_rel, sizeof(long long) * (P + 1), cudaMemcpyHostToDevice, st));
+
+    cudaEvent_t *ev = ctx->ev;
+    CK(cudaEventRecord(ev[0], st));
+    // 1. prepare
+    {
+        PrepareArgs a;
+        a.variant = variant; a.n_pairs = P; a.offsets = B[B_OFFS].as<long long>();
+        a.x1 = io.x1; a.x2 = io.x2; a.cams = io.cams;
+        a.max_epipolar_error = opt.max_epipolar_error; a.max_reproj_error = opt.max_reproj_error;
+        a.loss_scale = opt.loss_scale;
+        a.pts64 = pts64; a.pts32 = pts32; a.bear = bear; a.pairs = pairs;
+        prepare_kernel<<<cdiv((long long)P * 32, 256), 256, 0, st>>>(a);
+        LAUNCHED();
+    }
+    CK(cudaEventRecord(ev[1], st));
+    // 2. sample
+    if (iters > 0) {
+        sample_kernel<<<cdiv((long long)P * 32, 256), 256, 0, st>>>(P, iters, pairs, opt.seed, samples);
+        LAUNCHED();
+    }
+    CK(cudaEventRecord(ev[2], st));
+    // 3. solve
+    {
+        SolveArgs a;
+        a.variant = variant; a.iters = iters; a.nseg = nseg; a.pairs = pairs; a.samples = samples;
+        a.pts64 = pts64; a.d1 = io.d1; a.d2 = io.d2; a.models = models; a.hyp_iter = hyp_iter; a.seg_count = seg_count;
+        int rc = launch_solve(ctx, variant, a, P, st);
+        if (rc) return rc;
+    }
+    CK(cudaEventRecord(ev[3], st));
+    // 4. score the minimal models
+    ScoreArgs sa;
+    sa.pairs = pairs; sa.pts32 = pts32; sa.pts64 = pts64; sa.bear = bear; sa.mask = nullptr;
+    {
+        build_items_kernel<<<1, 1024, 0, st>>>(P * nseg, seg_count, item_prefix, &sc->n_items, &sc->n_hyp);
+        LAUNCHED();
+        sa.n_groups = P * nseg; sa.grp_stride = 4 * SEG; sa.grp_per_pair = nseg; sa.grp_cnt = seg_count;
+        sa.item_prefix = item_prefix; sa.n_items = &sc->n_items; sa.models = models; sa.score = score; sa.count = count;
+        sa.point_scores = &sc->point_scores;
+        int rc = launch_score(ctx, pose, false, sa, st);
+        if (rc) return rc;
+    }
+    CK(cudaEventRecord(ev[4], st));
+    // 5. scan + LO problem list
+    {
+        ScanArgs a;
+        a.n_pairs = P; a.nseg = nseg; a.seg_count = seg_count; a.score = score; a.count = count;
+        a.events = B[B_EVENTS].as<int>(); a.n_events = B[B_NEVENTS].as<int>(); a.overflow = &sc->overflow;
+        scan_kernel<<<cdiv((long long)P * 32, 256), 256, 0, st>>>(a);
+        LAUNCHED();
+        LoPrepArgs l;
+        l.n_pairs = P; l.nseg = nseg; l.events = a.events; l.n_events = a.n_events; l.hyp_iter = hyp_iter;
+        l.models = models; l.lo_models = B[B_LOMODELS].as<Model>(); l.lo_of_event = B[B_LOOFEV].as<int>();
+        l.lo_count = B[B_LOCOUNT].as<int>(); l.prob_list = B[B_PROBLIST].as<int>(); l.n_prob = &sc->n_prob;
+        lo_prepare_kernel<<<cdiv(P, 128), 128, 0, st>>>(l);
+        LAUNCHED();
+    }
+    CK(cudaEventRecord(ev[5], st));
+    // 6. LO refinement of every trigger (independent problems)
+    LMArgs la;
+    memset(&la, 0, sizeof la);
+    la.pairs = pairs; la.pts64 = pts64; la.d1 = io.d1; la.d2 = io.d2;
+    la.weight_sampson = opt.weight_sampson; la.gradient_tol = 1e-10; la.step_tol = 1e-8;
+    la.initial_lambda = 1e-3; la.min_lambda = 1e-10; la.max_lambda = 1e10;
+    la.loss_scale_override = -1.0; la.scale_reproj_override = -1.0;
+    la.lm_iters = &sc->lm_iters;
+    {
+        la.prob_list = B[B_PROBLIST].as<int>(); la.n_prob = &sc->n_prob; la.prob_per_pair = EV;
+        la.models = B[B_LOMODELS].as<Model>(); la.use_final = 0;
+        int rc = launch_lm(ctx, variant, la, st);
+        if (rc) return rc;
+    }
+    CK(cudaEventRecord(ev[6], st));
+    // 7. score LO results, merge
+    {
+        build_items_kernel<<<1, 1024, 0, st>>>(P, B[B_LOCOUNT].as<int>(), B[B_LOITEMPFX].as<int>(), &sc->n_lo_items, nullptr);
+        LAUNCHED();
+        ScoreArgs s2 = sa;
+        s2.n_groups = P; s2.grp_stride = EV; s2.grp_per_pair = 1; s2.grp_cnt = B[B_LOCOUNT].as<int>();
+        s2.item_prefix = B[B_LOITEMPFX].as<int>(); s2.n_items = &sc->n_lo_items; s2.models = B[B_LOMODELS].as<Model>();
+        s2.score = B[B_LOSCORE].as<double>(); s2.count = B[B_LOCNT].as<int>(); s2.point_scores = nullptr;
+        int rc = launch_score(ctx, pose, false, s2, st);
+        if (rc) return rc;
+        MergeArgs m;
+        m.n_pairs = P; m.nseg = nseg; m.iters = iters; m.pairs = pairs; m.events = B[B_EVENTS].as<int>();
+        m.n_events = B[B_NEVENTS].as<int>(); m.lo_of_event = B[B_LOOFEV].as<int>(); m.score = score; m.count = count;
+        m.models = models; m.lo_score = B[B_LOSCORE].as<double>(); m.lo_count_inl = B[B_LOCNT].as<int>();
+        m.lo_models = B[B_LOMODELS].as<Model>(); m.lo_count = B[B_LOCOUNT].as<int>();
+        m.best = B[B_BEST].as<Model>(); m.stats = B[B_STATS].as<rp_stats>(); m.final_start = B[B_FINSTART].as<Model>();
+        merge_kernel<<<cdiv(P, 128), 128, 0, st>>>(m);
+        LAUNCHED();
+        // final LO from the best model, rescore, accept when strictly better
+        la.prob_list = nullptr; la.n_prob = &sc->n_pairs_scalar; la.prob_per_pair = 1;
+        la.models = B[B_FINSTART].as<Model>(); la.use_final = 0;
+        rc = launch_lm(ctx, variant, la, st);
+        if (rc) return rc;
+        valid_ones_kernel<<<cdiv(P, 256), 256, 0, st>>>(P, pairs, B[B_ONES].as<int>());
+        LAUNCHED();
+        build_items_kernel<<<1, 1024, 0, st>>>(P, B[B_ONES].as<int>(), B[B_ONEPFX].as<int>(), &sc->n_one_items, nullptr);
+        LAUNCHED();
+        ScoreArgs s3 = s2;
+        s3.grp_stride = 1; s3.grp_cnt = B[B_ONES].as<int>(); s3.item_prefix = B[B_ONEPFX].as<int>();
+        s3.n_items = &sc->n_one_items; s3.models = B[B_FINSTART].as<Model>();
+        s3.score = B[B_FINSCORE].as<double>(); s3.count = B[B_FINCNT].as<int>();
+        rc = launch_score(ctx, pose, false, s3, st);
+        if (rc) return rc;
+        Merge2Args m2;
+        m2.n_pairs = P; m2.pairs = pairs; m2.refined = B[B_FINSTART].as<Model>(); m2.ref_score = B[B_FINSCORE].as<double>();
+        m2.ref_count = B[B_FINCNT].as<int>(); m2.best = B[B_BEST].as<Model>(); m2.stats = B[B_STATS].as<rp_stats>();
+        merge2_kernel<<<cdiv(P, 128), 128, 0, st>>>(m2);
+        LAUNCHED();
+        // get_inliers of the RANSAC model (this is the mask the reference returns in `info`)
+        CK(cudaMemsetAsync(io.masks_out, 0, (size_t)std::max<long long>(N, 1), st));
+        ScoreArgs s4 = s3;
+        s4.models = B[B_BEST].as<Model>(); s4.mask = io.masks_out;
+        rc = launch_score(ctx, pose, true, s4, st);
+        if (rc) return rc;
+    }
+    CK(cudaEventRecord(ev[7], st));
+    // 8. final refinement on the inliers with the user's bundle options (if num_inliers > 3)
+    {
+        enable_final_kernel<<<cdiv(P, 256), 256, 0, st>>>(P, B[B_STATS].as<rp_stats>(), B[B_ENABLE].as<int>());
+        LAUNCHED();
+        la.prob_list = nullptr; la.n_prob = &sc->n_pairs_scalar; la.prob_per_pair = 1;
+        la.models = B[B_BEST].as<Model>(); la.use_final = 1; la.mask = io.masks_out; la.enable = B[B_ENABLE].as<int>();
+        la.max_iterations = (int)opt.bundle_max_iterations; la.loss_type = opt.loss_type;
+        la.gradient_tol = opt.gradient_tol; la.step_tol = opt.step_tol; la.initial_lambda = opt.initial_lambda;
+        la.min_lambda = opt.min_lambda; la.max_lambda = opt.max_lambda;
+        int rc = launch_lm(ctx, variant, la, st);
+        if (rc) return rc;
+        finalize_kernel<<<cdiv(P, 256), 256, 0, st>>>(P, variant, pairs, B[B_BEST].as<Model>());
+        LAUNCHED();
+        CK(cudaMemcpyAsync(io.models_out, B[B_BEST].p, sizeof(Model) * P, cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(io.stats_out, B[B_STATS].p, sizeof(rp_stats) * P, cudaMemcpyDeviceToDevice, st));
+    }
+    CK(cudaEventRecord(ev[8], st));
+    CK(cudaMemcpyAsync(&h_sc, sc, sizeof h_sc, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int i = 0; i < 8; ++i) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+        ctx->last_ms[i] += ms;
+    }
+    {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, ev[0], ev[8]));
+        ctx->last_ms[8] += ms;
+    }
+    ctx->last_cnt[0] += h_sc.n_hyp;
+    ctx->last_cnt[1] += (int64_t)h_sc.point_scores;
+    ctx->last_cnt[2] += h_sc.n_prob + P;
+    ctx->last_cnt[3] += (int64_t)h_sc.lm_iters;
+    if (h_sc.overflow) return fail(ctx, RP_ERR_OVERFLOW, "trigger event list overflowed (EV)");
+    return RP_OK;
+}
+
+size_t bytes_per_pair(int iters, long long avg_points) {
+    const int nseg = std::max(1, cdiv(iters, SEG));
+    const size_t slots_pp = (size_t)nseg * 4 * SEG;
+    return slots_pp * (sizeof(Model) + 4 + 8 + 4) + (size_t)iters * 12 + (size_t)EV * (sizeof(Model) + 24) +
+           (size_t)avg_points * (sizeof(Pt64) + 16 + sizeof(Bear) + 1) + 1024;
+}
+
+int check_common(rp_ctx *ctx, int variant, int64_t n_pairs, const int64_t *offsets, const rp_options *opt) {
+    if (!ctx) return RP_ERR_INVALID;
+    if (variant < 0 || variant > 3) return fail(ctx, RP_ERR_INVALID, "unknown variant");
+    if (n_pairs < 0 || !offsets || !opt) return fail(ctx, RP_ERR_INVALID, "null or negative argument");
+    if (opt->max_iterations < 0 || opt->max_iterations > (1 << 24)) return fail(ctx, RP_ERR_INVALID, "max_iterations out of range");
+    for (int64_t p = 0; p < n_pairs; ++p)
+        if (offsets[p + 1] < offsets[p] || offsets[p + 1] - offsets[p] > (1 << 28))
+            return fail(ctx, RP_ERR_INVALID, "offsets must be non-decreasing");
+    return RP_OK;
+}
+
+int estimate_impl(rp_ctx *ctx, int variant, int64_t n_pairs, const int64_t *offsets, const double *x1,
+                  const double *x2, const double *d1, const double *d2, const double *cams, const rp_options *opt_in,
+                  rp_model *models, rp_stats *stats, uint8_t *masks, bool host_io, cudaStream_t st) {
+    int rc = check_common(ctx, variant, n_pairs, offsets, opt_in);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    rp_options opt = *opt_in;
+    if (variant == RP_CALIB && opt.estimate_shift) variant = RP_CALIB_SHIFT;
+    if (variant == RP_CALIB_SHIFT) opt.estimate_shift = 1;
+    const bool pose = variant == RP_CALIB || variant == RP_CALIB_SHIFT;
+    if (pose && !cams && n_pairs > 0) return fail(ctx, RP_ERR_INVALID, "calibrated variants need cams");
+    memset(ctx->last_ms, 0, sizeof ctx->last_ms);
+    memset(ctx->last_cnt, 0, sizeof ctx->last_cnt);
+    if (n_pairs == 0) return RP_OK;
+    const long long Ntot = offsets[n_pairs] - offsets[0];
+    const size_t bpp = bytes_per_pair((int)opt.max_iterations, Ntot / n_pairs + 1);
+    int64_t chunk = (int64_t)std::max<size_t>(1, ctx->workspace_budget / bpp);
+    chunk = std::min<int64_t>(chunk, 32768);
+    std::vector<long long> rel;
+    DevBuf *B = ctx->buf;
+    for (int64_t p0 = 0; p0 < n_pairs; p0 += chunk) {
+        const int64_t p1 = std::min(n_pairs, p0 + chunk);
+        const int P = (int)(p1 - p0);
+        const long long o0 = offsets[p0], N = offsets[p1] - o0;
+        rel.resize(P + 1);
+        for (int i = 0; i <= P; ++i) rel[i] = offsets[p0 + i] - o0;
+        ChunkIO io;
+        io.n_pairs = P; io.n_points = N; io.h_offsets_rel = rel.data();
+        cudaEvent_t e0 = ctx->ev[9], e1 = ctx->ev[10], e2 = ctx->ev[11];
+        if (host_io) {
+            const size_t nn = (size_t)std::max<long long>(N, 1);
+            CK(B[B_IN_X1].reserve(16 * nn)); CK(B[B_IN_X2].reserve(16 * nn));
+            CK(B[B_IN_D1].reserve(8 * nn)); CK(B[B_IN_D2].reserve(8 * nn));
+            CK(B[B_IN_CAMS].reserve(64 * (size_t)P));
+            CK(B[B_TMP0].reserve(sizeof(Model) * P)); CK(B[B_TMP1].reserve(sizeof(rp_stats) * P));
+            CK(B[B_MASK].reserve(nn));
+            CK(cudaEventRecord(e0, st));
+            CK(cudaMemcpyAsync(B[B_IN_X1].p, x1 + 2 * o0, 16 * (size_t)N, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(B[B_IN_X2].p, x2 + 2 * o0, 16 * (size_t)N, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(B[B_IN_D1].p, d1 + o0, 8 * (size_t)N, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(B[B_IN_D2].p, d2 + o0, 8 * (size_t)N, cudaMemcpyHostToDevice, st));
+            if (pose) CK(cudaMemcpyAsync(B[B_IN_CAMS].p, cams + 8 * p0, 64 * (size_t)P, cudaMemcpyHostToDevice, st));
+            CK(cudaEventRecord(e1, st));
+            io.x1 = B[B_IN_X1].as<double>(); io.x2 = B[B_IN_X2].as<double>();
+            io.d1 = B[B_IN_D1].as<double>(); io.d2 = B[B_IN_D2].as<double>();
+            io.cams = pose ? B[B_IN_CAMS].as<double>() : nullptr;
+            io.models_out = B[B_TMP0].as<Model>(); io.stats_out = B[B_TMP1].as<rp_stats>();
+            io.masks_out = B[B_MASK].as<unsigned char>();
+        } else {
+            io.x1 = x1 + 2 * o0; io.x2 = x2 + 2 * o0; io.d1 = d1 + o0; io.d2 = d2 + o0;
+            io.cams = pose ? cams + 8 * p0 : nullptr;
+            io.models_out = (Model *)models + p0; io.stats_out = stats + p0; io.masks_out = masks + o0;
+        }
+        rc = run_chunk(ctx, variant, opt, io, st);
+        if (rc) return rc;
+        if (host_io) {
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            ctx->last_ms[9] += ms;
+            CK(cudaEventRecord(e1, st));
+            CK(cudaMemcpyAsync(models + p0, io.models_out, sizeof(Model) * P, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(stats + p0, io.stats_out, sizeof(rp_stats) * P, cudaMemcpyDeviceToHost, st));
+            if (N > 0) CK(cudaMemcpyAsync(masks + o0, io.masks_out, (size_t)N, cudaMemcpyDeviceToHost, st));
+            CK(cudaEventRecord(e2, st));
+            CK(cudaStreamSynchronize(st));
+            CK(cudaEventElapsedTime(&ms, e1, e2));
+            ctx->last_ms[10] += ms;
+        }
+    }
+    return RP_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+int rp_create(int device, rp_ctx **out) {
+    if (!out) return RP_ERR_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e);
+        return RP_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= ndev) {
+        g_create_error = "device index out of range";
+        return RP_ERR_INVALID;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10) {
+        g_create_error = "device is not sm_100-class (this library only ships sm_100a code)";
+        return RP_ERR_NO_DEVICE;
+    }
+    rp_ctx *ctx = new rp_ctx();
+    ctx->device = device;
+    ctx->sms = prop.multiProcessorCount;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        g_create_error = "cudaSetDevice / stream creation failed";
+        delete ctx;
+        return RP_ERR_CUDA;
+    }
+    for (auto &ev : ctx->ev) cudaEventCreate(&ev);
+    if (const char *gb = getenv("RP_WORKSPACE_GB")) {
+        const double v = atof(gb);
+        if (v > 0.01) ctx->workspace_budget = (size_t)(v * (double)((size_t)1 << 30));
+    }
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) ctx->workspace_budget = std::min(ctx->workspace_budget, free_b / 2);
+    *out = ctx;
+    return RP_OK;
+}
+
+void rp_destroy(rp_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (auto &b : ctx->buf) b.release();
+    for (auto &ev : ctx->ev) cudaEventDestroy(ev);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *rp_last_error(const rp_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int64_t rp_launch_count(const rp_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+void rp_default_options(rp_options *o) {
+    if (!o) return;
+    memset(o, 0, sizeof *o);
+    o->max_iterations = 100000; o->min_iterations = 1000; o->dyn_num_trials_mult = 3.0; o->success_prob = 0.9999;
+    o->max_reproj_error = 12.0; o->max_epipolar_error = 1.0; o->seed = 0; o->estimate_shift = 0; o->weight_sampson = 1.0;
+    o->bundle_max_iterations = 100; o->loss_type = RP_LOSS_CAUCHY; o->loss_scale = 1.0; o->gradient_tol = 1e-10;
+    o->step_tol = 1e-8; o->initial_lambda = 1e-3; o->min_lambda = 1e-10; o->max_lambda = 1e10;
+}
+
+int rp_estimate_batch_host(rp_ctx *ctx, int variant, int64_t n_pairs, const int64_t *offsets, const double *x1,
+                           const double *x2, const double *d1, const double *d2, const double *cams,
+                           const rp_options *opt, rp_model *models, rp_stats *stats, uint8_t *masks) {
+    if (!ctx) return RP_ERR_INVALID;
+    if (n_pairs > 0 && (!x1 || !x2 || !d1 || !d2 || !models || !stats || !masks))
+        return fail(ctx, RP_ERR_INVALID, "null data pointer");
+    return estimate_impl(ctx, variant, n_pairs, offsets, x1, x2, d1, d2, cams, opt, models, stats, masks, true, ctx->stream);
+}
+
+int rp_estimate_batch_dev(rp_ctx *ctx, int variant, int64_t n_pairs, const int64_t *offsets, const double *x1,
+                          const double *x2, const double *d1, const double *d2, const double *cams,
+                          const rp_options *opt, rp_model *models, rp_stats *stats, uint8_t *masks, void *stream) {
+    if (!ctx) return RP_ERR_INVALID;
+    if (n_pairs > 0 && (!x1 || !x2 || !d1 || !d2 || !models || !stats || !masks))
+        return fail(ctx, RP_ERR_INVALID, "null data pointer");
+    return estimate_impl(ctx, variant, n_pairs, offsets, x1, x2, d1, d2, cams, opt, models, stats, masks, false,
+                         stream ? (cudaStream_t)stream : ctx->stream);
+}
+
+int rp_last_timing(const rp_ctx *ctx, double *ms11, int64_t *counters4) {
+    if (!ctx) return RP_ERR_INVALID;
+    if (ms11) memcpy(ms11, ctx->last_ms, sizeof ctx->last_ms);
+    if (counters4) memcpy(counters4, ctx->last_cnt, sizeof ctx->last_cnt);
+    return RP_OK;
+}
+
+// ---- stage entry points -----------------------------------------------------------------------
+int rp_sample_batch(rp_ctx *ctx, int64_t n, uint64_t seed, int64_t iters, int32_t *samples) {
+    if (!ctx || !samples || n < 3 || iters < 0) return fail(ctx, RP_ERR_INVALID, "bad argument");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    DevBuf *B = ctx->buf;
+    CK(B[B_PAIRS].reserve(sizeof(PairParams)));
+    CK(B[B_SAMPLES].reserve(sizeof(int) * 3 * (size_t)std::max<int64_t>(iters, 1)));
+    PairParams pp;
+    memset(&pp, 0, sizeof pp);
+    pp.n = (int)n; pp.valid = 1;
+    CK(cudaMemcpyAsync(B[B_PAIRS].p, &pp, sizeof pp, cudaMemcpyHostToDevice, st));
+    if (iters > 0) {
+        sample_kernel<<<1, 32, 0, st>>>(1, (int)iters, B[B_PAIRS].as<PairParams>(), seed, B[B_SAMPLES].as<int>());
+        LAUNCHED();
+        CK(cudaMemcpyAsync(samples, B[B_SAMPLES].p, sizeof(int) * 3 * (size_t)iters, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    return RP_OK;
+}
+
+int rp_solve_batch(rp_ctx *ctx, int variant, int64_t n, const double *x1h, const double *x2h, const double *d1,
+                   const double *d2, rp_model *models, int32_t *counts) {
+    if (!ctx || variant < 0 || variant > 3 || n < 0 || (n > 0 && (!x1h || !x2h || !d1 || !d2 || !models || !counts)))
+        return fail(ctx, RP_ERR_INVALID, "bad argument");
+    if (n == 0) return RP_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    DevBuf *B = ctx->buf;
+    CK(B[B_IN_X1].reserve(72 * (size_t)n)); CK(B[B_IN_X2].reserve(72 * (size_t)n));
+    CK(B[B_IN_D1].reserve(24 * (size_t)n)); CK(B[B_IN_D2].reserve(24 * (size_t)n));
+    CK(B[B_MODELS].reserve(sizeof(Model) * 4 * (size_t)n)); CK(B[B_COUNT].reserve(sizeof(int) * (size_t)n));
+    CK(cudaMemcpyAsync(B[B_IN_X1].p, x1h, 72 * (size_t)n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(B[B_IN_X2].p, x2h, 72 * (size_t)n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(B[B_IN_D1].p, d1, 24 * (size_t)n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(B[B_IN_D2].p, d2, 24 * (size_t)n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(B[B_MODELS].p, 0, sizeof(Model) * 4 * (size_t)n, st));
+    solve_problems_kernel<<<cdiv(n, 128), 128, 0, st>>>(variant, n, B[B_IN_X1].as<double>(), B[B_IN_X2].as<double>(),
+                                                       B[B_IN_D1].as<double>(), B[B_IN_D2].as<double>(),
+                                                       B[B_MODELS].as<Model>(), B[B_COUNT].as<int>());
+    LAUNCHED();
+    CK(cudaMemcpyAsync(models, B[B_MODELS].p, sizeof(Model) * 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(counts, B[B_COUNT].p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return RP_OK;
+}
+
+static int stage_pair(rp_ctx *ctx, int64_t n_points, const double *x1, const double *x2, double sq_thr, cudaStream_t st) {
+    DevBuf *B = ctx->buf;
+    const size_t nn = (size_t)std::max<int64_t>(n_points, 1);
+    CK(B[B_PAIRS].reserve(sizeof(PairParams)));
+    CK(B[B_PTS64].reserve(sizeof(Pt64) * nn)); CK(B[B_PTS32].reserve(sizeof(float4) * nn)); CK(B[B_BEAR].reserve(sizeof(Bear) * nn));
+    CK(B[B_IN_X1].reserve(16 * nn)); CK(B[B_IN_X2].reserve(16 * nn));
+    CK(cudaMemcpyAsync(B[B_IN_X1].p, x1, 16 * (size_t)n_points, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(B[B_IN_X2].p, x2, 16 * (size_t)n_points, cudaMemcpyHostToDevice, st));
+    stage_points_kernel<<<1, 32, 0, st>>>((int)n_points, B[B_IN_X1].as<double>(), B[B_IN_X2].as<double>(), sq_thr,
+                                         B[B_PTS64].as<Pt64>(), B[B_PTS32].as<float4>(), B[B_BEAR].as<Bear>(),
+                                         B[B_PAIRS].as<PairParams>());
+    LAUNCHED();
+    return RP_OK;
+}
+
+int rp_score_batch(rp_ctx *ctx, int variant, int64_t n_models, const rp_model *models, int64_t n_points,
+                   const double *x1, const double *x2, double sq_threshold, double *scores, int64_t *counts,
+                   uint8_t *masks) {
+    if (!ctx || variant < 0 || variant > 3 || n_models < 0 || n_points < 0 ||
+        (n_models > 0 && (!models || !scores || !counts)) || (n_points > 0 && (!x1 || !x2)))
+        return fail(ctx, RP_ERR_INVALID, "bad argument");
+    if (n_models == 0) return RP_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    DevBuf *B = ctx->buf;
+    const bool pose = variant == RP_CALIB || variant == RP_CALIB_SHIFT;
+    int rc = stage_pair(ctx, n_points, x1, x2, sq_threshold, st);
+    if (rc) return rc;
+    CK(B[B_MODELS].reserve(sizeof(Model) * (size_t)n_models));
+    CK(B[B_SCORE].reserve(sizeof(double) * (size_t)n_models)); CK(B[B_COUNT].reserve(sizeof(int) * (size_t)n_models));
+    CK(B[B_SEGCNT].reserve(sizeof(int) * 2)); CK(B[B_ITEMPFX].reserve(sizeof(int) * 4)); CK(B[B_SCALARS].reserve(sizeof(Scalars)));
+    Scalars *sc = B[B_SCALARS].as<Scalars>();
+    CK(cudaMemsetAsync(sc, 0, sizeof(Scalars), st));
+    CK(cudaMemcpyAsync(B[B_MODELS].p, models, sizeof(Model) * (size_t)n_models, cudaMemcpyHostToDevice, st));
+    const int cnt = (int)n_models;
+    CK(cudaMemcpyAsync(B[B_SEGCNT].p, &cnt, sizeof(int), cudaMemcpyHostToDevice, st));
+    build_items_kernel<<<1, 1024, 0, st>>>(1, B[B_SEGCNT].as<int>(), B[B_ITEMPFX].as<int>(), &sc->n_items, nullptr);
+    LAUNCHED();
+    ScoreArgs a;
+    a.n_groups = 1; a.grp_stride = 0; a.grp_per_pair = 1; a.grp_cnt = B[B_SEGCNT].as<int>();
+    a.item_prefix = B[B_ITEMPFX].as<int>(); a.n_items = &sc->n_items; a.pairs = B[B_PAIRS].as<PairParams>();
+    a.models = B[B_MODELS].as<Model>(); a.pts32 = B[B_PTS32].as<float4>(); a.pts64 = B[B_PTS64].as<Pt64>();
+    a.bear = B[B_BEAR].as<Bear>(); a.score = B[B_SCORE].as<double>(); a.count = B[B_COUNT].as<int>();
+    a.mask = nullptr; a.point_scores = nullptr;
+    rc = launch_score(ctx, pose, false, a, st);
+    if (rc) return rc;
+    std::vector<int> h_cnt((size_t)n_models);
+    CK(cudaMemcpyAsync(scores, B[B_SCORE].p, sizeof(double) * (size_t)n_models, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_cnt.data(), B[B_COUNT].p, sizeof(int) * (size_t)n_models, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int64_t i = 0; i < n_models; ++i) counts[i] = h_cnt[(size_t)i];
+    if (masks && n_points > 0) {
+        // I1 get_inliers: one launch per model with the mask variant of the same kernel
+        CK(B[B_MASK].reserve((size_t)n_points)); CK(B[B_TMP0].reserve(sizeof(double))); CK(B[B_TMP1].reserve(sizeof(int)));
+        const int one = 1;
+        CK(cudaMemcpyAsync(B[B_SEGCNT].p, &one, sizeof(int), cudaMemcpyHostToDevice, st));
+        build_items_kernel<<<1, 1024, 0, st>>>(1, B[B_SEGCNT].as<int>(), B[B_ITEMPFX].as<int>(), &sc->n_items, nullptr);
+        LAUNCHED();
+        for (int64_t i = 0; i < n_models; ++i) {
+            CK(cudaMemsetAsync(B[B_MASK].p, 0, (size_t)n_points, st));
+            ScoreArgs m = a;
+            m.models = B[B_MODELS].as<Model>() + i; m.score = B[B_TMP0].as<double>(); m.count = B[B_TMP1].as<int>();
+            m.mask = B[B_MASK].as<unsigned char>();
+            rc = launch_score(ctx, pose, true, m, st);
+            if (rc) return rc;
+            CK(cudaMemcpyAsync(masks + i * n_points, B[B_MASK].p, (size_t)n_points, cudaMemcpyDeviceToHost, st));
+        }
+        CK(cudaStreamSynchronize(st));
+    }
+    return RP_OK;
+}
+
+int rp_refine_batch(rp_ctx *ctx, int variant, int64_t n_models, rp_model *models, int64_t n_points, const double *x1,
+                    const double *x2, const double *d1, const double *d2, const uint8_t *mask, double scale_reproj,
+                    double weight_sampson, const rp_bundle_options *opt, rp_bundle_stats *stats) {
+    if (!ctx || variant < 0 || variant > 3 || n_models < 0 || n_points < 0 || !opt ||
+        (n_models > 0 && !models) || (n_points > 0 && (!x1 || !x2 || !d1 || !d2)))
+        return fail(ctx, RP_ERR_INVALID, "bad argument");
+    if (n_models == 0) return RP_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    DevBuf *B = ctx->buf;
+    int rc = stage_pair(ctx, n_points, x1, x2, 1.0, st);
+    if (rc) return rc;
+    const size_t nn = (size_t)std::max<int64_t>(n_points, 1);
+    CK(B[B_IN_D1].reserve(8 * nn)); CK(B[B_IN_D2].reserve(8 * nn)); CK(B[B_MASK].reserve(nn));
+    CK(B[B_MODELS].reserve(sizeof(Model) * (size_t)n_models)); CK(B[B_SCALARS].reserve(sizeof(Scalars)));
+    CK(B[B_TMP2].reserve(sizeof(rp_bundle_stats) * (size_t)n_models));
+    CK(cudaMemcpyAsync(B[B_IN_D1].p, d1, 8 * (size_t)n_points, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(B[B_IN_D2].p, d2, 8 * (size_t)n_points, cudaMemcpyHostToDevice, st));
+    if (mask) CK(cudaMemcpyAsync(B[B_MASK].p, mask, (size_t)n_points, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(B[B_MODELS].p, models, sizeof(Model) * (size_t)n_models, cudaMemcpyHostToDevice, st));
+    Scalars h;
+    memset(&h, 0, sizeof h);
+    h.n_prob = (int)n_models;
+    Scalars *sc = B[B_SCALARS].as<Scalars>();
+    CK(cudaMemcpyAsync(sc, &h, sizeof h, cudaMemcpyHostToDevice, st));
+    LMArgs la;
+    memset(&la, 0, sizeof la);
+    la.prob_list = nullptr; la.n_prob = &sc->n_prob; la.prob_per_pair = 1 << 30;  // every problem -> pair 0
+    la.pairs = B[B_PAIRS].as<PairParams>(); la.pts64 = B[B_PTS64].as<Pt64>();
+    la.d1 = B[B_IN_D1].as<double>(); la.d2 = B[B_IN_D2].as<double>();
+    la.mask = mask ? B[B_MASK].as<unsigned char>() : nullptr; la.enable = nullptr;
+    la.models = B[B_MODELS].as<Model>(); la.use_final = 1;
+    la.max_iterations = (int)opt->max_iterations; la.loss_type = opt->loss_type;
+    la.weight_sampson = weight_sampson; la.gradient_tol = opt->gradient_tol; la.step_tol = opt->step_tol;
+    la.initial_lambda = opt->initial_lambda; la.min_lambda = opt->min_lambda; la.max_lambda = opt->max_lambda;
+    la.loss_scale_override = opt->loss_scale; la.scale_reproj_override = scale_reproj;
+    la.stats = B[B_TMP2].as<rp_bundle_stats>(); la.lm_iters = nullptr;
+    rc = launch_lm(ctx, variant, la, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(models, B[B_MODELS].p, sizeof(Model) * (size_t)n_models, cudaMemcpyDeviceToHost, st));
+    if (stats) CK(cudaMemcpyAsync(stats, B[B_TMP2].p, sizeof(rp_bundle_stats) * (size_t)n_models, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return RP_OK;
+}
+
+int rp_measure_pipes(rp_ctx *ctx, double *fp64_tflops, double *fp32_tflops) {
+    if (!ctx) return RP_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    DevBuf *B = ctx->buf;
+    const int blocks = ctx->sms * 8, threads = 256, iters = 1 << 14;
+    CK(B[B_TMP0].reserve(sizeof(double) * (size_t)blocks * threads));
+    cudaEvent_t e0 = ctx->ev[9], e1 = ctx->ev[10];
+    for (int pass = 0; pass < 2; ++pass) {
+        double best = 0.0;
+        for (int rep = 0; rep < 4; ++rep) {
+            CK(cudaEventRecord(e0, st));
+            if (pass == 0) fp64_pipe_kernel<<<blocks, threads, 0, st>>>(B[B_TMP0].as<double>(), iters);
+            else fp32_pipe_kernel<<<blocks, threads, 0, st>>>(B[B_TMP0].as<float>(), iters);
+            LAUNCHED();
+            CK(cudaEventRecord(e1, st));
+            CK(cudaStreamSynchronize(st));
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            const double flops = 2.0 * 8.0 * (double)iters * (double)blocks * threads;
+            if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+        }
+        if (pass == 0 && fp64_tflops) *fp64_tflops = best;
+        if (pass == 1 && fp32_tflops) *fp32_tflops = best;
+    }
+    return RP_OK;
+}
+
+}  // extern "C"

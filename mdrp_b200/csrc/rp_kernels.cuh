@@ -1,0 +1,897 @@
+// rp_kernels.cuh — CUDA kernels of the batched RePoseD LO-RANSAC (sm_100a).
+//
+// Pipeline per chunk of image pairs (SURVEY.md §3.2 restated as a parallel schedule, §7 step 4):
+//   prepare  -> normalised points (FP64 + FP32 copies), unit bearings, per-pair thresholds
+//   sample   -> RandomSampler::generate_sample for every iteration (warp per pair, speculative)
+//   solve    -> minimal solvers, one thread per RANSAC iteration, ordered per-segment compaction
+//   score    -> hypotheses x correspondences MSAC (the dominant kernel)
+//   scan     -> sequential-semantics prefix scan: which minimal models trigger LO / become best
+//   lm       -> batched Levenberg-Marquardt (LO, final LO, final refinement), block per problem
+//   merge    -> replay of score_models()/ransac() bookkeeping in trigger order
+// HBM layout: every per-hypothesis array is indexed by a "slot"; the minimal models of
+// (pair p, iteration segment s) own slots [(p*nseg+s)*4*SEG, +count) in iteration order.
+#pragma once
+#include <cuda_runtime.h>
+#include "rp_solvers.cuh"
+#include "rp_score.cuh"
+#include "rp_lm.cuh"
+
+namespace rp {
+
+constexpr int SEG = 1024;          // RANSAC iterations per solve block (4 rounds of 256 threads)
+constexpr int SOLVE_THREADS = 256;
+constexpr int HB = 128;            // hypotheses per scoring work item
+constexpr int SCORE_THREADS = 256;
+constexpr int SCORE_WARPS = SCORE_THREADS / 32;
+constexpr int PT = 4;              // correspondences per thread per slice
+constexpr int EV = 128;            // trigger events kept per pair
+constexpr int LM_THREADS = 128;
+constexpr int LM_WARPS = LM_THREADS / 32;
+
+struct PairParams {
+    long long off;        // first correspondence of this pair in the packed arrays
+    int n;                // number of correspondences
+    int valid;            // n >= 3
+    double thr;           // max_epipolar_error in normalised units
+    double sq_thr;        // thr^2
+    double scale_reproj;  // (thr_epi/thr_reproj)^2 or 0
+    double lo_loss_scale; // loss_scale of the LO refinement (see varying-focal note in DESIGN.md)
+    double final_loss_scale;
+    double nscale;        // focal variants: normalize_points scale (1 for calibrated)
+    double Mmax, mmax;    // bounds used by the FP32 filter
+};
+
+struct alignas(16) Pt64 {
+    double x1_0, x1_1, x2_0, x2_1;
+};
+struct Bear {
+    double b1x, b1y, b1z, b2x, b2y, b2z;
+};
+
+// ---------------------------------------------------------------------------------------------
+// warp helpers
+RP_D double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+RP_D double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// prepare: P1/P2 pre-processing (estimate_monodepth_relative_pose so@0x224170: Camera::unproject,
+// threshold scaling by 0.5(1/f1+1/f2); focal variants so@0x223300/0x223a40: normalize_points
+// so@0x4f6ae0 with a SEQUENTIAL sum in index order, thresholds / loss_scale divided by it).
+// One warp per pair.
+struct PrepareArgs {
+    int variant;
+    int n_pairs;
+    const long long *offsets;  // [n_pairs+1], relative to the chunk
+    const double *x1, *x2;     // [N,2] pixels
+    const double *cams;        // [n_pairs,8] or null
+    double max_epipolar_error, max_reproj_error, loss_scale;
+    Pt64 *pts64;
+    float4 *pts32;
+    Bear *bear;
+    PairParams *pairs;
+};
+
+__global__ void prepare_kernel(PrepareArgs a) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= a.n_pairs) return;
+    const long long off = a.offsets[warp];
+    const int n = (int)(a.offsets[warp + 1] - off);
+    const bool pose = a.variant == RP_CALIB || a.variant == RP_CALIB_SHIFT;
+    PairParams pp;
+    pp.off = off;
+    pp.n = n;
+    pp.valid = n >= 3;
+    pp.nscale = 1.0;
+    double Mmax = 0.0, mmax = 0.0;
+    if (pose) {
+        const double *c = a.cams + 8 * (long long)warp;
+        const double fx1 = c[0], fy1 = c[1], cx1 = c[2], cy1 = c[3], fx2 = c[4], fy2 = c[5], cx2 = c[6], cy2 = c[7];
+        const double fo1 = 0.5 * (fx1 + fy1), fo2 = 0.5 * (fx2 + fy2);
+        const double k = 0.5 * (1.0 / fo1 + 1.0 / fo2);
+        pp.thr = a.max_epipolar_error * k;
+        const double rep = a.max_reproj_error * k;
+        pp.scale_reproj = rep > 0.0 ? (pp.thr * pp.thr) / (rep * rep) : 0.0;
+        pp.lo_loss_scale = pp.thr;
+        pp.final_loss_scale = 0.5 * pp.thr;  // user loss_scale is overwritten for this variant
+        for (int k0 = lane; k0 < n; k0 += 32) {
+            const long long g = off + k0;
+            Pt64 p;
+            p.x1_0 = (a.x1[2 * g] - cx1) / fx1;
+            p.x1_1 = (a.x1[2 * g + 1] - cy1) / fy1;
+            p.x2_0 = (a.x2[2 * g] - cx2) / fx2;
+            p.x2_1 = (a.x2[2 * g + 1] - cy2) / fy2;
+            a.pts64[g] = p;
+            a.pts32[g] = make_float4((float)p.x1_0, (float)p.x1_1, (float)p.x2_0, (float)p.x2_1);
+            const V3 b1 = bearing(p.x1_0, p.x1_1), b2 = bearing(p.x2_0, p.x2_1);
+            Bear b;
+            b.b1x = b1.x; b.b1y = b1.y; b.b1z = b1.z; b.b2x = b2.x; b.b2y = b2.y; b.b2z = b2.z;
+            a.bear[g] = b;
+            const double m1 = fabs(p.x1_0) + fabs(p.x1_1) + 1.0, m2 = fabs(p.x2_0) + fabs(p.x2_1) + 1.0;
+            Mmax = fmax(Mmax, m1 * m2);
+            mmax = fmax(mmax, fmax(m1, m2));
+        }
+    } else {
+        // sequential sum s += |x1_k|; s += |x2_k| in index order: lanes compute the norms of 32
+        // correspondences at a time, lane 0 adds them in order
+        double s = 0.0;
+        for (int base = 0; base < n; base += 32) {
+            const int k0 = base + lane;
+            double n1 = 0.0, n2 = 0.0;
+            if (k0 < n) {
+                const long long g = off + k0;
+                const double ax = a.x1[2 * g], ay = a.x1[2 * g + 1], bx = a.x2[2 * g], by = a.x2[2 * g + 1];
+                n1 = sqrt(ax * ax + ay * ay);
+                n2 = sqrt(bx * bx + by * by);
+            }
+            const int cntv = min(32, n - base);
+            for (int l = 0; l < cntv; ++l) {
+                const double v1 = __shfl_sync(0xffffffffu, n1, l);
+                const double v2 = __shfl_sync(0xffffffffu, n2, l);
+                s += v1;
+                s += v2;
+            }
+        }
+        const double nscale = s / (sqrt(2.0) * (double)n);
+        pp.nscale = nscale;
+        pp.thr = a.max_epipolar_error / nscale;
+        const double rep = a.max_reproj_error / nscale;
+        pp.scale_reproj = rep > 0.0 ? (pp.thr * pp.thr) / (rep * rep) : 0.0;
+        // VaryingFocalMonodepthPoseEstimator::refine_model so@0x4fb0a0 leaves loss_scale at the
+        // BundleOptions default 1.0; the shared-focal estimator so@0x4fad60 uses the threshold
+        pp.lo_loss_scale = a.variant == RP_VARYING ? 1.0 : pp.thr;
+        pp.final_loss_scale = a.loss_scale / nscale;
+        for (int k0 = lane; k0 < n; k0 += 32) {
+            const long long g = off + k0;
+            Pt64 p;
+            p.x1_0 = a.x1[2 * g] / nscale;
+            p.x1_1 = a.x1[2 * g + 1] / nscale;
+            p.x2_0 = a.x2[2 * g] / nscale;
+            p.x2_1 = a.x2[2 * g + 1] / nscale;
+            a.pts64[g] = p;
+            a.pts32[g] = make_float4((float)p.x1_0, (float)p.x1_1, (float)p.x2_0, (float)p.x2_1);
+            const double m1 = fabs(p.x1_0) + fabs(p.x1_1) + 1.0, m2 = fabs(p.x2_0) + fabs(p.x2_1) + 1.0;
+            Mmax = fmax(Mmax, m1 * m2);
+            mmax = fmax(mmax, fmax(m1, m2));
+        }
+    }
+    Mmax = warp_max(Mmax);
+    mmax = warp_max(mmax);
+    if (lane == 0) {
+        pp.sq_thr = pp.thr * pp.thr;
+        pp.Mmax = Mmax * 1.000001;  // cover the FP32 rounding of the inputs themselves
+        pp.mmax = mmax * 1.000001;
+        a.pairs[warp] = pp;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// sample: R2 (RandomSampler::generate_sample so@0x4f8970 -> draw_sample so@0x4f87f0 -> random_int
+// so@0x4f87a0).  SplitMix64 is counter based, but the rejection of duplicate indices makes the
+// number of draws per sample data dependent.  A warp speculates 32 iterations at 3 draws each;
+// the first lane that sees a duplicate replays its sample sequentially and re-bases the rest.
+RP_D uint32_t splitmix_int(uint64_t state_after_increment) {
+    uint64_t z = state_after_increment;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    z = z ^ (z >> 31);
+    return (uint32_t)z;
+}
+RP_D uint32_t draw_index(uint64_t &state, uint64_t n) {
+    state += 0x9e3779b97f4a7c15ULL;
+    const int32_t v = (int32_t)splitmix_int(state);
+    return (uint32_t)((uint64_t)(int64_t)v % n);  // (size_t)(int64)ret % N as the reference does
+}
+
+__global__ void sample_kernel(int n_pairs, int iters, const PairParams *pairs, uint64_t seed, int *samples) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= n_pairs) return;
+    const PairParams pp = pairs[warp];
+    if (!pp.valid) return;
+    const uint64_t n = (uint64_t)pp.n;
+    const uint64_t G = 0x9e3779b97f4a7c15ULL;
+    int *out = samples + (size_t)warp * iters * 3;
+    uint64_t base = seed;
+    for (int it0 = 0; it0 < iters; it0 += 32) {
+        const int group = min(32, iters - it0);
+        int done = 0;
+        while (done < group) {
+            uint64_t st = base + 3ULL * G * (uint64_t)(lane >= done ? lane - done : 0);
+            const uint64_t st0 = st;
+            const uint32_t i0 = draw_index(st, n), i1 = draw_index(st, n), i2 = draw_index(st, n);
+            const bool active = lane >= done && lane < group;
+            const bool dup = active && (i1 == i0 || i2 == i0 || i2 == i1);
+            const unsigned m = __ballot_sync(0xffffffffu, dup);
+            const int first = m ? (__ffs(m) - 1) : group;
+            if (active && lane < first) {
+                int *o = out + (size_t)(it0 + lane) * 3;
+                o[0] = (int)i0; o[1] = (int)i1; o[2] = (int)i2;
+            }
+            if (first < group) {
+                uint64_t s2 = st0;
+                if (lane == first) {
+                    uint32_t s[3];
+                    for (int i = 0; i < 3; ++i) {
+                        bool ok = false;
+                        while (!ok) {
+                            s[i] = draw_index(s2, n);
+                            ok = true;
+                            for (int j = 0; j < i; ++j) if (s[i] == s[j]) ok = false;
+                        }
+                    }
+                    int *o = out + (size_t)(it0 + lane) * 3;
+                    o[0] = (int)s[0]; o[1] = (int)s[1]; o[2] = (int)s[2];
+                }
+                base = __shfl_sync(0xffffffffu, s2, first);
+                done = first + 1;
+            } else {
+                base = base + 3ULL * G * (uint64_t)(group - done);
+                done = group;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// solve: one thread per RANSAC iteration, block = (segment of SEG iterations, pair).  Solutions
+// are compacted in (iteration, solution) order with a block-wide exclusive scan per round.
+struct SolveArgs {
+    int variant, iters, nseg;
+    const PairParams *pairs;
+    const int *samples;
+    const Pt64 *pts64;
+    const double *d1, *d2;
+    Model *models;   // slots
+    int *hyp_iter;   // slots
+    int *seg_count;  // [n_pairs*nseg]
+};
+
+template <int VARIANT>
+__global__ void __launch_bounds__(SOLVE_THREADS) solve_kernel(SolveArgs a) {
+    const int seg = blockIdx.x, pair = blockIdx.y;
+    const PairParams pp = a.pairs[pair];
+    __shared__ int warp_tot[SOLVE_THREADS / 32];
+    __shared__ int running_s;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const size_t slot0 = ((size_t)pair * a.nseg + seg) * (size_t)(4 * SEG);
+    if (tid == 0) running_s = 0;
+    __syncthreads();
+    if (!pp.valid) {
+        if (tid == 0) a.seg_count[pair * a.nseg + seg] = 0;
+        return;
+    }
+    for (int round = 0; round < SEG / SOLVE_THREADS; ++round) {
+        const int it = seg * SEG + round * SOLVE_THREADS + tid;
+        ModelSet ms;
+        ms.n = 0;
+        if (it < a.iters) {
+            const int *s = a.samples + ((size_t)pair * a.iters + it) * 3;
+            Triplet t;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const long long g = pp.off + s[i];
+                const Pt64 p = a.pts64[g];
+                t.p1[i] = v3(p.x1_0, p.x1_1, 1.0);
+                t.p2[i] = v3(p.x2_0, p.x2_1, 1.0);
+                t.d1[i] = a.d1[g];
+                t.d2[i] = a.d2[g];
+            }
+            if (VARIANT == RP_CALIB) solve_calib_scale(t, ms);
+            else if (VARIANT == RP_CALIB_SHIFT) solve_calib_shift(t, ms);
+            else if (VARIANT == RP_SHARED) solve_shared_focal(t, ms);
+            else solve_varying_focal(t, ms);
+        }
+        // exclusive scan of ms.n over the block, in thread (= iteration) order
+        int incl = ms.n;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) warp_tot[wid] = incl;
+        __syncthreads();
+        int wbase = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < SOLVE_THREADS / 32; ++w) {
+            const int v = warp_tot[w];
+            if (w < wid) wbase += v;
+            total += v;
+        }
+        const int running = running_s;
+        const size_t dst = slot0 + running + wbase + (incl - ms.n);
+        if (ms.n > 0) { a.models[dst] = ms.m[0]; a.hyp_iter[dst] = it; }
+        if (ms.n > 1) { a.models[dst + 1] = ms.m[1]; a.hyp_iter[dst + 1] = it; }
+        if (ms.n > 2) { a.models[dst + 2] = ms.m[2]; a.hyp_iter[dst + 2] = it; }
+        if (ms.n > 3) { a.models[dst + 3] = ms.m[3]; a.hyp_iter[dst + 3] = it; }
+        __syncthreads();
+        if (tid == 0) running_s = running + total;
+        __syncthreads();
+    }
+    if (tid == 0) a.seg_count[pair * a.nseg + seg] = running_s;
+}
+
+// stage entry point helper: independent triplets, one thread each (rp_solve_batch)
+__global__ void solve_problems_kernel(int variant, long long n, const double *x1h, const double *x2h,
+                                      const double *d1, const double *d2, Model *models, int *counts) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Triplet t;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        t.p1[k] = v3(x1h[9 * i + 3 * k], x1h[9 * i + 3 * k + 1], x1h[9 * i + 3 * k + 2]);
+        t.p2[k] = v3(x2h[9 * i + 3 * k], x2h[9 * i + 3 * k + 1], x2h[9 * i + 3 * k + 2]);
+        t.d1[k] = d1[3 * i + k];
+        t.d2[k] = d2[3 * i + k];
+    }
+    ModelSet ms;
+    solve_minimal(variant, t, ms);
+    counts[i] = ms.n;
+    if (ms.n > 0) models[4 * i] = ms.m[0];
+    if (ms.n > 1) models[4 * i + 1] = ms.m[1];
+    if (ms.n > 2) models[4 * i + 2] = ms.m[2];
+    if (ms.n > 3) models[4 * i + 3] = ms.m[3];
+}
+
+// ---------------------------------------------------------------------------------------------
+// work items of the scoring kernel: group e (a (pair, segment), or a pair) owns grp_cnt[e] models
+// at slots [e*grp_stride, …); item = HB consecutive models of one group.  Exclusive scan of
+// ceil(cnt/HB) over the groups; single block.
+__global__ void build_items_kernel(int n_groups, const int *grp_cnt, int *item_prefix, int *n_items,
+                                   long long *n_hyp_total) {
+    __shared__ int sh[1024];
+    __shared__ int carry;
+    __shared__ long long hyps;
+    if (threadIdx.x == 0) { carry = 0; hyps = 0; }
+    __syncthreads();
+    for (int base = 0; base < n_groups; base += 1024) {
+        const int e = base + threadIdx.x;
+        const int c = e < n_groups ? grp_cnt[e] : 0;
+        const int v = (c + HB - 1) / HB;
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            const int t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+            __syncthreads();
+            sh[threadIdx.x] += t;
+            __syncthreads();
+        }
+        if (e < n_groups) item_prefix[e] = carry + sh[threadIdx.x] - v;
+        if (c) atomicAdd((unsigned long long *)&hyps, (unsigned long long)c);
+        __syncthreads();
+        if (threadIdx.x == 0) carry += sh[1023];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        item_prefix[n_groups] = carry;
+        *n_items = carry;
+        if (n_hyp_total) *n_hyp_total = hyps;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// score: SC / SF / I1.  Block = one work item = up to HB models of one pair against all of the
+// pair's correspondences.  Lanes are correspondences (coalesced FP32 float4 loads, PT per thread),
+// the models' E / F matrices are staged in shared memory and broadcast.  Tier 0 is the FP32
+// filter, tier 1 the exact FP64 test (rp_score.cuh).  Inlier counts are exact; the MSAC score is
+// thr^2 (N - count) + sum of inlier r^2 with a fixed (deterministic) summation order.
+struct ScoreArgs {
+    int n_groups, grp_stride, grp_per_pair;
+    const int *grp_cnt;
+    const int *item_prefix;  // [n_groups+1]
+    const int *n_items;
+    const PairParams *pairs;
+    const Model *models;     // slots
+    const float4 *pts32;
+    const Pt64 *pts64;
+    const Bear *bear;
+    double *score;           // slots
+    int *count;              // slots
+    unsigned char *mask;     // optional, per correspondence; only with one model per pair
+    unsigned long long *point_scores;  // optional counter
+};
+
+struct HypConst {
+    M3 E;      // essential (pose variants) or fundamental matrix
+    Quat q;
+    V3 t;
+};
+
+template <bool POSE, bool MASK>
+__global__ void __launch_bounds__(SCORE_THREADS) score_kernel(ScoreArgs a) {
+    __shared__ HypConst hc[HB];
+    __shared__ Filter32 hf[HB];
+    __shared__ double psum[HB][SCORE_WARPS];
+    __shared__ int pcnt[HB][SCORE_WARPS];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int n_items = *a.n_items;
+    const int per = (n_items + gridDim.x - 1) / gridDim.x;
+    const int item_end = min(n_items, (int)(blockIdx.x + 1) * per);
+    for (int item = blockIdx.x * per; item < item_end; ++item) {
+        // group of this item: last e with item_prefix[e] <= item
+        int lo = 0, hi = a.n_groups;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (a.item_prefix[mid] <= item) lo = mid; else hi = mid;
+        }
+        const int e = lo;
+        const int pair = e / a.grp_per_pair;
+        const int h0 = (item - a.item_prefix[e]) * HB;
+        const int nh = min(HB, a.grp_cnt[e] - h0);
+        const size_t slot0 = (size_t)e * a.grp_stride + h0;
+        const PairParams pp = a.pairs[pair];
+        __syncthreads();  // previous item's shared state fully consumed
+        if (tid < nh) {
+            const Model m = a.models[slot0 + tid];
+            HypConst c;
+            c.E = POSE ? essential_from_motion(m.q, m.t) : fundamental_from_model(m);
+            c.q = m.q;
+            c.t = m.t;
+            hc[tid] = c;
+            hf[tid] = make_filter32(c.E, pp.thr, pp.Mmax, pp.mmax);
+        }
+        for (int i = tid; i < HB * SCORE_WARPS; i += SCORE_THREADS) {
+            (&psum[0][0])[i] = 0.0;
+            (&pcnt[0][0])[i] = 0;
+        }
+        __syncthreads();
+        const int n = pp.n;
+        const double sq_thr = pp.sq_thr;
+        const int slice_pts = 32 * PT;
+        const int n_slices = (n + slice_pts - 1) / slice_pts;
+        for (int sl = wid; sl < n_slices; sl += SCORE_WARPS) {
+            float4 p[PT];
+            bool valid[PT];
+#pragma unroll
+            for (int j = 0; j < PT; ++j) {
+                const int k = sl * slice_pts + j * 32 + lane;
+                valid[j] = k < n;
+                p[j] = valid[j] ? a.pts32[pp.off + k] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            for (int h = 0; h < nh; ++h) {
+                const Filter32 f = hf[h];
+                unsigned cand = 0;
+#pragma unroll
+                for (int j = 0; j < PT; ++j)
+                    if (valid[j] && !certain_outlier32(f, p[j].x, p[j].y, p[j].z, p[j].w)) cand |= 1u << j;
+                if (__any_sync(0xffffffffu, cand != 0)) {
+                    int c = 0;
+                    double s = 0.0;
+                    if (cand) {
+                        const M3 E = hc[h].E;
+#pragma unroll
+                        for (int j = 0; j < PT; ++j) {
+                            if (!(cand >> j & 1)) continue;
+                            const long long g = pp.off + sl * slice_pts + j * 32 + lane;
+                            const Pt64 q64 = a.pts64[g];
+                            const double r2 = sampson_r2_exact(E, q64.x1_0, q64.x1_1, q64.x2_0, q64.x2_1);
+                            bool inl = r2 < sq_thr;
+                            if (POSE && inl) {
+                                const Bear b = a.bear[g];
+                                inl = cheirality_exact(hc[h].q, hc[h].t, v3(b.b1x, b.b1y, b.b1z), v3(b.b2x, b.b2y, b.b2z));
+                            }
+                            if (inl) { ++c; s += r2; }
+                            if (MASK && inl) a.mask[g] = 1;
+                        }
+                    }
+                    const unsigned anyinl = __ballot_sync(0xffffffffu, c != 0);
+                    if (anyinl) {
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            c += __shfl_xor_sync(0xffffffffu, c, o);
+                            s += __shfl_xor_sync(0xffffffffu, s, o);
+                        }
+                        if (lane == 0) { pcnt[h][wid] += c; psum[h][wid] += s; }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (tid < nh) {
+            int c = 0;
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < SCORE_WARPS; ++w) { c += pcnt[tid][w]; s += psum[tid][w]; }
+            a.count[slot0 + tid] = c;
+            a.score[slot0 + tid] = s + sq_thr * (double)(n - c);
+        }
+        if (a.point_scores && tid == 0) atomicAdd(a.point_scores, (unsigned long long)nh * (unsigned long long)n);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// scan: the part of score_models() so@0x22ebc0 that does not depend on LO results.  A minimal
+// model "triggers" when it has more inliers than every earlier minimal model or a lower MSAC
+// score than every earlier one (running max / running min, strict).  One warp per pair walks the
+// pair's slots in order and emits the triggering slots.
+struct ScanArgs {
+    int n_pairs, nseg;
+    const int *seg_count;
+    const double *score;
+    const int *count;
+    int *events;      // [n_pairs*EV] slot of each trigger, in order
+    int *n_events;    // [n_pairs]
+    int *overflow;
+};
+
+__global__ void scan_kernel(ScanArgs a) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= a.n_pairs) return;
+    long long best_cnt = 0;  // best_minimal_inlier_count starts at 0
+    double best_score = DBL_MAX;
+    int nev = 0;
+    for (int seg = 0; seg < a.nseg; ++seg) {
+        const int e = warp * a.nseg + seg;
+        const int cnt = a.seg_count[e];
+        const size_t slot0 = (size_t)e * (4 * SEG);
+        for (int base = 0; base < cnt; base += 32) {
+            const int h = base + lane;
+            const bool v = h < cnt;
+            const long long c = v ? (long long)a.count[slot0 + h] : -1;
+            double s = v ? a.score[slot0 + h] : DBL_MAX;
+            if (s != s) s = DBL_MAX;  // NaN scores never compare "less" in the reference either
+            // exclusive running max / min within the warp
+            long long cmax = c;
+            double smin = s;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const long long c2 = __shfl_up_sync(0xffffffffu, cmax, o);
+                const double s2 = __shfl_up_sync(0xffffffffu, smin, o);
+                if (lane >= o) { cmax = max(cmax, c2); smin = fmin(smin, s2); }
+            }
+            long long cprev = __shfl_up_sync(0xffffffffu, cmax, 1);
+            double sprev = __shfl_up_sync(0xffffffffu, smin, 1);
+            if (lane == 0) { cprev = best_cnt; sprev = best_score; }
+            else { cprev = max(cprev, best_cnt); sprev = fmin(sprev, best_score); }
+            const bool trig = v && (c > cprev || s < sprev);
+            const unsigned m = __ballot_sync(0xffffffffu, trig);
+            if (trig) {
+                const int pos = nev + __popc(m & ((1u << lane) - 1));
+                if (pos < EV) a.events[warp * EV + pos] = (int)(slot0 + h - (size_t)warp * a.nseg * (4 * SEG));
+                else *a.overflow = 1;
+            }
+            nev += __popc(m);
+            best_cnt = max(best_cnt, __shfl_sync(0xffffffffu, cmax, 31));
+            best_score = fmin(best_score, __shfl_sync(0xffffffffu, smin, 31));
+        }
+    }
+    if (lane == 0) a.n_events[warp] = min(nev, EV);
+}
+
+// LO problem list: the LO of an iteration starts from the LAST triggering model of that
+// iteration (models[best_model_ind], so@0x22ed60).  Thread per pair.
+struct LoPrepArgs {
+    int n_pairs, nseg;
+    const int *events, *n_events;
+    const int *hyp_iter;
+    const Model *models;
+    Model *lo_models;   // [n_pairs*EV]
+    int *lo_of_event;   // [n_pairs*EV] index of the LO problem started by this event or -1
+    int *lo_count;      // [n_pairs]
+    int *prob_list;     // compact list of lo_models indices
+    int *n_prob;
+};
+
+__global__ void lo_prepare_kernel(LoPrepArgs a) {
+    const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pair >= a.n_pairs) return;
+    const size_t pslot = (size_t)pair * a.nseg * (4 * SEG);
+    const int nev = a.n_events[pair];
+    int nlo = 0;
+    for (int i = 0; i < nev; ++i) {
+        const int ev = a.events[pair * EV + i];
+        const int it = a.hyp_iter[pslot + ev];
+        const bool last = (i + 1 == nev) || a.hyp_iter[pslot + a.events[pair * EV + i + 1]] != it;
+        if (last) {
+            a.lo_models[pair * EV + nlo] = a.models[pslot + ev];
+            a.lo_of_event[pair * EV + i] = nlo;
+            ++nlo;
+        } else {
+            a.lo_of_event[pair * EV + i] = -1;
+        }
+    }
+    a.lo_count[pair] = nlo;
+    if (nlo) {
+        const int p0 = atomicAdd(a.n_prob, nlo);
+        for (int j = 0; j < nlo; ++j) a.prob_list[p0 + j] = pair * EV + j;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// lm: lm_impl<> of PoseLib bundle.cc, one block per problem (persistent over the problem list).
+// JtJ + lambda I (lower LLT), accept when the cost decreases (lambda /= 10, recompute J) else
+// lambda *= 10; stop on |J^T r| < gradient_tol or |step| < step_tol.
+struct LMArgs {
+    const int *prob_list;  // indices into models (null: identity)
+    const int *n_prob;
+    int prob_per_pair;     // pair = index / prob_per_pair
+    const PairParams *pairs;
+    const Pt64 *pts64;
+    const double *d1, *d2;
+    const unsigned char *mask;   // optional per-correspondence subset
+    const int *enable;           // optional per-pair switch (final refinement: num_inliers > 3)
+    Model *models;
+    int use_final;               // 0: LO options (25 its, TRUNCATED, lo_loss_scale); 1: user bundle options
+    int max_iterations, loss_type;
+    double weight_sampson, gradient_tol, step_tol, initial_lambda, min_lambda, max_lambda;
+    double loss_scale_override;  // >0: stage entry point passes its own loss scale / scale_reproj
+    double scale_reproj_override;
+    rp_bundle_stats *stats;      // optional, per problem index
+    unsigned long long *lm_iters;
+};
+
+template <int NP>
+RP_D void warp_reduce_normal(NormalEq<NP> &N) {
+#pragma unroll
+    for (int i = 0; i < NP * (NP + 1) / 2; ++i) N.A[i] = warp_sum(N.A[i]);
+#pragma unroll
+    for (int i = 0; i < NP; ++i) N.g[i] = warp_sum(N.g[i]);
+}
+
+template <int VARIANT, int NP>
+__global__ void __launch_bounds__(LM_THREADS) lm_kernel(LMArgs a) {
+    constexpr int NA = NP * (NP + 1) / 2;
+    __shared__ Model cur, trial;
+    __shared__ double red[LM_WARPS][NA + NP];
+    __shared__ double sA[NA], sg[NP];
+    __shared__ double cred[LM_WARPS];
+    __shared__ int stop_s;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int n_prob = *a.n_prob;
+    for (int pj = blockIdx.x; pj < n_prob; pj += gridDim.x) {
+        const int prob = a.prob_list ? a.prob_list[pj] : pj;
+        const int pair = prob / a.prob_per_pair;
+        const PairParams pp = a.pairs[pair];
+        if (!pp.valid) continue;
+        if (a.enable && !a.enable[pair]) continue;
+        LMParams P;
+        P.weight_sampson = a.weight_sampson;
+        P.scale_reproj = a.scale_reproj_override >= 0.0 ? a.scale_reproj_override : pp.scale_reproj;
+        if (a.use_final) {
+            P.loss_type = a.loss_type;
+            P.loss_scale = a.loss_scale_override > 0.0 ? a.loss_scale_override : pp.final_loss_scale;
+        } else {
+            P.loss_type = RP_LOSS_TRUNCATED;
+            P.loss_scale = pp.lo_loss_scale;
+        }
+        const int max_it = a.use_final ? a.max_iterations : 25;
+        const int n = pp.n;
+        const Pt64 *pts = a.pts64 + pp.off;
+        const double *d1 = a.d1 + pp.off, *d2 = a.d2 + pp.off;
+        const unsigned char *mask = a.mask ? a.mask + pp.off : nullptr;
+        __syncthreads();
+        if (tid == 0) { cur = a.models[prob]; stop_s = 0; }
+        __syncthreads();
+
+        auto block_cost = [&](const Model &m) -> double {
+            const LMFrame F = make_frame(m);
+            double c = 0.0;
+            for (int k = tid; k < n; k += LM_THREADS) {
+                if (mask && !mask[k]) continue;
+                const Pt64 p = pts[k];
+                c += point_cost<VARIANT>(F, P, p.x1_0, p.x1_1, p.x2_0, p.x2_1, d1[k], d2[k]);
+            }
+            c = warp_sum(c);
+            __syncthreads();
+            if (lane == 0) cred[wid] = c;
+            __syncthreads();
+            double tot = 0.0;
+#pragma unroll
+            for (int w = 0; w < LM_WARPS; ++w) tot += cred[w];
+            return tot;
+        };
+
+        double cost = block_cost(cur);
+        const double initial_cost = cost;
+        double lambda = a.initial_lambda;
+        double grad_norm = -1.0, step_norm = -1.0;
+        long long invalid_steps = 0;
+        bool recompute = true;
+        int it = 0;
+        for (; it < max_it; ++it) {
+            if (recompute) {
+                const LMFrame F = make_frame(cur);
+                NormalEq<NP> N;
+                N.clear();
+                for (int k = tid; k < n; k += LM_THREADS) {
+                    if (mask && !mask[k]) continue;
+                    const Pt64 p = pts[k];
+                    point_accumulate<VARIANT, NP>(F, P, p.x1_0, p.x1_1, p.x2_0, p.x2_1, d1[k], d2[k], N);
+                }
+                warp_reduce_normal<NP>(N);
+                if (lane == 0) {
+#pragma unroll
+                    for (int i = 0; i < NA; ++i) red[wid][i] = N.A[i];
+#pragma unroll
+                    for (int i = 0; i < NP; ++i) red[wid][NA + i] = N.g[i];
+                }
+                __syncthreads();
+                if (tid < NA + NP) {
+                    double v = 0.0;
+#pragma unroll
+                    for (int w = 0; w < LM_WARPS; ++w) v += red[w][tid];
+                    if (tid < NA) sA[tid] = v; else sg[tid - NA] = v;
+                }
+                __syncthreads();
+                double g2 = 0.0;
+#pragma unroll
+                for (int i = 0; i < NP; ++i) g2 += sg[i] * sg[i];
+                grad_norm = sqrt(g2);
+                if (grad_norm < a.gradient_tol) break;  // uniform: every thread reads the same sg
+            }
+            if (tid == 0) {
+                double x[NP];
+                llt_solve<NP>(sA, lambda, sg, x);
+                double sn = 0.0;
+#pragma unroll
+                for (int i = 0; i < NP; ++i) { x[i] = -x[i]; sn += x[i] * x[i]; }
+                cred[0] = sqrt(sn);
+                if (sqrt(sn) < a.step_tol) stop_s = 1;
+                else trial = model_step<VARIANT>(cur, x);
+            }
+            __syncthreads();
+            step_norm = cred[0];
+            if (stop_s) break;
+            const double cost_new = block_cost(trial);
+            if (cost_new < cost) {
+                __syncthreads();
+                if (tid == 0) cur = trial;
+                lambda = fmax(a.min_lambda, lambda / 10);
+                cost = cost_new;
+                recompute = true;
+            } else {
+                ++invalid_steps;
+                lambda = fmin(a.max_lambda, lambda * 10);
+                recompute = false;
+            }
+            __syncthreads();
+        }
+        __syncthreads();
+        if (tid == 0) {
+            a.models[prob] = cur;
+            if (a.stats) {
+                rp_bundle_stats s;
+                s.iterations = it; s.initial_cost = initial_cost; s.cost = cost; s.lambda = lambda;
+                s.invalid_steps = invalid_steps; s.step_norm = step_norm; s.grad_norm = grad_norm;
+                a.stats[prob] = s;
+            }
+            if (a.lm_iters) atomicAdd(a.lm_iters, (unsigned long long)it);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// merge: replay of score_models() / ransac() bookkeeping (so@0x22ebc0, so@0x22f030) over the
+// trigger events in order: a triggering minimal model becomes the best model if its score beats
+// stats.model_score; after the last trigger of an iteration the LO result is compared (strict <).
+struct MergeArgs {
+    int n_pairs, nseg, iters;
+    const PairParams *pairs;
+    const int *events, *n_events, *lo_of_event;
+    const double *score;     // minimal slots
+    const int *count;
+    const Model *models;
+    const double *lo_score;  // [n_pairs*EV]
+    const int *lo_count_inl;
+    const Model *lo_models;
+    const int *lo_count;     // number of LO problems per pair
+    Model *best;             // [n_pairs]
+    rp_stats *stats;         // [n_pairs]
+    Model *final_start;      // [n_pairs] copy of best (start of the final LO)
+};
+
+__global__ void merge_kernel(MergeArgs a) {
+    const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pair >= a.n_pairs) return;
+    const PairParams pp = a.pairs[pair];
+    rp_stats st;
+    st.refinements = 0; st.iterations = 0; st.num_inliers = 0; st.inlier_ratio = 0.0; st.model_score = DBL_MAX;
+    Model best = identity_model();
+    if (pp.valid) {
+        const size_t pslot = (size_t)pair * a.nseg * (4 * SEG);
+        const int nev = a.n_events[pair];
+        for (int i = 0; i < nev; ++i) {
+            const int ev = a.events[pair * EV + i];
+            const double s = a.score[pslot + ev];
+            if (s < st.model_score) {
+                st.model_score = s;
+                best = a.models[pslot + ev];
+                st.num_inliers = a.count[pslot + ev];
+            }
+            const int lo = a.lo_of_event[pair * EV + i];
+            if (lo >= 0) {
+                st.refinements++;
+                const double rs = a.lo_score[pair * EV + lo];
+                if (rs < st.model_score) {
+                    st.model_score = rs;
+                    st.num_inliers = a.lo_count_inl[pair * EV + lo];
+                    best = a.lo_models[pair * EV + lo];
+                }
+                st.inlier_ratio = (double)st.num_inliers / (double)pp.n;
+            }
+        }
+        st.iterations = a.iters;
+    }
+    a.best[pair] = best;
+    a.final_start[pair] = best;
+    a.stats[pair] = st;
+}
+
+// final LO of ransac(): refinements++, accept when strictly better
+struct Merge2Args {
+    int n_pairs;
+    const PairParams *pairs;
+    const Model *refined;
+    const double *ref_score;
+    const int *ref_count;
+    Model *best;
+    rp_stats *stats;
+};
+__global__ void merge2_kernel(Merge2Args a) {
+    const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pair >= a.n_pairs) return;
+    const PairParams pp = a.pairs[pair];
+    if (!pp.valid) return;
+    rp_stats st = a.stats[pair];
+    st.refinements++;
+    const double rs = a.ref_score[pair];
+    if (rs < st.model_score) {
+        st.model_score = rs;
+        st.num_inliers = a.ref_count[pair];
+        a.best[pair] = a.refined[pair];
+    }
+    st.inlier_ratio = (double)st.num_inliers / (double)pp.n;
+    a.stats[pair] = st;
+}
+
+// per-pair switch of the final refinement (stats.num_inliers > 3) and the output conversion
+// (focal variants: f *= normalisation scale)
+__global__ void enable_final_kernel(int n_pairs, const rp_stats *stats, int *enable) {
+    const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pair < n_pairs) enable[pair] = stats[pair].num_inliers > 3;
+}
+__global__ void finalize_kernel(int n_pairs, int variant, const PairParams *pairs, Model *best) {
+    const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pair >= n_pairs) return;
+    if (variant == RP_SHARED || variant == RP_VARYING) {
+        best[pair].f1 *= pairs[pair].nscale;
+        best[pair].f2 *= pairs[pair].nscale;
+    }
+}
+
+__global__ void fill_int_kernel(int *p, int n, int v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pipe micro-benchmarks (the FP64 / FP32 FMA peaks are not in MEASURED_PEAKS.json)
+__global__ void fp64_pipe_kernel(double *out, int iters) {
+    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double b = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+__global__ void fp32_pipe_kernel(float *out, int iters) {
+    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const float b = 1.0000001f, c = 1e-9f;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fmaf(a0, b, c); a1 = fmaf(a1, b, c); a2 = fmaf(a2, b, c); a3 = fmaf(a3, b, c);
+        a4 = fmaf(a4, b, c); a5 = fmaf(a5, b, c); a6 = fmaf(a6, b, c); a7 = fmaf(a7, b, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+}  // namespace rp

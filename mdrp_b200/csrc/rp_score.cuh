@@ -56,7 +56,7 @@ RP_HD bool cheirality_exact(Quat q, V3 t, V3 b1, V3 b2) {
 // implies C^2/den > thr^2 (1+1e-6): the FP64 reference would also say "outlier".  The constants
 // carry >2x slack over the derived bounds; hypotheses whose Emax / thr leave the range where FP32
 // products stay normal get eps = +inf (filter disabled, everything goes to tier 1).
-struct Filter32 {
+struct alignas(16) Filter32 {
     float e00, e01, e02, e10, e11, e12, e20, e21, e22;
     float eps, g, pad;
 };
