@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py — image pairs/s (and hypothesis-scores/s) of the batched RePoseD LO-RANSAC on B200.
+
+A "step" = one pass of the hot path over one batch of synthetic two-view scenes.  Workload at
+N=1 = BASELINE.json configs[1]: calibrated scale+shift (monodepth_estimate_shift=True), 2 000
+matches per pair, 10 000 RANSAC iterations (min = max), 30 % outliers, truncated-Cauchy final
+refinement; `--pairs` pairs per GPU per step (default 10 000 = the config's batch).
+
+  value     whole-job pairs/s with the inputs already resident in HBM (rp_estimate_batch_dev),
+            CUDA events on the launching stream, max over ranks
+  e2e       the same through the reference-facing entry point with HOST buffers
+            (rp_estimate_batch_host): pinned host -> device copies and result read-back inside
+            the timed region
+  roofline  dominant kernel (score_kernel over the minimal models): 34 algorithmic FP64 flops per
+            point-score over its device time measured live with CUDA events,
+            against the FP64 FMA pipe peak measured on this device by rp_measure_pipes
+  cpu_baseline  the reference's own CPU implementation (oracle/_ref wheel, else the C port) on a
+            bounded sample of the same workload on all host cores
+
+Launch: python bench.py --gpus N --steps K --warmup W   (N>1 under torchrun, one rank per GPU)
+        python bench.py --impl reference …              (the reference arm: CPU path only)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOPS_PER_POINT_SCORE = 34.0
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg2_calib_shift")
+    ap.add_argument("--pairs", type=int, default=10000, help="image pairs per GPU per step")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="pairs in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(cfg_name, c, pairs):
+    return (f"{cfg_name}: {c['variant']}{'+shift' if c['shift'] else ''}, {pairs} pairs x {c['n']} matches, "
+            f"{c['iters']} RANSAC iters (min=max), {int(c['outlier_ratio'] * 100)}% outliers, "
+            "t=2px r=16px, TRUNCATED_CAUCHY final refinement")
+
+
+# ---- clocks ---------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(2)
+            except Exception:
+                self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---- CPU reference arm --------------------------------------------------------------------------------
+def cpu_pairs_per_s(cfg_name, n_sample, seed=12345):
+    """The reference's CPU path on `n_sample` pairs of the workload, all host cores (GIL released)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from mdrp_b200 import synth
+    from oracle import build_ref, port, ref_wheel
+    c = synth.CONFIGS[cfg_name]
+    cores = os.cpu_count() or 1
+    batch = synth.make_batch(cfg_name, n_sample, seed=seed)
+    offs = batch["offsets"]
+    iters = c["iters"]
+    use_ref = build_ref.have_ref()
+    if use_ref:
+        pl = ref_wheel.poselib()
+        ro = {"max_iterations": iters, "min_iterations": iters, "max_epipolar_error": 2.0, "max_reproj_error": 16.0,
+              "seed": 0, "monodepth_estimate_shift": c["shift"]}
+        bo = {"loss_type": "TRUNCATED_CAUCHY"}
+
+        def run(i):
+            sl = slice(offs[i], offs[i + 1])
+            if c["variant"] == "calib":
+                k = batch["cams"][i]
+                cam1 = {"model": "PINHOLE", "width": -1, "height": -1, "params": list(k[:4])}
+                cam2 = {"model": "PINHOLE", "width": -1, "height": -1, "params": list(k[4:])}
+                pl.estimate_monodepth_relative_pose(batch["x1"][sl], batch["x2"][sl], batch["d1"][sl], batch["d2"][sl],
+                                                    cam1, cam2, ro, bo)
+            elif c["variant"] == "shared":
+                pl.estimate_monodepth_shared_focal_relative_pose(batch["x1"][sl], batch["x2"][sl], batch["d1"][sl],
+                                                                 batch["d2"][sl], ro, bo)
+            else:
+                pl.estimate_monodepth_varying_focal_relative_pose(batch["x1"][sl], batch["x2"][sl], batch["d1"][sl],
+                                                                  batch["d2"][sl], ro, bo)
+    else:
+        port.build()
+        variant = {"calib": 1 if c["shift"] else 0, "shared": 2, "varying": 3}[c["variant"]]
+        rop = port.ransac_opt(max_iterations=iters, min_iterations=iters, max_epipolar_error=2.0, max_reproj_error=16.0,
+                              estimate_shift=c["shift"])
+        bop = port.bundle_opt(loss_type="TRUNCATED_CAUCHY")
+
+        def run(i):
+            sl = slice(offs[i], offs[i + 1])
+            k = batch["cams"][i] if batch["cams"] is not None else None
+            port.estimate(variant, batch["x1"][sl], batch["x2"][sl], batch["d1"][sl], batch["d2"][sl],
+                          None if k is None else k[:4], None if k is None else k[4:], rop, bop)
+
+    run(0)  # warm (page in the library)
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(cores) as ex:
+        list(ex.map(run, range(n_sample)))
+    dt = time.perf_counter() - t0
+    return n_sample / dt, cores, ("reference" if use_ref else "port"), dt
+
+
+def reference_arm(args, c, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_sample = args.cpu_sample or max(4 * cores, 16)
+    for _ in range(args.warmup):
+        cpu_pairs_per_s(args.config, max(2, min(n_sample, cores)), seed=1)
+    t_tot, n_tot, kind = 0.0, 0, "port"
+    for k in range(args.steps):
+        pps, cores, kind, dt = cpu_pairs_per_s(args.config, n_sample, seed=100 + k)
+        t_tot += dt
+        n_tot += n_sample
+    value = n_tot / t_tot
+    sample = f"{n_sample} pairs per step of the workload, per-pair calls from a {cores}-thread pool"
+    line = {"impl": "reference", "metric": "image_pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * t_tot / max(args.steps, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args.config, c, args.pairs), "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---- the GPU arm ------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    from mdrp_b200 import synth
+    c = synth.CONFIGS[args.config]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, c, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from mdrp_b200 import _native as nv
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ctx = nv.Context(local_rank)
+    variant = {"calib": nv.CALIB_SHIFT if c["shift"] else nv.CALIB, "shared": nv.SHARED, "varying": nv.VARYING}[c["variant"]]
+    opt = nv.default_options()
+    opt.max_iterations = opt.min_iterations = c["iters"]
+    opt.max_epipolar_error, opt.max_reproj_error, opt.seed = 2.0, 16.0, 0
+    opt.estimate_shift = int(c["shift"])
+    opt.loss_type = nv.LOSS["TRUNCATED_CAUCHY"]
+    opt.loss_scale = 1.0  # binding default 0.5*max_epipolar_error for the focal variants
+
+    P = args.pairs
+    batch = synth.make_batch(args.config, P, seed=1000 + rank)
+    offs = batch["offsets"]
+    N = int(offs[-1])
+    # pinned host buffers (e2e leg) and device-resident copies (value leg)
+    host = {k: torch.from_numpy(np.ascontiguousarray(batch[k])).pin_memory() for k in ("x1", "x2", "d1", "d2")}
+    host_cams = torch.from_numpy(batch["cams"]).pin_memory() if batch["cams"] is not None else None
+    devt = {k: v.to(dev) for k, v in host.items()}
+    dev_cams = host_cams.to(dev) if host_cams is not None else None
+    d_models = torch.zeros(P, 12, dtype=torch.float64, device=dev)
+    d_stats = torch.zeros(P, 5, dtype=torch.int64, device=dev)
+    d_masks = torch.zeros(max(N, 1), dtype=torch.uint8, device=dev)
+    h_models = torch.zeros(P, 12, dtype=torch.float64).pin_memory()
+    h_stats = torch.zeros(P, 5, dtype=torch.int64).pin_memory()
+    h_masks = torch.zeros(max(N, 1), dtype=torch.uint8).pin_memory()
+    stream = torch.cuda.current_stream()
+
+    def step_dev():
+        ctx.estimate_batch_dev(variant, offs, devt["x1"].data_ptr(), devt["x2"].data_ptr(), devt["d1"].data_ptr(),
+                               devt["d2"].data_ptr(), dev_cams.data_ptr() if dev_cams is not None else None, opt,
+                               d_models.data_ptr(), d_stats.data_ptr(), d_masks.data_ptr(), stream.cuda_stream)
+
+    import ctypes as C
+
+    def step_host():
+        L = ctx._lib
+        rc = L.rp_estimate_batch_host(ctx._h, variant, P, offs.ctypes.data, host["x1"].data_ptr(), host["x2"].data_ptr(),
+                                      host["d1"].data_ptr(), host["d2"].data_ptr(),
+                                      host_cams.data_ptr() if host_cams is not None else None, C.byref(opt),
+                                      h_models.data_ptr(), h_stats.data_ptr(), h_masks.data_ptr())
+        ctx._check(rc)
+
+    fp64_tf, fp32_tf = ctx.measure_pipes()
+
+    # ---- value: inputs resident in HBM ------------------------------------------------------------
+    for _ in range(args.warmup):
+        step_dev()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    launches0 = ctx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stage_ms = {}
+    counters = {}
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_dev()
+        tm, cn = ctx.last_timing()
+        for k, v in tm.items():
+            stage_ms[k] = stage_ms.get(k, 0.0) + v
+        for k, v in cn.items():
+            counters[k] = counters.get(k, 0) + v
+    e1.record(stream)
+    barrier()
+    elapsed = e0.elapsed_time(e1) / 1000.0
+    launches = ctx.launch_count - launches0
+    clk = clocks.stop()
+    t = torch.tensor([elapsed], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_max = float(t.item())
+    value = world * P * args.steps / elapsed_max
+
+    # sanity of what was timed: every pair produced a model with a plausible inlier count
+    ninl = d_stats[:, 2].float().mean().item()
+    assert ninl > 0.5 * c["n"] * (1 - c["outlier_ratio"]), f"implausible result (mean inliers {ninl})"
+
+    # ---- e2e: host buffers through the C ABI, copies inside the timed region --------------------------
+    for _ in range(max(1, min(args.warmup, 3))):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    torch.cuda.synchronize()
+    e2e_elapsed = time.perf_counter() - t0
+    t = torch.tensor([e2e_elapsed], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * P * args.steps / float(t.item())
+    assert torch.equal(h_stats.to(dev), d_stats), "host-buffer and device-buffer paths disagree"
+    h2d = N * 48 + (P * 64 if host_cams is not None else 0) + (P + 1) * 8
+    d2h = P * (96 + 40) + N
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel -------------------------------------------------------------------
+    score_s = stage_ms["score_minimal"] / 1000.0
+    ps = counters["point_scores"]
+    hyps = counters["hypotheses"]
+    n_chunk_launches = max(1, int(counters["chunks"]))
+    achieved_tf = FLOPS_PER_POINT_SCORE * ps / score_s / 1e12
+    alg_bytes = args.steps * N * 32 + hyps * (96 + 12)  # points once per pair; model in, score+count out per hypothesis
+    roofline = {"kernel": "score_kernel<pose> (minimal models)", "bound": "fp64_pipe", "achieved": achieved_tf,
+                "peak": fp64_tf, "unit": "TFLOP/s", "frac": achieved_tf / fp64_tf if fp64_tf else None,
+                "peak_source": "rp_measure_pipes on this device (FP64 FMA chain; MEASURED_PEAKS.json has no FP64 figure)",
+                "fp32_peak_tflops": fp32_tf, "traffic": None,
+                "point_scores_per_s": ps / score_s, "flops_per_point_score": FLOPS_PER_POINT_SCORE,
+                "launches": n_chunk_launches, "ms_per_launch": 1000.0 * score_s / n_chunk_launches,
+                "share_of_step": score_s / (stage_ms["device_total"] / 1000.0),
+                "hbm_algorithmic_gbs": alg_bytes / score_s / 1e9}
+
+    line = {"metric": "image_pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 * elapsed_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args.config, c, P), "pairs_per_gpu_per_step": P,
+                       "l2": "inputs_larger_than_l2 (%.0f MB per step)" % (N * 48 / 1e6), "parallelism": f"pairs sharded x{world}, no collective"},
+            "secondary": {"hypothesis_scores_per_sec": world * hyps / elapsed_max, "point_scores_per_sec": world * ps / elapsed_max,
+                          "models_per_iteration": hyps / (args.steps * P * c["iters"])},
+            "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
+            "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches), "clocks": clk, "roofline": roofline}
+    if not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        n_sample = args.cpu_sample or max(4 * cores, 16)
+        pps, cores, kind, dt = cpu_pairs_per_s(args.config, n_sample)
+        line["cpu_baseline"] = {"value": pps, "unit": "pairs/s", "cores": cores, "kind": kind,
+                                "sample": f"{n_sample} pairs of the workload, per-pair calls from a {cores}-thread pool, {dt:.1f} s"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

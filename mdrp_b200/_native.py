@@ -130,7 +130,7 @@ def _ptr(a):
 
 TIMING_KEYS = ["prepare", "sample", "solve", "score_minimal", "scan", "lo_refine", "lo_score_merge",
                "final_refine", "device_total", "h2d", "d2h"]
-COUNTER_KEYS = ["hypotheses", "point_scores", "lm_problems", "lm_iterations"]
+COUNTER_KEYS = ["hypotheses", "point_scores", "lm_problems", "lm_iterations", "chunks", "reserved"]
 
 
 class Context:
@@ -167,7 +167,7 @@ class Context:
 
     def last_timing(self):
         ms = (C.c_double * 11)()
-        cn = (C.c_int64 * 4)()
+        cn = (C.c_int64 * 6)()
         self._check(self._lib.rp_last_timing(self._h, ms, cn))
         return dict(zip(TIMING_KEYS, list(ms))), dict(zip(COUNTER_KEYS, list(cn)))
 

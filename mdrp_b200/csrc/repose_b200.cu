@@ -48,7 +48,7 @@ enum { B_OFFS, B_PAIRS, B_PTS64, B_PTS32, B_BEAR, B_SAMPLES, B_MODELS, B_HYPITER
 
 // device scalars living in B_SCALARS
 struct Scalars {
-    int n_items, n_lo_items, n_one_items, n_prob, n_pairs_scalar, overflow, pad0, pad1;
+    int n_items, n_lo_items, n_one_items, n_prob, n_pairs_scalar, overflow, need_more, pad1;
     unsigned long long point_scores, lm_iters;
     long long n_hyp;
 };
@@ -66,7 +66,7 @@ struct rp_ctx {
     DevBuf buf[B_NBUF];
     cudaEvent_t ev[N_EVENTS];
     double last_ms[11] = {0};
-    int64_t last_cnt[4] = {0};
+    int64_t last_cnt[6] = {0};
     size_t workspace_budget = (size_t)12 << 30;
     int occ_score[4] = {0}, occ_lm[4] = {0};
 };
@@ -202,11 +202,11 @@ struct ChunkIO {
     unsigned char *masks_out;        // device [n_points]
 };
 
-int run_chunk(rp_ctx *ctx, int variant, const rp_options &opt, const ChunkIO &io, cudaStream_t st) {
+int run_chunk(rp_ctx *ctx, int variant, const rp_options &opt, const ChunkIO &io, int iters, bool *need_more,
+              cudaStream_t st) {
     const int P = io.n_pairs;
     const long long N = io.n_points;
     const bool pose = variant == RP_CALIB || variant == RP_CALIB_SHIFT;
-    const int iters = (int)opt.max_iterations;
     const int nseg = std::max(1, cdiv(iters, SEG));
     const size_t slots_pp = (size_t)nseg * 4 * SEG;
     const size_t slots = slots_pp * (size_t)P;
@@ -346,6 +346,9 @@ int run_chunk(rp_ctx *ctx, int variant, const rp_options &opt, const ChunkIO &io
         if (rc) return rc;
         MergeArgs m;
         m.n_pairs = P; m.nseg = nseg; m.iters = iters; m.pairs = pairs; m.events = B[B_EVENTS].as<int>();
+        m.min_iterations = opt.min_iterations; m.max_iterations = opt.max_iterations;
+        m.dyn_num_trials_mult = opt.dyn_num_trials_mult; m.log_prob_missing = log(1.0 - opt.success_prob);
+        m.hyp_iter = hyp_iter; m.need_more = &sc->need_more;
         m.n_events = B[B_NEVENTS].as<int>(); m.lo_of_event = B[B_LOOFEV].as<int>(); m.score = score; m.count = count;
         m.models = models; m.lo_score = B[B_LOSCORE].as<double>(); m.lo_count_inl = B[B_LOCNT].as<int>();
         m.lo_models = B[B_LOMODELS].as<Model>(); m.lo_count = B[B_LOCOUNT].as<int>();
@@ -413,7 +416,9 @@ int run_chunk(rp_ctx *ctx, int variant, const rp_options &opt, const ChunkIO &io
     ctx->last_cnt[1] += (int64_t)h_sc.point_scores;
     ctx->last_cnt[2] += h_sc.n_prob + P;
     ctx->last_cnt[3] += (int64_t)h_sc.lm_iters;
+    ctx->last_cnt[4] += 1;
     if (h_sc.overflow) return fail(ctx, RP_ERR_OVERFLOW, "trigger event list overflowed (EV)");
+    *need_more = h_sc.need_more != 0;
     return RP_OK;
 }
 
@@ -450,7 +455,10 @@ int estimate_impl(rp_ctx *ctx, int variant, int64_t n_pairs, const int64_t *offs
     memset(ctx->last_cnt, 0, sizeof ctx->last_cnt);
     if (n_pairs == 0) return RP_OK;
     const long long Ntot = offsets[n_pairs] - offsets[0];
-    const size_t bpp = bytes_per_pair((int)opt.max_iterations, Ntot / n_pairs + 1);
+    const int plan_iters = opt.min_iterations < opt.max_iterations
+                               ? (int)std::min<int64_t>(opt.max_iterations, 16 * (opt.min_iterations + 1))
+                               : (int)opt.max_iterations;
+    const size_t bpp = bytes_per_pair(plan_iters, Ntot / n_pairs + 1);
     int64_t chunk = (int64_t)std::max<size_t>(1, ctx->workspace_budget / bpp);
     chunk = std::min<int64_t>(chunk, 32768);
     std::vector<long long> rel;
@@ -488,8 +496,19 @@ int estimate_impl(rp_ctx *ctx, int variant, int64_t n_pairs, const int64_t *offs
             io.cams = pose ? cams + 8 * p0 : nullptr;
             io.models_out = (Model *)models + p0; io.stats_out = stats + p0; io.masks_out = masks + o0;
         }
-        rc = run_chunk(ctx, variant, opt, io, st);
-        if (rc) return rc;
+        // Early termination (min_iterations < max_iterations): the reference stops at the first
+        // it > min_iterations with it > dynamic_max_iter.  Generate min_iterations+1 iterations, let
+        // the merge kernel replay the stop rule exactly, and only if some pair would have kept going
+        // regenerate the chunk with 4x more iterations (same seeds => same prefix).
+        int iters = (int)opt.max_iterations;
+        if (opt.min_iterations < opt.max_iterations) iters = (int)std::min<int64_t>(opt.max_iterations, opt.min_iterations + 1);
+        for (;;) {
+            bool need_more = false;
+            rc = run_chunk(ctx, variant, opt, io, iters, &need_more, st);
+            if (rc) return rc;
+            if (!need_more || iters >= opt.max_iterations) break;
+            iters = (int)std::min<int64_t>(opt.max_iterations, (int64_t)iters * 4);
+        }
         if (host_io) {
             float ms = 0.f;
             CK(cudaEventElapsedTime(&ms, e0, e1));
@@ -590,10 +609,10 @@ int rp_estimate_batch_dev(rp_ctx *ctx, int variant, int64_t n_pairs, const int64
                          stream ? (cudaStream_t)stream : ctx->stream);
 }
 
-int rp_last_timing(const rp_ctx *ctx, double *ms11, int64_t *counters4) {
+int rp_last_timing(const rp_ctx *ctx, double *ms11, int64_t *counters6) {
     if (!ctx) return RP_ERR_INVALID;
     if (ms11) memcpy(ms11, ctx->last_ms, sizeof ctx->last_ms);
-    if (counters4) memcpy(counters4, ctx->last_cnt, sizeof ctx->last_cnt);
+    if (counters6) memcpy(counters6, ctx->last_cnt, sizeof ctx->last_cnt);
     return RP_OK;
 }
 

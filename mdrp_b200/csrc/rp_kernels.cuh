@@ -774,9 +774,12 @@ __global__ void __launch_bounds__(LM_THREADS) lm_kernel(LMArgs a) {
 // trigger events in order: a triggering minimal model becomes the best model if its score beats
 // stats.model_score; after the last trigger of an iteration the LO result is compared (strict <).
 struct MergeArgs {
-    int n_pairs, nseg, iters;
+    int n_pairs, nseg, iters;  // iters = iterations actually generated for this chunk
+    long long min_iterations, max_iterations;
+    double dyn_num_trials_mult, log_prob_missing;
     const PairParams *pairs;
     const int *events, *n_events, *lo_of_event;
+    const int *hyp_iter;
     const double *score;     // minimal slots
     const int *count;
     const Model *models;
@@ -787,6 +790,7 @@ struct MergeArgs {
     Model *best;             // [n_pairs]
     rp_stats *stats;         // [n_pairs]
     Model *final_start;      // [n_pairs] copy of best (start of the final LO)
+    int *need_more;          // set when a pair neither stopped nor reached max_iterations
 };
 
 __global__ void merge_kernel(MergeArgs a) {
@@ -799,8 +803,15 @@ __global__ void merge_kernel(MergeArgs a) {
     if (pp.valid) {
         const size_t pslot = (size_t)pair * a.nseg * (4 * SEG);
         const int nev = a.n_events[pair];
+        // the loop of ransac<>() breaks at the first it > min_iterations with it > dynamic_max_iter;
+        // dynamic_max_iter only changes after an LO, so the break point is known between events
+        double dyn_max_iter = (double)a.max_iterations;
+        long long stop_it = -1;
         for (int i = 0; i < nev; ++i) {
             const int ev = a.events[pair * EV + i];
+            const long long it_e = a.hyp_iter[pslot + ev];
+            const long long cand = max(a.min_iterations + 1, (long long)floor(dyn_max_iter) + 1);
+            if (cand <= it_e) { stop_it = cand; break; }
             const double s = a.score[pslot + ev];
             if (s < st.model_score) {
                 st.model_score = s;
@@ -817,9 +828,22 @@ __global__ void merge_kernel(MergeArgs a) {
                     best = a.lo_models[pair * EV + lo];
                 }
                 st.inlier_ratio = (double)st.num_inliers / (double)pp.n;
+                if (st.inlier_ratio >= 0.9999) dyn_max_iter = (double)a.min_iterations;
+                else if (st.inlier_ratio <= 0.0001) dyn_max_iter = (double)a.max_iterations;
+                else {
+                    const double prob_outlier = 1.0 - pow(st.inlier_ratio, 3.0);
+                    dyn_max_iter = ceil(a.log_prob_missing / log(prob_outlier) * a.dyn_num_trials_mult);
+                }
             }
         }
-        st.iterations = a.iters;
+        if (stop_it < 0) {
+            const long long cand = max(a.min_iterations + 1, (long long)floor(dyn_max_iter) + 1);
+            if (cand < a.iters) stop_it = cand;                             // stopped inside what we generated
+            else if (a.iters >= a.max_iterations) stop_it = a.max_iterations;  // loop ran to the end
+            else if (cand == a.iters) stop_it = cand;                        // would stop exactly at the next it
+            else { stop_it = a.iters; *a.need_more = 1; }
+        }
+        st.iterations = stop_it;
     }
     a.best[pair] = best;
     a.final_start[pair] = best;

@@ -112,3 +112,47 @@ def translation_error_deg(t, t_gt):
         return 180.0
     c = np.clip(np.dot(t, t_gt) / n, -1.0, 1.0)
     return float(np.degrees(np.arccos(c)))
+
+
+def make_batch(config: str, n_pairs: int, seed: int = 0, n: int | None = None):
+    """Vectorised generator for the benchmark: the same scene model as make_scene for `n_pairs`
+    pairs at once (one RNG stream for the whole batch, so individual scenes differ from
+    make_scene(index) — parity tests use make_scene, the bench only needs data of this shape).
+    Returns dict(offsets, x1, x2, d1, d2, cams, R, t) with packed [n_pairs*n, …] arrays; x are full
+    pixel coordinates for the calibrated variants and principal-point-centred for the focal ones."""
+    c = CONFIGS[config]
+    n = n or c["n"]
+    f1, f2 = c["f1"], c["f2"]
+    out_ratio, scale = c["outlier_ratio"], 1.7
+    shift1, shift2 = c.get("shift1", 0.0), c.get("shift2", 0.0)
+    sigma, dn = c.get("sigma_px", 0.5), c.get("depth_noise", 0.01)
+    rng = np.random.default_rng(seed)
+    P = n_pairs
+    axis = rng.normal(size=(P, 3))
+    axis /= np.linalg.norm(axis, axis=1, keepdims=True)
+    ang = np.deg2rad(20.0) * rng.uniform(0.2, 1.0, size=P)
+    K = np.zeros((P, 3, 3))
+    K[:, 0, 1], K[:, 0, 2], K[:, 1, 0] = -axis[:, 2], axis[:, 1], axis[:, 2]
+    K[:, 1, 2], K[:, 2, 0], K[:, 2, 1] = -axis[:, 0], -axis[:, 1], axis[:, 0]
+    R = np.eye(3)[None] + np.sin(ang)[:, None, None] * K + (1 - np.cos(ang))[:, None, None] * (K @ K)
+    t = rng.normal(size=(P, 3))
+    t = 0.5 * t / np.linalg.norm(t, axis=1, keepdims=True)
+    x1 = np.stack([rng.uniform(0, W, (P, n)), rng.uniform(0, H, (P, n))], axis=2)
+    z1 = rng.uniform(2.0, 8.0, (P, n))
+    X1 = np.concatenate([(x1 - PP) / f1, np.ones((P, n, 1))], axis=2) * z1[..., None]
+    X2 = np.einsum("pij,pnj->pni", R, X1) + t[:, None, :]
+    z2 = X2[..., 2]
+    x2 = X2[..., :2] / z2[..., None] * f2 + PP
+    x1n = x1 + sigma * rng.normal(size=(P, n, 2))
+    x2n = x2 + sigma * rng.normal(size=(P, n, 2))
+    d1 = z1 * (1 + dn * rng.normal(size=(P, n))) - shift1
+    d2 = (z2 / scale) * (1 + dn * rng.normal(size=(P, n))) - shift2
+    outl = rng.uniform(size=(P, n)) < out_ratio
+    rnd = np.stack([rng.uniform(0, W, (P, n)), rng.uniform(0, H, (P, n))], axis=2)
+    x2n = np.where(outl[..., None], rnd, x2n)
+    focal = c["variant"] in ("shared", "varying")
+    if focal:
+        x1n, x2n = x1n - PP, x2n - PP
+    cams = None if focal else np.tile(np.array([f1, f1, PP[0], PP[1], f2, f2, PP[0], PP[1]]), (P, 1))
+    return dict(offsets=np.arange(P + 1, dtype=np.int64) * n, x1=x1n.reshape(-1, 2), x2=x2n.reshape(-1, 2),
+                d1=d1.reshape(-1), d2=d2.reshape(-1), cams=cams, R=R, t=t, inliers=~outl.reshape(-1))

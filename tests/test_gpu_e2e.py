@@ -1,0 +1,223 @@
+"""GPU tier: the batched estimators through the C ABI against the reference's golden outputs, the
+oracle on the same inputs, the reference's edge-case behaviour and size-independent properties at
+BASELINE.json's full sizes."""
+import sys
+
+import numpy as np
+import pytest
+
+from mdrp_b200 import _native as nv, api, synth
+from util import maa, models_close, rot_err_deg, trans_err_deg
+
+pytestmark = pytest.mark.gpu
+DBL_MAX = sys.float_info.max
+
+
+def _options(iters, shift=False, seed=0, min_iters=None, loss_scale=1.0):
+    o = nv.default_options()
+    o.max_iterations = iters
+    o.min_iterations = iters if min_iters is None else min_iters
+    o.max_epipolar_error, o.max_reproj_error, o.seed = 2.0, 16.0, seed
+    o.estimate_shift = int(shift)
+    o.loss_type = nv.LOSS["TRUNCATED_CAUCHY"]
+    o.loss_scale = loss_scale
+    return o
+
+
+def _batch(cfg, indices, n=None):
+    c = synth.CONFIGS[cfg]
+    scs = [synth.scene_for(cfg, i, n=n) for i in indices]
+    variant = {"calib": 1 if c["shift"] else 0, "shared": 2, "varying": 3}[c["variant"]]
+    offs = np.r_[0, np.cumsum([len(s.d1) for s in scs])]
+    if variant < 2:
+        x1, x2 = np.concatenate([s.x1 for s in scs]), np.concatenate([s.x2 for s in scs])
+        cams = np.array([[s.f1, s.f1, 640, 480, s.f2, s.f2, 640, 480] for s in scs], dtype=np.float64)
+    else:
+        x1, x2 = np.concatenate([s.centred()[0] for s in scs]), np.concatenate([s.centred()[1] for s in scs])
+        cams = None
+    return scs, variant, offs, x1, x2, np.concatenate([s.d1 for s in scs]), np.concatenate([s.d2 for s in scs]), cams
+
+
+def test_golden_end_to_end(ctx, e2e_golden):
+    """Outputs of the reference binary on committed inputs: stats, mask and model must agree."""
+    g = e2e_golden
+    keys = sorted(k[:-6] for k in g.files if k.endswith("_model"))
+    for key in keys:
+        name = key.split("_cfg")[0].split("_hard")[0]
+        variant = {"calib": 0, "calib_shift": 1, "shared": 2, "varying": 3, "calib_default_iters": 0}[name]
+        iters = int(g[key + "_iters"][0])
+        idx = int(key[-1])
+        o = _options(iters if iters > 0 else 5000, shift=variant == 1, seed=idx, min_iters=None if iters > 0 else 100)
+        n = len(g[key + "_d1"])
+        f1, f2 = g[key + "_f"]
+        cams = np.array([[f1, f1, 640, 480, f2, f2, 640, 480]]) if variant < 2 else None
+        models, stats, masks = ctx.estimate_batch_host(variant, [0, n], g[key + "_x1"], g[key + "_x2"], g[key + "_d1"],
+                                                       g[key + "_d2"], cams, o)
+        ref = g[key + "_stats"]
+        assert (stats[0]["refinements"], stats[0]["iterations"], stats[0]["num_inliers"]) == tuple(ref), key
+        assert abs(stats[0]["model_score"] - g[key + "_fstats"][1]) <= 1e-11 * g[key + "_fstats"][1], key
+        assert abs(stats[0]["inlier_ratio"] - g[key + "_fstats"][0]) <= 1e-12, key
+        assert np.array_equal(masks, g[key + "_mask"]), key
+        assert models_close(models[0], g[key + "_model"], rtol=1e-6, atol=1e-8), key  # north_star: 1e-6 relative
+
+
+@pytest.mark.parametrize("cfg", ["cfg1_calib_scale", "cfg2_calib_shift", "cfg3_shared_focal", "cfg4_varying_focal"])
+def test_batch_vs_oracle(ctx, port, cfg):
+    """A ragged batch (different N per pair) against the oracle run pair by pair."""
+    c = synth.CONFIGS[cfg]
+    sizes = [300, 64, 1000, 3, 517, 129]
+    scs = [synth.scene_for(cfg, 60 + i, n=n) for i, n in enumerate(sizes)]
+    variant = {"calib": 1 if c["shift"] else 0, "shared": 2, "varying": 3}[c["variant"]]
+    offs = np.r_[0, np.cumsum(sizes)]
+    if variant < 2:
+        x1, x2 = np.concatenate([s.x1 for s in scs]), np.concatenate([s.x2 for s in scs])
+        cams = np.array([[s.f1, s.f1, 640, 480, s.f2, s.f2, 640, 480] for s in scs], dtype=np.float64)
+    else:
+        x1, x2 = np.concatenate([s.centred()[0] for s in scs]), np.concatenate([s.centred()[1] for s in scs])
+        cams = None
+    d1, d2 = np.concatenate([s.d1 for s in scs]), np.concatenate([s.d2 for s in scs])
+    iters = 500
+    models, stats, masks = ctx.estimate_batch_host(variant, offs, x1, x2, d1, d2, cams, _options(iters, c["shift"]))
+    rop = port.ransac_opt(max_iterations=iters, min_iterations=iters, max_epipolar_error=2.0, max_reproj_error=16.0,
+                          seed=0, estimate_shift=c["shift"])
+    bop = port.bundle_opt(loss_type="TRUNCATED_CAUCHY", loss_scale=1.0)
+    for i, s in enumerate(scs):
+        sl = slice(offs[i], offs[i + 1])
+        cam = ([s.f1, s.f1, 640, 480], [s.f2, s.f2, 640, 480]) if variant < 2 else (None, None)
+        m, st, mk = port.estimate(variant, x1[sl], x2[sl], d1[sl], d2[sl], cam[0], cam[1], rop, bop)
+        assert (st.refinements, st.iterations, st.num_inliers) == (
+            stats[i]["refinements"], stats[i]["iterations"], stats[i]["num_inliers"]), (cfg, i)
+        assert np.array_equal(mk, masks[sl].astype(bool)), (cfg, i)
+        if sizes[i] > 3:
+            assert models_close(models[i], m, rtol=1e-6, atol=1e-8), (cfg, i)
+
+
+def test_edge_cases_match_reference_behaviour(ctx):
+    """SURVEY §8b 'Errors': N<3 -> identity, iterations 0, model_score DBL_MAX, all-False mask; empty
+    batch; a pair with zero correspondences inside a batch."""
+    o = _options(200)
+    cams = np.tile(np.array([800., 800, 640, 480, 800, 800, 640, 480]), (3, 1))
+    sc = synth.scene_for("cfg1_calib_scale", 0, n=200)
+    x1 = np.concatenate([sc.x1[:2], sc.x1])
+    x2 = np.concatenate([sc.x2[:2], sc.x2])
+    d1, d2 = np.concatenate([sc.d1[:2], sc.d1]), np.concatenate([sc.d2[:2], sc.d2])
+    models, stats, masks = ctx.estimate_batch_host(0, [0, 2, 2, 202], x1, x2, d1, d2, cams, o)
+    for i in (0, 1):  # N=2 and N=0
+        assert np.array_equal(models[i]["q"], [1, 0, 0, 0]) and np.array_equal(models[i]["t"], [0, 0, 0])
+        assert models[i]["scale"] == 1.0
+        assert stats[i]["iterations"] == 0 and stats[i]["refinements"] == 0 and stats[i]["num_inliers"] == 0
+        assert stats[i]["model_score"] == DBL_MAX
+    assert masks[:2].sum() == 0
+    assert stats[2]["num_inliers"] > 100 and masks[2:].sum() == stats[2]["num_inliers"]
+    m0, s0, k0 = ctx.estimate_batch_host(0, [0], np.zeros((0, 2)), np.zeros((0, 2)), np.zeros(0), np.zeros(0),
+                                         np.zeros((0, 8)), o)
+    assert len(m0) == 0 and len(s0) == 0 and len(k0) == 0
+    with pytest.raises(ValueError):
+        ctx.estimate_batch_host(0, [0, 5], np.zeros((4, 2)), np.zeros((5, 2)), np.zeros(5), np.zeros(5), cams[:1], o)
+
+
+def test_early_termination_matches_reference_rule(ctx, port):
+    """Default options (min 1000 / max 100000): the loop stops at the first it > min_iterations with
+    it > dynamic_max_iter — iteration 1001 on easy data (demo/reposed_demo.ipynb:659)."""
+    for cfg, n, min_it, max_it in (("cfg1_calib_scale", 150, 1000, 100000), ("hard_calib", 200, 50, 20000)):
+        sc = synth.scene_for(cfg, 77, n=n)
+        o = _options(max_it, min_iters=min_it)
+        cams = np.array([[800., 800, 640, 480, 800, 800, 640, 480]])
+        models, stats, masks = ctx.estimate_batch_host(0, [0, n], sc.x1, sc.x2, sc.d1, sc.d2, cams, o)
+        rop = port.ransac_opt(max_iterations=max_it, min_iterations=min_it, max_epipolar_error=2.0, max_reproj_error=16.0)
+        m, st, mk = port.estimate(0, sc.x1, sc.x2, sc.d1, sc.d2, [800, 800, 640, 480], [800, 800, 640, 480], rop,
+                                  port.bundle_opt(loss_type="TRUNCATED_CAUCHY"))
+        assert stats[0]["iterations"] == st.iterations, cfg
+        assert (stats[0]["refinements"], stats[0]["num_inliers"]) == (st.refinements, st.num_inliers), cfg
+        assert np.array_equal(mk, masks.astype(bool))
+        assert models_close(models[0], m, rtol=1e-6, atol=1e-8)
+    assert True
+
+
+def test_result_independent_of_batch_composition(ctx):
+    """Determinism per pair: seed per pair = opt.seed as in the reference, so a pair's result must
+    not depend on what else is in the batch, nor on repetition."""
+    scs, variant, offs, x1, x2, d1, d2, cams = _batch("cfg2_calib_shift", range(12), n=400)
+    o = _options(1000, shift=True)
+    a = ctx.estimate_batch_host(variant, offs, x1, x2, d1, d2, cams, o)
+    b = ctx.estimate_batch_host(variant, offs, x1, x2, d1, d2, cams, o)
+    for u, v in zip(a, b):
+        assert u.tobytes() == v.tobytes()
+    for i in (0, 5, 11):
+        sl = slice(offs[i], offs[i + 1])
+        m, s, k = ctx.estimate_batch_host(variant, [0, offs[i + 1] - offs[i]], x1[sl], x2[sl], d1[sl], d2[sl],
+                                          cams[i:i + 1], o)
+        assert m[0].tobytes() == a[0][i].tobytes() and s[0].tobytes() == a[1][i].tobytes()
+        assert np.array_equal(k, a[2][sl])
+
+
+@pytest.mark.parametrize("cfg", ["cfg2_calib_shift", "cfg3_shared_focal", "cfg4_varying_focal", "cfg5_roma_calib"])
+def test_full_size_properties(ctx, cfg):
+    """BASELINE.json full sizes (2k matches x 10k iterations; 10k matches): size-independent checks —
+    recovered pose close to ground truth, mask == get_inliers of the RANSAC model (count identity),
+    mask mostly the true inliers, score bound."""
+    c = synth.CONFIGS[cfg]
+    scs, variant, offs, x1, x2, d1, d2, cams = _batch(cfg, range(200, 216))
+    o = _options(c["iters"], shift=c["shift"])
+    models, stats, masks = ctx.estimate_batch_host(variant, offs, x1, x2, d1, d2, cams, o)
+    for i, s in enumerate(scs):
+        sl = slice(offs[i], offs[i + 1])
+        assert stats[i]["iterations"] == c["iters"]
+        assert masks[sl].sum() == stats[i]["num_inliers"]
+        assert abs(stats[i]["inlier_ratio"] - stats[i]["num_inliers"] / len(s.d1)) < 1e-12
+        assert rot_err_deg(models[i]["q"], s.R) < 0.1
+        assert trans_err_deg(models[i]["t"], s.t) < 1.0
+        assert abs(models[i]["scale"] - s.scale) < 0.02 * s.scale
+        inl = masks[sl].astype(bool)
+        assert (inl & s.inlier_mask).sum() > 0.9 * s.inlier_mask.sum()
+        if variant >= 2:
+            assert abs(models[i]["f1"] - s.f1) < 0.02 * s.f1 and abs(models[i]["f2"] - s.f2) < 0.02 * s.f2
+        if variant == 1:
+            assert abs(models[i]["shift1"] - s.shift1) < 0.05 and abs(models[i]["shift2"] - s.shift2) < 0.05
+
+
+def test_pose_auc_parity_on_hard_scenes(ctx, port):
+    """north_star: end-to-end pose AUC on synthetic scenes within 0.5 points of the reference path
+    (hard variant: sigma 2 px, 10 % depth noise, 60 % outliers, 1000 iterations — SURVEY §8d)."""
+    idx = range(300, 340)
+    scs, variant, offs, x1, x2, d1, d2, cams = _batch("hard_calib", idx)
+    models, stats, masks = ctx.estimate_batch_host(variant, offs, x1, x2, d1, d2, cams, _options(1000))
+    rop = port.ransac_opt(max_iterations=1000, min_iterations=1000, max_epipolar_error=2.0, max_reproj_error=16.0)
+    bop = port.bundle_opt(loss_type="TRUNCATED_CAUCHY")
+    e_gpu, e_ref = [], []
+    for i, s in enumerate(scs):
+        m, st, mk = port.estimate(0, s.x1, s.x2, s.d1, s.d2, [800, 800, 640, 480], [800, 800, 640, 480], rop, bop)
+        e_ref.append(max(rot_err_deg(np.array(m.q), s.R), trans_err_deg(np.array(m.t), s.t)))
+        e_gpu.append(max(rot_err_deg(models[i]["q"], s.R), trans_err_deg(models[i]["t"], s.t)))
+    for deg in (5, 10, 20):
+        assert abs(maa(e_gpu, deg) - maa(e_ref, deg)) <= 0.5
+
+
+def test_python_surface_matches_reference_api(ctx):
+    """Same call and return surface as poselib (whl:_core.pyi:446-501) and the fork names of eval*.py."""
+    sc = synth.scene_for("cfg1_calib_scale", 9, n=300)
+    c1, c2 = sc.camera_dicts()
+    ro = {"max_iterations": 300, "min_iterations": 300, "max_epipolar_error": 2.0, "max_reproj_error": 16.0,
+          "lo_iterations": 25, "weight_sampson": 1.0}
+    geom, info = api.estimate_monodepth_relative_pose(sc.x1.astype(np.float32), sc.x2, list(sc.d1), sc.d2, c1, c2, ro,
+                                                      {"loss_type": "TRUNCATED_CAUCHY"})
+    assert set(info) == {"refinements", "iterations", "num_inliers", "inlier_ratio", "model_score", "inliers"}
+    assert len(info["inliers"]) == 300 and isinstance(info["inliers"][0], bool)
+    assert geom.pose.R.shape == (3, 3) and geom.pose.t.shape == (3,) and geom.pose.q.shape == (4,)
+    assert np.allclose(geom.pose.Rt[:, :3], geom.pose.R) and geom.shift1 == 0.0
+    assert rot_err_deg(geom.pose.q, sc.R) < 0.5 and abs(geom.scale - 1.7) < 0.05
+    x1, x2 = sc.centred()
+    pair, info2 = api.estimate_monodepth_shared_focal_relative_pose(x1, x2, sc.d1, sc.d2, ro, {})
+    assert abs(pair.camera1.focal() - 800) < 20 and pair.camera1.model_name() == "SIMPLE_PINHOLE"
+    assert pair.camera1.params[1:] == [0.0, 0.0] and pair.geometry.pose.R.shape == (3, 3)
+    pair3, _ = api.estimate_monodepth_varying_focal_relative_pose(x1, x2, sc.d1, sc.d2, ro, {})
+    assert abs(pair3.camera2.focal() - 800) < 40
+    # fork names (eval.py:153, eval_shared_f.py:177)
+    K = {"model": "PINHOLE", "width": -1, "height": -1, "params": [800.0, 800.0, 640.0, 480.0]}
+    pose, info3 = api.estimate_relative_pose_w_mono_depth(sc.x1, sc.x2, np.c_[sc.d1, sc.d2], K, K,
+                                                          dict(ro, use_p3p=True, use_ours=False, solver_shift=False), {})
+    assert rot_err_deg(pose.q, sc.R) < 0.5 and pose.R.shape == (3, 3)
+    ip, _ = api.estimate_shared_focal_monodepth_relative_pose(x1, x2, np.c_[sc.d1, sc.d2], ro, {})
+    assert ip.pose.R.shape == (3, 3) and ip.camera1.focal() > 0
+    assert len(api.monodepth_pose_3pt(np.c_[sc.x1[:3] / 800, np.ones(3)], np.c_[sc.x2[:3] / 800, np.ones(3)],
+                                      sc.d1[:3], sc.d2[:3])) <= 4
