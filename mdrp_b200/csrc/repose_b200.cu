@@ -435,8 +435,8 @@ int check_common(rp_ctx *ctx, int variant, int64_t n_pairs, const int64_t *offse
     if (n_pairs < 0 || !offsets || !opt) return fail(ctx, RP_ERR_INVALID, "null or negative argument");
     if (opt->max_iterations < 0 || opt->max_iterations > (1 << 24)) return fail(ctx, RP_ERR_INVALID, "max_iterations out of range");
     for (int64_t p = 0; p < n_pairs; ++p)
-        if (offsets[p + 1] < offsets[p] || offsets[p + 1] - offsets[p] > (1 << 28))
-            return fail(ctx, RP_ERR_INVALID, "offsets must be non-decreasing");
+        if (offsets[p + 1] < offsets[p] || offsets[p + 1] - offsets[p] >= (1 << 24))
+            return fail(ctx, RP_ERR_INVALID, "offsets must be non-decreasing, at most 2^24-1 correspondences per pair");
     return RP_OK;
 }
 

@@ -405,16 +405,96 @@ struct HypConst {
     V3 t;
 };
 
+constexpr int QCAP = 32 + 32 * PT;  // per-warp candidate queue: < 32 left over + one full push
+
+struct ScoreShared {
+    HypConst hc[HB];
+    Filter32 hf[HB];
+    Cheir32 hch[HB];
+    double psum[HB][SCORE_WARPS];  // per-warp partial sums of inlier r^2 (only warp w touches [.][w])
+    int pcnt[HB][SCORE_WARPS];
+    unsigned queue[SCORE_WARPS][QCAP];
+};
+
+// tier 1 for up to 32 queued (model, correspondence) candidates, one per lane.  The queue content
+// and order of a warp are a pure function of its inputs, and the reductions below have a fixed
+// shape, so the FP64 sums are reproducible run to run (no floating-point atomics).
+template <bool POSE, bool MASK>
+__device__ __noinline__ void score_candidates(ScoreShared &sh, const ScoreArgs &a, const PairParams &pp,
+                                              unsigned entry, bool active) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int h = active ? (int)(entry >> 24) : 0;
+    const int k = (int)(entry & 0xffffffu);
+    bool inl = false;
+    double v = 0.0;
+    if (active) {
+        const long long g = pp.off + k;
+        const Pt64 p = a.pts64[g];
+        const double r2 = sampson_r2_exact(sh.hc[h].E, p.x1_0, p.x1_1, p.x2_0, p.x2_1);
+        inl = r2 < pp.sq_thr;
+        if (POSE && inl) {
+            const int scr = cheirality32(sh.hch[h], (float)p.x1_0, (float)p.x1_1, (float)p.x2_0, (float)p.x2_1);
+            if (scr == 0) {
+                const Bear b = a.bear[g];
+                inl = cheirality_exact(sh.hc[h].q, sh.hc[h].t, v3(b.b1x, b.b1y, b.b1z), v3(b.b2x, b.b2y, b.b2z));
+            } else {
+                inl = scr > 0;
+            }
+        }
+        if (inl) {
+            v = r2;
+            if (MASK) a.mask[g] = 1;
+        }
+    }
+    const unsigned inl_mask = __ballot_sync(0xffffffffu, inl);
+    if (inl_mask == 0) return;
+    const int h0 = __shfl_sync(0xffffffffu, h, __ffs(inl_mask) - 1);
+    if (__all_sync(0xffffffffu, !inl || h == h0)) {
+        // every inlier of this batch belongs to one model: butterfly sum, one update
+        v = warp_sum(v);
+        if (lane == 0) {
+            sh.pcnt[h0][wid] += __popc(inl_mask);
+            sh.psum[h0][wid] += v;
+        }
+        __syncwarp();
+        return;
+    }
+    // general case: segmented inclusive scan over runs of equal model index (lane order)
+    int c = inl ? 1 : 0;
+    const int h_prev = __shfl_up_sync(0xffffffffu, h, 1);
+    const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || h != h_prev);
+    const int run_start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double vu = __shfl_up_sync(0xffffffffu, v, o);
+        const int cu = __shfl_up_sync(0xffffffffu, c, o);
+        if (lane - o >= run_start) { v += vu; c += cu; }
+    }
+    const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
+    const bool do_add = tail && c > 0;
+    const unsigned add_mask = __ballot_sync(0xffffffffu, do_add);
+    unsigned rank = 0;
+    if (do_add) rank = __popc(__match_any_sync(add_mask, h) & lt_mask);  // same model in two runs of the batch
+    const unsigned max_rank = __reduce_max_sync(0xffffffffu, rank);
+    for (unsigned r = 0; r <= max_rank; ++r) {
+        if (do_add && rank == r) {
+            sh.pcnt[h][wid] += c;
+            sh.psum[h][wid] += v;
+        }
+        __syncwarp();
+    }
+}
+
 template <bool POSE, bool MASK>
 __global__ void __launch_bounds__(SCORE_THREADS) score_kernel(ScoreArgs a) {
-    __shared__ HypConst hc[HB];
-    __shared__ Filter32 hf[HB];
-    __shared__ double psum[HB][SCORE_WARPS];
-    __shared__ int pcnt[HB][SCORE_WARPS];
+    __shared__ ScoreShared sh;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
     const int n_items = *a.n_items;
     const int per = (n_items + gridDim.x - 1) / gridDim.x;
     const int item_end = min(n_items, (int)(blockIdx.x + 1) * per);
+    unsigned *q = sh.queue[wid];
     for (int item = blockIdx.x * per; item < item_end; ++item) {
         // group of this item: last e with item_prefix[e] <= item
         int lo = 0, hi = a.n_groups;
@@ -435,73 +515,67 @@ __global__ void __launch_bounds__(SCORE_THREADS) score_kernel(ScoreArgs a) {
             c.E = POSE ? essential_from_motion(m.q, m.t) : fundamental_from_model(m);
             c.q = m.q;
             c.t = m.t;
-            hc[tid] = c;
-            hf[tid] = make_filter32(c.E, pp.thr, pp.Mmax, pp.mmax);
+            sh.hc[tid] = c;
+            sh.hf[tid] = make_filter32(c.E, pp.thr, pp.Mmax, pp.mmax);
+            if (POSE) sh.hch[tid] = make_cheir32(m.q, m.t);
         }
         for (int i = tid; i < HB * SCORE_WARPS; i += SCORE_THREADS) {
-            (&psum[0][0])[i] = 0.0;
-            (&pcnt[0][0])[i] = 0;
+            (&sh.psum[0][0])[i] = 0.0;
+            (&sh.pcnt[0][0])[i] = 0;
         }
         __syncthreads();
         const int n = pp.n;
-        const double sq_thr = pp.sq_thr;
         const int slice_pts = 32 * PT;
         const int n_slices = (n + slice_pts - 1) / slice_pts;
+        int qn = 0;
         for (int sl = wid; sl < n_slices; sl += SCORE_WARPS) {
             float4 p[PT];
             bool valid[PT];
+            const int kbase = sl * slice_pts + lane;
 #pragma unroll
             for (int j = 0; j < PT; ++j) {
-                const int k = sl * slice_pts + j * 32 + lane;
+                const int k = kbase + j * 32;
                 valid[j] = k < n;
                 p[j] = valid[j] ? a.pts32[pp.off + k] : make_float4(0.f, 0.f, 0.f, 0.f);
             }
             for (int h = 0; h < nh; ++h) {
-                const Filter32 f = hf[h];
+                const Filter32 f = sh.hf[h];
                 unsigned cand = 0;
 #pragma unroll
                 for (int j = 0; j < PT; ++j)
                     if (valid[j] && !certain_outlier32(f, p[j].x, p[j].y, p[j].z, p[j].w)) cand |= 1u << j;
                 if (__any_sync(0xffffffffu, cand != 0)) {
-                    int c = 0;
-                    double s = 0.0;
-                    if (cand) {
-                        const M3 E = hc[h].E;
+                    // warp-aggregated push of (model, correspondence) candidates
 #pragma unroll
-                        for (int j = 0; j < PT; ++j) {
-                            if (!(cand >> j & 1)) continue;
-                            const long long g = pp.off + sl * slice_pts + j * 32 + lane;
-                            const Pt64 q64 = a.pts64[g];
-                            const double r2 = sampson_r2_exact(E, q64.x1_0, q64.x1_1, q64.x2_0, q64.x2_1);
-                            bool inl = r2 < sq_thr;
-                            if (POSE && inl) {
-                                const Bear b = a.bear[g];
-                                inl = cheirality_exact(hc[h].q, hc[h].t, v3(b.b1x, b.b1y, b.b1z), v3(b.b2x, b.b2y, b.b2z));
-                            }
-                            if (inl) { ++c; s += r2; }
-                            if (MASK && inl) a.mask[g] = 1;
-                        }
+                    for (int j = 0; j < PT; ++j) {
+                        const bool c = (cand >> j) & 1u;
+                        const unsigned m = __ballot_sync(0xffffffffu, c);
+                        if (c) q[qn + __popc(m & lt_mask)] = ((unsigned)h << 24) | (unsigned)(kbase + j * 32);
+                        qn += __popc(m);
                     }
-                    const unsigned anyinl = __ballot_sync(0xffffffffu, c != 0);
-                    if (anyinl) {
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) {
-                            c += __shfl_xor_sync(0xffffffffu, c, o);
-                            s += __shfl_xor_sync(0xffffffffu, s, o);
-                        }
-                        if (lane == 0) { pcnt[h][wid] += c; psum[h][wid] += s; }
+                    __syncwarp();
+                    while (qn >= 32) {
+                        qn -= 32;
+                        const unsigned entry = q[qn + lane];
+                        __syncwarp();
+                        score_candidates<POSE, MASK>(sh, a, pp, entry, true);
                     }
                 }
             }
+        }
+        if (qn > 0) {
+            const unsigned entry = lane < qn ? q[lane] : 0u;
+            __syncwarp();
+            score_candidates<POSE, MASK>(sh, a, pp, entry, lane < qn);
         }
         __syncthreads();
         if (tid < nh) {
             int c = 0;
             double s = 0.0;
 #pragma unroll
-            for (int w = 0; w < SCORE_WARPS; ++w) { c += pcnt[tid][w]; s += psum[tid][w]; }
+            for (int w = 0; w < SCORE_WARPS; ++w) { c += sh.pcnt[tid][w]; s += sh.psum[tid][w]; }
             a.count[slot0 + tid] = c;
-            a.score[slot0 + tid] = s + sq_thr * (double)(n - c);
+            a.score[slot0 + tid] = s + pp.sq_thr * (double)(n - c);
         }
         if (a.point_scores && tid == 0) atomicAdd(a.point_scores, (unsigned long long)nh * (unsigned long long)n);
     }

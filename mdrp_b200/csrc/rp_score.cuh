@@ -90,4 +90,61 @@ RP_HD bool certain_outlier32(const Filter32 &f, float x1_0, float x1_1, float x2
     return tt * tt > f.g * den;
 }
 
+
+// ---- FP32 cheirality screen ------------------------------------------------------------------
+// check_cheirality so@0x1dce00 evaluated in FP32 with R(q) as a matrix and bearings recomputed as
+// (x,y,1)*rsqrt(x^2+y^2+1).  With u = 2^-24, |b| <= 1, |R_ij| <= 1, T = |t|_1:
+//   bearings carry <= 8u relative error (input rounding, sum, rsqrt <= 2 ulp, product),
+//   |d(R b1)_i| <= 12u,  |da| <= 38u,  |d beta1| <= 16uT,  |d beta2| <= 12uT,
+//   |d lambda_i| <= 70uT,  |d(0.01(1-a^2))| <= 0.8u.
+// The screen answers +1 / -1 only when min(lambda1,lambda2) - 0.01(1-a^2) clears
+// mu = 128uT + 2u (again ~2x slack); 0 sends the point to the exact FP64 test.
+struct alignas(16) Cheir32 {
+    float r00, r01, r02, r10, r11, r12, r20, r21, r22;
+    float tx, ty, tz, mu, pad0, pad1, pad2;
+};
+
+RP_HD Cheir32 make_cheir32(Quat q, V3 t) {
+    const M3 R = quat_to_rotmat(q);
+    Cheir32 c;
+    c.r00 = (float)R.r0.x; c.r01 = (float)R.r0.y; c.r02 = (float)R.r0.z;
+    c.r10 = (float)R.r1.x; c.r11 = (float)R.r1.y; c.r12 = (float)R.r1.z;
+    c.r20 = (float)R.r2.x; c.r21 = (float)R.r2.y; c.r22 = (float)R.r2.z;
+    c.tx = (float)t.x; c.ty = (float)t.y; c.tz = (float)t.z;
+    const double T = fabs(t.x) + fabs(t.y) + fabs(t.z);
+    const double u = 5.9604644775390625e-08;
+    const double qn = q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z;
+    const bool sane = fabs(qn - 1.0) < 1e-6 && T > 1e-12 && T < 1e12;
+    c.mu = sane ? (float)((128.0 * u * T + 2.0 * u) * 1.0001) : INFINITY;
+    c.pad0 = c.pad1 = c.pad2 = 0.f;
+    return c;
+}
+
+RP_HD float rsqrt32(float x) {
+#if defined(__CUDA_ARCH__)
+    return rsqrtf(x);
+#else
+    return 1.0f / sqrtf(x);
+#endif
+}
+
+// +1: the FP64 reference test certainly passes, -1: certainly fails, 0: undecided
+RP_HD int cheirality32(const Cheir32 &c, float x1_0, float x1_1, float x2_0, float x2_1) {
+    const float n1 = rsqrt32(fmaf_(x1_0, x1_0, fmaf_(x1_1, x1_1, 1.0f)));
+    const float n2 = rsqrt32(fmaf_(x2_0, x2_0, fmaf_(x2_1, x2_1, 1.0f)));
+    const float b1x = x1_0 * n1, b1y = x1_1 * n1, b1z = n1;
+    const float b2x = x2_0 * n2, b2y = x2_1 * n2, b2z = n2;
+    const float rx = fmaf_(c.r00, b1x, fmaf_(c.r01, b1y, c.r02 * b1z));
+    const float ry = fmaf_(c.r10, b1x, fmaf_(c.r11, b1y, c.r12 * b1z));
+    const float rz = fmaf_(c.r20, b1x, fmaf_(c.r21, b1y, c.r22 * b1z));
+    const float a = -fmaf_(rx, b2x, fmaf_(ry, b2y, rz * b2z));
+    const float be1 = -fmaf_(rx, c.tx, fmaf_(ry, c.ty, rz * c.tz));
+    const float be2 = fmaf_(b2x, c.tx, fmaf_(b2y, c.ty, b2z * c.tz));
+    const float l1 = fmaf_(-a, be2, be1);
+    const float l2 = fmaf_(-a, be1, be2);
+    const float md = 0.01f * fmaf_(-a, a, 1.0f);
+    const float m = fminf(l1, l2) - md;
+    return m > c.mu ? 1 : (m < -c.mu ? -1 : 0);
+}
+
 }  // namespace rp

@@ -24,6 +24,9 @@ HC int hc_solve(int variant, const double *x1h, const double *x2h, const double 
     return ms.n;
 }
 
+static long g_screen_contradictions = 0, g_screen_decided = 0, g_screen_undecided = 0;
+HC void hc_screen_stats(long *out) { out[0] = g_screen_contradictions; out[1] = g_screen_decided; out[2] = g_screen_undecided; }
+
 // full two-tier point decision as the scoring kernel makes it; also reports how many points
 // the FP32 filter rejected (tier 0) so the test can check it never rejects a reference inlier
 HC double hc_score(int variant, const rp_model *model, const double *x1, const double *x2, long n,
@@ -39,6 +42,7 @@ HC double hc_score(int variant, const rp_model *model, const double *x1, const d
         mmax = fmax(mmax, fmax(a, b));
     }
     const Filter32 f = make_filter32(E, sqrt(sq_thr), Mmax, mmax);
+    const Cheir32 ch = make_cheir32(m.q, m.t);
     long c = 0, t0 = 0;
     double sum = 0.0;
     for (long k = 0; k < n; ++k) {
@@ -48,7 +52,14 @@ HC double hc_score(int variant, const rp_model *model, const double *x1, const d
         } else {
             const double r2 = sampson_r2_exact(E, x1[2 * k], x1[2 * k + 1], x2[2 * k], x2[2 * k + 1]);
             if (r2 < sq_thr) {
-                inl = !pose || cheirality_exact(m.q, m.t, bearing(x1[2 * k], x1[2 * k + 1]), bearing(x2[2 * k], x2[2 * k + 1]));
+                if (!pose) inl = true;
+                else {
+                    const bool exact = cheirality_exact(m.q, m.t, bearing(x1[2 * k], x1[2 * k + 1]), bearing(x2[2 * k], x2[2 * k + 1]));
+                    const int scr = cheirality32(ch, (float)x1[2 * k], (float)x1[2 * k + 1], (float)x2[2 * k], (float)x2[2 * k + 1]);
+                    if (scr != 0 && (scr > 0) != exact) g_screen_contradictions++;
+                    if (scr != 0) g_screen_decided++; else g_screen_undecided++;
+                    inl = scr != 0 ? scr > 0 : exact;
+                }
                 if (inl) { ++c; sum += r2; }
             }
         }

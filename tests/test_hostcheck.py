@@ -101,6 +101,11 @@ def test_two_tier_scorer_exact_counts(hc, port, variant):
             t0_total += t0.value
     assert tested > 50
     assert t0_total / (tested * len(x1)) > 0.5  # the FP32 tier does most of the work
+    st = (C.c_long * 3)()
+    hc.hc_screen_stats(st)
+    assert st[0] == 0  # the FP32 cheirality screen never contradicts the exact FP64 test
+    if variant in ("calib", "calib_shift"):
+        assert st[1] > 20 * max(1, st[2])  # and it decides almost every point
 
 
 @pytest.mark.parametrize("variant", ["calib", "calib_shift", "shared", "varying"])
