@@ -120,26 +120,8 @@ int launch_score(rp_ctx *ctx, bool pose, bool mask, const ScoreArgs &a, cudaStre
 }
 
 int launch_lm(rp_ctx *ctx, int variant, const LMArgs &a, cudaStream_t st) {
-    int grid;
-    switch (variant) {
-    case RP_CALIB:
-        grid = occupancy_grid(ctx, lm_kernel<RP_CALIB, 7>, LM_THREADS);
-        lm_kernel<RP_CALIB, 7><<<grid, LM_THREADS, 0, st>>>(a);
-        break;
-    case RP_CALIB_SHIFT:
-        grid = occupancy_grid(ctx, lm_kernel<RP_CALIB_SHIFT, 9>, LM_THREADS);
-        lm_kernel<RP_CALIB_SHIFT, 9><<<grid, LM_THREADS, 0, st>>>(a);
-        break;
-    case RP_SHARED:
-        grid = occupancy_grid(ctx, lm_kernel<RP_SHARED, 8>, LM_THREADS);
-        lm_kernel<RP_SHARED, 8><<<grid, LM_THREADS, 0, st>>>(a);
-        break;
-    default:
-        grid = occupancy_grid(ctx, lm_kernel<RP_VARYING, 9>, LM_THREADS);
-        lm_kernel<RP_VARYING, 9><<<grid, LM_THREADS, 0, st>>>(a);
-        break;
-    }
-    LAUNCHED();
+    ctx->launches++;
+    CK((cudaError_t)launch_lm_kernel(ctx->sms, variant, a, st));
     return RP_OK;
 }
 

@@ -73,13 +73,19 @@ struct NormalEq {
 #pragma unroll
         for (int i = 0; i < NP; ++i) g[i] = 0.0;
     }
+    // rank-1 update restricted to the columns whose bit is set in MASK (structural zeros of the row)
+    template <unsigned MASK>
     RP_HD void add_row(double w, const double (&J)[NP], double r) {
 #pragma unroll
         for (int i = 0; i < NP; ++i) {
+            if (!((MASK >> i) & 1u)) continue;
             const double wi = w * J[i];
             g[i] = fma_(wi, r, g[i]);
 #pragma unroll
-            for (int j = 0; j <= i; ++j) A[i * (i + 1) / 2 + j] = fma_(wi, J[j], A[i * (i + 1) / 2 + j]);
+            for (int j = 0; j <= i; ++j) {
+                if (!((MASK >> j) & 1u)) continue;
+                A[i * (i + 1) / 2 + j] = fma_(wi, J[j], A[i * (i + 1) / 2 + j]);
+            }
         }
     }
 };
@@ -123,20 +129,35 @@ RP_HD double point_cost(const LMFrame &F, const LMParams &P, double x1_0, double
     return cost;
 }
 
-// J^T J / J^T r contribution of one correspondence
+// J^T J / J^T r contribution of one correspondence.  Derivatives are written out per parameter
+// (cross products with unit vectors expanded by hand) and each residual row only touches its
+// structurally non-zero columns:
+//   Sampson          : w, t            (+ f | f1, f2)
+//   reprojection 1->2: w, t, shift1    (+ f | f1, f2)         (no scale, no shift2)
+//   reprojection 2->1: w, t, scale, shift2 (+ f | f1, f2)     (no shift1)
 template <int VARIANT, int NP>
 RP_HD void point_accumulate(const LMFrame &F, const LMParams &P, double x1_0, double x1_1, double x2_0,
                             double x2_1, double d1, double d2, NormalEq<NP> &N) {
     constexpr bool FOCAL = (VARIANT == RP_SHARED || VARIANT == RP_VARYING);
     constexpr int CF2 = (VARIANT == RP_SHARED) ? 7 : 8;  // column of f2 (== f column when shared)
-    const V3 p1 = v3(x1_0 / F.f1, x1_1 / F.f1, 1.0);
-    const V3 p2 = v3(x2_0 / F.f2, x2_1 / F.f2, 1.0);
+    constexpr unsigned M_POSE = 0x3Fu;                    // w (0-2), t (3-5)
+    constexpr unsigned M_FOC = VARIANT == RP_SHARED ? 0x80u : (VARIANT == RP_VARYING ? 0x180u : 0u);
+    constexpr unsigned M_S = M_POSE | M_FOC;
+    constexpr unsigned M_12 = M_POSE | M_FOC | (VARIANT == RP_CALIB_SHIFT ? 0x80u : 0u);
+    constexpr unsigned M_21 = M_POSE | 0x40u | M_FOC | (VARIANT == RP_CALIB_SHIFT ? 0x100u : 0u);
+    const double px = x1_0 / F.f1, py = x1_1 / F.f1;  // p1 = (px, py, 1)
+    const double qx = x2_0 / F.f2, qy = x2_1 / F.f2;  // p2 = (qx, qy, 1)
+    const M3 &R = F.R;
+    const M3 &E = F.E;
     double J[NP];
 
     // ---- Sampson row ----
     if (P.weight_sampson > 0.0) {
-        const V3 Ep1 = mul(F.E, p1), Etp2 = mulT(F.E, p2);
-        const double C = dot(p2, Ep1);
+        const V3 Ep1 = v3(E.r0.x * px + E.r0.y * py + E.r0.z, E.r1.x * px + E.r1.y * py + E.r1.z,
+                          E.r2.x * px + E.r2.y * py + E.r2.z);
+        const V3 Etp2 = v3(E.r0.x * qx + E.r1.x * qy + E.r2.x, E.r0.y * qx + E.r1.y * qy + E.r2.y,
+                           E.r0.z * qx + E.r1.z * qy + E.r2.z);
+        const double C = qx * Ep1.x + qy * Ep1.y + Ep1.z;
         const double A = Ep1.x * Ep1.x + Ep1.y * Ep1.y, B = Etp2.x * Etp2.x + Etp2.y * Etp2.y;
         const double inv = 1.0 / sqrt(A * F.if2sq + B * F.if1sq);
         const double rs = C * inv;
@@ -144,49 +165,68 @@ RP_HD void point_accumulate(const LMFrame &F, const LMParams &P, double x1_0, do
         if (w != 0.0) {
 #pragma unroll
             for (int i = 0; i < NP; ++i) J[i] = 0.0;
-            const double k = 0.5 * C * inv * inv * inv;
-            const V3 Rp1 = mul(F.R, p1);
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                const V3 e = unit(i);
-                // d/dw_i : dE = E [e_i]x
-                const V3 exp1 = cross(e, p1);
-                V3 dEp1 = mul(F.E, exp1);
-                V3 tmp = cross(e, Etp2);
-                double dC = dot(Etp2, exp1);
-                double dden = 2.0 * (Ep1.x * dEp1.x + Ep1.y * dEp1.y) * F.if2sq +
-                              2.0 * (Etp2.x * (-tmp.x) + Etp2.y * (-tmp.y)) * F.if1sq;
-                J[i] = dC * inv - k * dden;
-                // d/dt_i : dE = [e_i]x R
-                dEp1 = cross(e, Rp1);
-                tmp = mulT(F.R, cross(e, p2));
-                dC = dot(p2, dEp1);
-                dden = 2.0 * (Ep1.x * dEp1.x + Ep1.y * dEp1.y) * F.if2sq +
-                       2.0 * (Etp2.x * (-tmp.x) + Etp2.y * (-tmp.y)) * F.if1sq;
-                J[3 + i] = dC * inv - k * dden;
+            const double k = C * inv * inv * inv;  // = 2 * (0.5 C inv^3): the factor 2 of d(den) folded in
+            const double a2 = F.if2sq, a1 = F.if1sq;
+            // rotation: dE = E [e_i]x ;  d(Ep1) = E (e_i x p1),  d(E^T p2) = -(e_i x E^T p2)
+            {
+                const double dx = py * E.r0.z - E.r0.y, dy = py * E.r1.z - E.r1.y;
+                const double dC = py * Etp2.z - Etp2.y;
+                J[0] = dC * inv - k * ((Ep1.x * dx + Ep1.y * dy) * a2 + (Etp2.y * Etp2.z) * a1);
+            }
+            {
+                const double dx = E.r0.x - px * E.r0.z, dy = E.r1.x - px * E.r1.z;
+                const double dC = Etp2.x - px * Etp2.z;
+                J[1] = dC * inv - k * ((Ep1.x * dx + Ep1.y * dy) * a2 - (Etp2.x * Etp2.z) * a1);
+            }
+            {
+                const double dx = px * E.r0.y - py * E.r0.x, dy = px * E.r1.y - py * E.r1.x;
+                const double dC = px * Etp2.y - py * Etp2.x;
+                J[2] = dC * inv - k * ((Ep1.x * dx + Ep1.y * dy) * a2);
+            }
+            // translation: dE = [e_i]x R ;  d(Ep1) = e_i x (R p1),  d(E^T p2) = -R^T (e_i x p2)
+            const V3 s = v3(R.r0.x * px + R.r0.y * py + R.r0.z, R.r1.x * px + R.r1.y * py + R.r1.z,
+                            R.r2.x * px + R.r2.y * py + R.r2.z);
+            {
+                // e_0 x s = (0, -s.z, s.y);  e_0 x p2 = (0, -1, qy) -> d(E^T p2) = row1(R) - qy row2(R)
+                const double tx = R.r1.x - qy * R.r2.x, ty = R.r1.y - qy * R.r2.y;
+                const double dC = s.y - qy * s.z;
+                J[3] = dC * inv - k * ((-Ep1.y * s.z) * a2 + (Etp2.x * tx + Etp2.y * ty) * a1);
+            }
+            {
+                // e_1 x s = (s.z, 0, -s.x);  e_1 x p2 = (1, 0, -qx) -> d(E^T p2) = qx row2(R) - row0(R)
+                const double tx = qx * R.r2.x - R.r0.x, ty = qx * R.r2.y - R.r0.y;
+                const double dC = qx * s.z - s.x;
+                J[4] = dC * inv - k * ((Ep1.x * s.z) * a2 + (Etp2.x * tx + Etp2.y * ty) * a1);
+            }
+            {
+                // e_2 x s = (-s.y, s.x, 0);  e_2 x p2 = (-qy, qx, 0) -> d(E^T p2) = qy row0(R) - qx row1(R)
+                const double tx = qy * R.r0.x - qx * R.r1.x, ty = qy * R.r0.y - qx * R.r1.y;
+                const double dC = qy * s.x - qx * s.y;
+                J[5] = dC * inv - k * ((Ep1.y * s.x - Ep1.x * s.y) * a2 + (Etp2.x * tx + Etp2.y * ty) * a1);
             }
             if (FOCAL) {
-                const V3 dp1 = v3(-p1.x / F.f1, -p1.y / F.f1, 0.0);
-                const V3 dp2 = v3(-p2.x / F.f2, -p2.y / F.f2, 0.0);
-                const V3 dEp1 = mul(F.E, dp1), dEtp2 = mulT(F.E, dp2);
-                const double dden1 = 2.0 * (Ep1.x * dEp1.x + Ep1.y * dEp1.y) * F.if2sq - 2.0 * B * F.if1sq / F.f1;
-                const double dden2 = 2.0 * (Etp2.x * dEtp2.x + Etp2.y * dEtp2.y) * F.if1sq - 2.0 * A * F.if2sq / F.f2;
-                const double j1 = dot(Etp2, dp1) * inv - k * dden1;
-                const double j2 = dot(Ep1, dp2) * inv - k * dden2;
+                // p1 = (x1/f1, 1): dp1/df1 = -(px, py, 0)/f1 ; den = A/f2^2 + B/f1^2
+                const double dpx = -px / F.f1, dpy = -py / F.f1, dqx = -qx / F.f2, dqy = -qy / F.f2;
+                const double e1x = E.r0.x * dpx + E.r0.y * dpy, e1y = E.r1.x * dpx + E.r1.y * dpy;
+                const double e2x = E.r0.x * dqx + E.r1.x * dqy, e2y = E.r0.y * dqx + E.r1.y * dqy;
+                const double j1 = (Etp2.x * dpx + Etp2.y * dpy) * inv -
+                                  k * ((Ep1.x * e1x + Ep1.y * e1y) * a2 - B * a1 / F.f1);
+                const double j2 = (Ep1.x * dqx + Ep1.y * dqy) * inv -
+                                  k * ((Etp2.x * e2x + Etp2.y * e2y) * a1 - A * a2 / F.f2);
                 if (VARIANT == RP_SHARED) J[7] = j1 + j2;
                 else { J[7] = j1; J[CF2] = j2; }
             }
-            N.add_row(w, J, rs);
+            N.template add_row<M_S>(w, J, rs);
         }
     }
     if (!(P.scale_reproj > 0.0)) return;
 
-    // ---- reprojection 1 -> 2 ----
+    // ---- reprojection 1 -> 2 : Z = R (a p1) + t ----
     {
         const double a = d1 + F.shift1;
-        const V3 Pt = v3(a * p1.x, a * p1.y, a * p1.z);
-        V3 Z = mul(F.R, Pt);
-        Z = Z + F.t;
+        const double Px = a * px, Py = a * py, Pz = a;
+        const V3 Z = v3(R.r0.x * Px + R.r0.y * Py + R.r0.z * Pz + F.t.x, R.r1.x * Px + R.r1.y * Py + R.r1.z * Pz + F.t.y,
+                        R.r2.x * Px + R.r2.y * Py + R.r2.z * Pz + F.t.z);
         if (Z.z > 0.0) {
             const double iz = 1.0 / Z.z;
             const double u0 = Z.x * iz, u1 = Z.y * iz;
@@ -198,37 +238,47 @@ RP_HD void point_accumulate(const LMFrame &F, const LMParams &P, double x1_0, do
                 double J0[NP], J1[NP];
 #pragma unroll
                 for (int i = 0; i < NP; ++i) { J0[i] = 0.0; J1[i] = 0.0; }
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    const V3 dZ = mul(F.R, cross(unit(i), Pt));
-                    J0[i] = g * (dZ.x - u0 * dZ.z);
-                    J1[i] = g * (dZ.y - u1 * dZ.z);
-                    const V3 e = unit(i);
-                    J0[3 + i] = g * (e.x - u0 * e.z);
-                    J1[3 + i] = g * (e.y - u1 * e.z);
+                // dZ/dw_i = R (e_i x P):  Py c2 - Pz c1,  Pz c0 - Px c2,  Px c1 - Py c0  (c_j columns of R)
+                {
+                    const double dx = Py * R.r0.z - Pz * R.r0.y, dy = Py * R.r1.z - Pz * R.r1.y, dz = Py * R.r2.z - Pz * R.r2.y;
+                    J0[0] = g * (dx - u0 * dz); J1[0] = g * (dy - u1 * dz);
                 }
+                {
+                    const double dx = Pz * R.r0.x - Px * R.r0.z, dy = Pz * R.r1.x - Px * R.r1.z, dz = Pz * R.r2.x - Px * R.r2.z;
+                    J0[1] = g * (dx - u0 * dz); J1[1] = g * (dy - u1 * dz);
+                }
+                {
+                    const double dx = Px * R.r0.y - Py * R.r0.x, dy = Px * R.r1.y - Py * R.r1.x, dz = Px * R.r2.y - Py * R.r2.x;
+                    J0[2] = g * (dx - u0 * dz); J1[2] = g * (dy - u1 * dz);
+                }
+                // dZ/dt = I
+                J0[3] = g; J0[5] = -g * u0;
+                J1[4] = g; J1[5] = -g * u1;
                 if (VARIANT == RP_CALIB_SHIFT) {
-                    const V3 dZ = mul(F.R, p1);
-                    J0[7] = g * (dZ.x - u0 * dZ.z);
-                    J1[7] = g * (dZ.y - u1 * dZ.z);
+                    // dZ/dshift1 = R p1
+                    const double dx = R.r0.x * px + R.r0.y * py + R.r0.z, dy = R.r1.x * px + R.r1.y * py + R.r1.z,
+                                 dz = R.r2.x * px + R.r2.y * py + R.r2.z;
+                    J0[7] = g * (dx - u0 * dz); J1[7] = g * (dy - u1 * dz);
                 }
                 if (FOCAL) {
-                    const V3 dZ = mul(F.R, v3(-a * p1.x / F.f1, -a * p1.y / F.f1, 0.0));
-                    J0[7] = g * (dZ.x - u0 * dZ.z);
-                    J1[7] = g * (dZ.y - u1 * dZ.z);
-                    J0[CF2] += u0;
-                    J1[CF2] += u1;
+                    // dZ/df1 = R (-a px/f1, -a py/f1, 0) ; d(pi)/df2 = (u0, u1)
+                    const double ex = -Px / F.f1, ey = -Py / F.f1;
+                    const double dx = R.r0.x * ex + R.r0.y * ey, dy = R.r1.x * ex + R.r1.y * ey, dz = R.r2.x * ex + R.r2.y * ey;
+                    J0[7] = g * (dx - u0 * dz); J1[7] = g * (dy - u1 * dz);
+                    J0[CF2] += u0; J1[CF2] += u1;
                 }
-                N.add_row(w, J0, r0);
-                N.add_row(w, J1, r1);
+                N.template add_row<M_12>(w, J0, r0);
+                N.template add_row<M_12>(w, J1, r1);
             }
         }
     }
-    // ---- reprojection 2 -> 1 ----
+    // ---- reprojection 2 -> 1 : Y = R^T (b p2 - t) ----
     {
         const double bb = d2 + F.shift2;
         const double b = F.scale * bb;
-        const V3 Y = mulT(F.R, v3(b * p2.x - F.t.x, b * p2.y - F.t.y, b * p2.z - F.t.z));
+        const double Qx = b * qx - F.t.x, Qy = b * qy - F.t.y, Qz = b - F.t.z;
+        const V3 Y = v3(R.r0.x * Qx + R.r1.x * Qy + R.r2.x * Qz, R.r0.y * Qx + R.r1.y * Qy + R.r2.y * Qz,
+                        R.r0.z * Qx + R.r1.z * Qy + R.r2.z * Qz);
         if (Y.z > 0.0) {
             const double iz = 1.0 / Y.z;
             const double u0 = Y.x * iz, u1 = Y.y * iz;
@@ -240,34 +290,29 @@ RP_HD void point_accumulate(const LMFrame &F, const LMParams &P, double x1_0, do
                 double J0[NP], J1[NP];
 #pragma unroll
                 for (int i = 0; i < NP; ++i) { J0[i] = 0.0; J1[i] = 0.0; }
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    const V3 dY = cross(Y, unit(i));
-                    J0[i] = g * (dY.x - u0 * dY.z);
-                    J1[i] = g * (dY.y - u1 * dY.z);
-                    const V3 dT = neg(row(F.R, i));
-                    J0[3 + i] = g * (dT.x - u0 * dT.z);
-                    J1[3 + i] = g * (dT.y - u1 * dT.z);
-                }
-                {
-                    const V3 dY = mulT(F.R, v3(bb * p2.x, bb * p2.y, bb * p2.z));
-                    J0[6] = g * (dY.x - u0 * dY.z);
-                    J1[6] = g * (dY.y - u1 * dY.z);
-                }
-                if (VARIANT == RP_CALIB_SHIFT) {
-                    const V3 dY = mulT(F.R, v3(F.scale * p2.x, F.scale * p2.y, F.scale * p2.z));
-                    J0[8] = g * (dY.x - u0 * dY.z);
-                    J1[8] = g * (dY.y - u1 * dY.z);
-                }
+                // dY/dw_i = Y x e_i:  (0, Yz, -Yy), (-Yz, 0, Yx), (Yy, -Yx, 0)
+                J0[0] = g * (u0 * Y.y);          J1[0] = g * (Y.z + u1 * Y.y);
+                J0[1] = g * (-Y.z - u0 * Y.x);   J1[1] = g * (-u1 * Y.x);
+                J0[2] = g * Y.y;                 J1[2] = -g * Y.x;
+                // dY/dt_i = -row_i(R)
+                J0[3] = g * (u0 * R.r0.z - R.r0.x); J1[3] = g * (u1 * R.r0.z - R.r0.y);
+                J0[4] = g * (u0 * R.r1.z - R.r1.x); J1[4] = g * (u1 * R.r1.z - R.r1.y);
+                J0[5] = g * (u0 * R.r2.z - R.r2.x); J1[5] = g * (u1 * R.r2.z - R.r2.y);
+                // dY/dscale = R^T ((d2+v) p2),  dY/dshift2 = R^T (scale p2): both along m = R^T p2
+                const double mx = R.r0.x * qx + R.r1.x * qy + R.r2.x, my = R.r0.y * qx + R.r1.y * qy + R.r2.y,
+                             mz = R.r0.z * qx + R.r1.z * qy + R.r2.z;
+                const double m0 = g * (mx - u0 * mz), m1 = g * (my - u1 * mz);
+                J0[6] = bb * m0; J1[6] = bb * m1;
+                if (VARIANT == RP_CALIB_SHIFT) { J0[8] = F.scale * m0; J1[8] = F.scale * m1; }
                 if (FOCAL) {
-                    const V3 dY = mulT(F.R, v3(-b * p2.x / F.f2, -b * p2.y / F.f2, 0.0));
-                    J0[CF2] += g * (dY.x - u0 * dY.z);
-                    J1[CF2] += g * (dY.y - u1 * dY.z);
-                    J0[7] += u0;
-                    J1[7] += u1;
+                    // dY/df2 = R^T (-b qx/f2, -b qy/f2, 0) ; d(pi1)/df1 = (u0, u1)
+                    const double ex = -b * qx / F.f2, ey = -b * qy / F.f2;
+                    const double dx = R.r0.x * ex + R.r1.x * ey, dy = R.r0.y * ex + R.r1.y * ey, dz = R.r0.z * ex + R.r1.z * ey;
+                    J0[CF2] += g * (dx - u0 * dz); J1[CF2] += g * (dy - u1 * dz);
+                    J0[7] += u0; J1[7] += u1;
                 }
-                N.add_row(w, J0, r0);
-                N.add_row(w, J1, r1);
+                N.template add_row<M_21>(w, J0, r0);
+                N.template add_row<M_21>(w, J1, r1);
             }
         }
     }

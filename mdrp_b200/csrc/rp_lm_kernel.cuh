@@ -1,0 +1,175 @@
+// rp_lm_kernel.cuh — batched Levenberg-Marquardt kernel (compiled in its own translation unit,
+// repose_lm.cu, WITH FMA contraction: this path is not bit-pinned).
+#pragma once
+#include "rp_types.cuh"
+#include "rp_lm.cuh"
+
+namespace rp {
+
+// ---------------------------------------------------------------------------------------------
+// lm: lm_impl<> of PoseLib bundle.cc, one block per problem (persistent over the problem list).
+// JtJ + lambda I (lower LLT), accept when the cost decreases (lambda /= 10, recompute J) else
+// lambda *= 10; stop on |J^T r| < gradient_tol or |step| < step_tol.
+struct LMArgs {
+    const int *prob_list;  // indices into models (null: identity)
+    const int *n_prob;
+    int prob_per_pair;     // pair = index / prob_per_pair
+    const PairParams *pairs;
+    const Pt64 *pts64;
+    const double *d1, *d2;
+    const unsigned char *mask;   // optional per-correspondence subset
+    const int *enable;           // optional per-pair switch (final refinement: num_inliers > 3)
+    Model *models;
+    int use_final;               // 0: LO options (25 its, TRUNCATED, lo_loss_scale); 1: user bundle options
+    int max_iterations, loss_type;
+    double weight_sampson, gradient_tol, step_tol, initial_lambda, min_lambda, max_lambda;
+    double loss_scale_override;  // >0: stage entry point passes its own loss scale / scale_reproj
+    double scale_reproj_override;
+    rp_bundle_stats *stats;      // optional, per problem index
+    unsigned long long *lm_iters;
+};
+
+template <int NP>
+RP_D void warp_reduce_normal(NormalEq<NP> &N) {
+#pragma unroll
+    for (int i = 0; i < NP * (NP + 1) / 2; ++i) N.A[i] = warp_sum(N.A[i]);
+#pragma unroll
+    for (int i = 0; i < NP; ++i) N.g[i] = warp_sum(N.g[i]);
+}
+
+template <int VARIANT, int NP>
+__global__ void __launch_bounds__(LM_THREADS) lm_kernel(LMArgs a) {
+    constexpr int NA = NP * (NP + 1) / 2;
+    __shared__ Model cur, trial;
+    __shared__ double red[LM_WARPS][NA + NP];
+    __shared__ double sA[NA], sg[NP];
+    __shared__ double cred[LM_WARPS];
+    __shared__ int stop_s;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int n_prob = *a.n_prob;
+    for (int pj = blockIdx.x; pj < n_prob; pj += gridDim.x) {
+        const int prob = a.prob_list ? a.prob_list[pj] : pj;
+        const int pair = prob / a.prob_per_pair;
+        const PairParams pp = a.pairs[pair];
+        if (!pp.valid) continue;
+        if (a.enable && !a.enable[pair]) continue;
+        LMParams P;
+        P.weight_sampson = a.weight_sampson;
+        P.scale_reproj = a.scale_reproj_override >= 0.0 ? a.scale_reproj_override : pp.scale_reproj;
+        if (a.use_final) {
+            P.loss_type = a.loss_type;
+            P.loss_scale = a.loss_scale_override > 0.0 ? a.loss_scale_override : pp.final_loss_scale;
+        } else {
+            P.loss_type = RP_LOSS_TRUNCATED;
+            P.loss_scale = pp.lo_loss_scale;
+        }
+        const int max_it = a.use_final ? a.max_iterations : 25;
+        const int n = pp.n;
+        const Pt64 *pts = a.pts64 + pp.off;
+        const double *d1 = a.d1 + pp.off, *d2 = a.d2 + pp.off;
+        const unsigned char *mask = a.mask ? a.mask + pp.off : nullptr;
+        __syncthreads();
+        if (tid == 0) { cur = a.models[prob]; stop_s = 0; }
+        __syncthreads();
+
+        auto block_cost = [&](const Model &m) -> double {
+            const LMFrame F = make_frame(m);
+            double c = 0.0;
+            for (int k = tid; k < n; k += LM_THREADS) {
+                if (mask && !mask[k]) continue;
+                const Pt64 p = pts[k];
+                c += point_cost<VARIANT>(F, P, p.x1_0, p.x1_1, p.x2_0, p.x2_1, d1[k], d2[k]);
+            }
+            c = warp_sum(c);
+            __syncthreads();
+            if (lane == 0) cred[wid] = c;
+            __syncthreads();
+            double tot = 0.0;
+#pragma unroll
+            for (int w = 0; w < LM_WARPS; ++w) tot += cred[w];
+            return tot;
+        };
+
+        double cost = block_cost(cur);
+        const double initial_cost = cost;
+        double lambda = a.initial_lambda;
+        double grad_norm = -1.0, step_norm = -1.0;
+        long long invalid_steps = 0;
+        bool recompute = true;
+        int it = 0;
+        for (; it < max_it; ++it) {
+            if (recompute) {
+                const LMFrame F = make_frame(cur);
+                NormalEq<NP> N;
+                N.clear();
+                for (int k = tid; k < n; k += LM_THREADS) {
+                    if (mask && !mask[k]) continue;
+                    const Pt64 p = pts[k];
+                    point_accumulate<VARIANT, NP>(F, P, p.x1_0, p.x1_1, p.x2_0, p.x2_1, d1[k], d2[k], N);
+                }
+                warp_reduce_normal<NP>(N);
+                if (lane == 0) {
+#pragma unroll
+                    for (int i = 0; i < NA; ++i) red[wid][i] = N.A[i];
+#pragma unroll
+                    for (int i = 0; i < NP; ++i) red[wid][NA + i] = N.g[i];
+                }
+                __syncthreads();
+                if (tid < NA + NP) {
+                    double v = 0.0;
+#pragma unroll
+                    for (int w = 0; w < LM_WARPS; ++w) v += red[w][tid];
+                    if (tid < NA) sA[tid] = v; else sg[tid - NA] = v;
+                }
+                __syncthreads();
+                double g2 = 0.0;
+#pragma unroll
+                for (int i = 0; i < NP; ++i) g2 += sg[i] * sg[i];
+                grad_norm = sqrt(g2);
+                if (grad_norm < a.gradient_tol) break;  // uniform: every thread reads the same sg
+            }
+            if (tid == 0) {
+                double x[NP];
+                llt_solve<NP>(sA, lambda, sg, x);
+                double sn = 0.0;
+#pragma unroll
+                for (int i = 0; i < NP; ++i) { x[i] = -x[i]; sn += x[i] * x[i]; }
+                cred[0] = sqrt(sn);
+                if (sqrt(sn) < a.step_tol) stop_s = 1;
+                else trial = model_step<VARIANT>(cur, x);
+            }
+            __syncthreads();
+            step_norm = cred[0];
+            if (stop_s) break;
+            const double cost_new = block_cost(trial);
+            if (cost_new < cost) {
+                __syncthreads();
+                if (tid == 0) cur = trial;
+                lambda = fmax(a.min_lambda, lambda / 10);
+                cost = cost_new;
+                recompute = true;
+            } else {
+                ++invalid_steps;
+                lambda = fmin(a.max_lambda, lambda * 10);
+                recompute = false;
+            }
+            __syncthreads();
+        }
+        __syncthreads();
+        if (tid == 0) {
+            a.models[prob] = cur;
+            if (a.stats) {
+                rp_bundle_stats s;
+                s.iterations = it; s.initial_cost = initial_cost; s.cost = cost; s.lambda = lambda;
+                s.invalid_steps = invalid_steps; s.step_norm = step_norm; s.grad_norm = grad_norm;
+                a.stats[prob] = s;
+            }
+            if (a.lm_iters) atomicAdd(a.lm_iters, (unsigned long long)it);
+        }
+    }
+}
+
+// defined in repose_lm.cu; returns the cudaError_t of the launch
+int launch_lm_kernel(int sms, int variant, const LMArgs &a, cudaStream_t st);
+
+}  // namespace rp
