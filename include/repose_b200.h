@@ -167,7 +167,8 @@ RP_API int rp_measure_pipes(rp_ctx *ctx, double *fp64_tflops, double *fp32_tflop
  * [0] prepare, [1] sample, [2] solve, [3] score(minimal), [4] scan, [5] LO refine,
  * [6] LO score+merge, [7] final refine, [8] total device, [9] H2D, [10] D2H;
  * counters: [0] hypotheses scored, [1] point-scores, [2] LO problems, [3] LM iterations,
- * [4] chunks (= launches of each pipeline kernel), [5] reserved */
+ * [4] chunks (= launches of each pipeline kernel), [5] minimal models that needed the exact scorer
+ *     (the rest were proven irrelevant by the FP32 bound kernel) */
 RP_API int rp_last_timing(const rp_ctx *ctx, double *ms11, int64_t *counters6);
 
 #ifdef __cplusplus

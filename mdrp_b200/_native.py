@@ -130,7 +130,7 @@ def _ptr(a):
 
 TIMING_KEYS = ["prepare", "sample", "solve", "score_minimal", "scan", "lo_refine", "lo_score_merge",
                "final_refine", "device_total", "h2d", "d2h"]
-COUNTER_KEYS = ["hypotheses", "point_scores", "lm_problems", "lm_iterations", "chunks", "reserved"]
+COUNTER_KEYS = ["hypotheses", "point_scores", "lm_problems", "lm_iterations", "chunks", "exact_models"]
 
 
 class Context:

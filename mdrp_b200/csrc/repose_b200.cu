@@ -44,12 +44,14 @@ struct DevBuf {
 enum { B_OFFS, B_PAIRS, B_PTS64, B_PTS32, B_BEAR, B_SAMPLES, B_MODELS, B_HYPITER, B_SCORE, B_COUNT, B_SEGCNT,
        B_ITEMPFX, B_SCALARS, B_EVENTS, B_NEVENTS, B_LOMODELS, B_LOOFEV, B_LOCOUNT, B_PROBLIST, B_LOSCORE,
        B_LOCNT, B_LOITEMPFX, B_BEST, B_FINSTART, B_FINSCORE, B_FINCNT, B_ONES, B_ONEPFX, B_ENABLE, B_STATS,
+       B_UB, B_LB, B_FIRSTCNT, B_FIRSTPFX, B_B0, B_S0, B_SURVLIST, B_SURVCNT, B_SURVPFX,
        B_MASK, B_IN_X1, B_IN_X2, B_IN_D1, B_IN_D2, B_IN_CAMS, B_TMP0, B_TMP1, B_TMP2, B_NBUF };
 
 // device scalars living in B_SCALARS
 struct Scalars {
-    int n_items, n_lo_items, n_one_items, n_prob, n_pairs_scalar, overflow, need_more, pad1;
-    unsigned long long point_scores, lm_iters;
+    int n_items, n_lo_items, n_one_items, n_prob, n_pairs_scalar, overflow, need_more, n_first_items;
+    int n_surv_items, pad0, pad1, pad2;
+    unsigned long long point_scores, lm_iters, n_survivors;
     long long n_hyp;
 };
 
@@ -66,8 +68,9 @@ struct rp_ctx {
     DevBuf buf[B_NBUF];
     cudaEvent_t ev[N_EVENTS];
     double last_ms[11] = {0};
-    int64_t last_cnt[6] = {0};
+    int64_t last_cnt[6] = {0};  // [5] = models that went through the exact kernel
     size_t workspace_budget = (size_t)12 << 30;
+    bool prune = true;  // hypothesis-level pruning (RP_NO_PRUNE=1 scores every minimal model exactly)
     int occ_score[4] = {0}, occ_lm[4] = {0};
 };
 
@@ -115,6 +118,13 @@ int launch_score(rp_ctx *ctx, bool pose, bool mask, const ScoreArgs &a, cudaStre
         if (mask) { grid = occupancy_grid(ctx, score_kernel<false, true>, SCORE_THREADS); score_kernel<false, true><<<grid, SCORE_THREADS, 0, st>>>(a); }
         else { grid = occupancy_grid(ctx, score_kernel<false, false>, SCORE_THREADS); score_kernel<false, false><<<grid, SCORE_THREADS, 0, st>>>(a); }
     }
+    LAUNCHED();
+    return RP_OK;
+}
+
+int launch_bound(rp_ctx *ctx, bool pose, const BoundArgs &a, cudaStream_t st) {
+    if (pose) bound_kernel<true><<<occupancy_grid(ctx, bound_kernel<true>, SCORE_THREADS), SCORE_THREADS, 0, st>>>(a);
+    else bound_kernel<false><<<occupancy_grid(ctx, bound_kernel<false>, SCORE_THREADS), SCORE_THREADS, 0, st>>>(a);
     LAUNCHED();
     return RP_OK;
 }
@@ -224,6 +234,17 @@ int run_chunk(rp_ctx *ctx, int variant, const rp_options &opt, const ChunkIO &io
     CK(B[B_ONEPFX].reserve(sizeof(int) * (P + 1)));
     CK(B[B_ENABLE].reserve(sizeof(int) * P));
     CK(B[B_STATS].reserve(sizeof(rp_stats) * P));
+    if (ctx->prune) {
+        CK(B[B_UB].reserve(sizeof(int) * slots));
+        CK(B[B_LB].reserve(sizeof(float) * slots));
+        CK(B[B_SURVLIST].reserve(sizeof(int) * slots));
+        CK(B[B_FIRSTCNT].reserve(sizeof(int) * P));
+        CK(B[B_FIRSTPFX].reserve(sizeof(int) * (P + 1)));
+        CK(B[B_B0].reserve(sizeof(int) * P));
+        CK(B[B_S0].reserve(sizeof(double) * P));
+        CK(B[B_SURVCNT].reserve(sizeof(int) * P));
+        CK(B[B_SURVPFX].reserve(sizeof(int) * (P + 1)));
+    }
 
     Scalars *sc = B[B_SCALARS].as<Scalars>();
     PairParams *pairs = B[B_PAIRS].as<PairParams>();
@@ -276,13 +297,50 @@ int run_chunk(rp_ctx *ctx, int variant, const rp_options &opt, const ChunkIO &io
     // 4. score the minimal models
     ScoreArgs sa;
     sa.pairs = pairs; sa.pts32 = pts32; sa.pts64 = pts64; sa.bear = bear; sa.mask = nullptr;
-    {
-        build_items_kernel<<<1, 1024, 0, st>>>(P * nseg, seg_count, item_prefix, &sc->n_items, &sc->n_hyp);
-        LAUNCHED();
+    sa.slot_list = nullptr; sa.list_stride = 0;
+    build_items_kernel<<<1, 1024, 0, st>>>(P * nseg, seg_count, item_prefix, &sc->n_items, &sc->n_hyp);
+    LAUNCHED();
+    if (!ctx->prune) {
         sa.n_groups = P * nseg; sa.grp_stride = 4 * SEG; sa.grp_per_pair = nseg; sa.grp_cnt = seg_count;
         sa.item_prefix = item_prefix; sa.n_items = &sc->n_items; sa.models = models; sa.score = score; sa.count = count;
         sa.point_scores = &sc->point_scores;
         int rc = launch_score(ctx, pose, false, sa, st);
+        if (rc) return rc;
+    } else {
+        // 4a. the first HB models of every pair, exactly -> (B0, S0)
+        int *first_cnt = B[B_FIRSTCNT].as<int>();
+        first_count_kernel<<<cdiv(P, 256), 256, 0, st>>>(P, nseg, seg_count, first_cnt);
+        LAUNCHED();
+        build_items_kernel<<<1, 1024, 0, st>>>(P, first_cnt, B[B_FIRSTPFX].as<int>(), &sc->n_first_items, nullptr);
+        LAUNCHED();
+        sa.n_groups = P; sa.grp_stride = (int)slots_pp; sa.grp_per_pair = 1; sa.grp_cnt = first_cnt;
+        sa.item_prefix = B[B_FIRSTPFX].as<int>(); sa.n_items = &sc->n_first_items; sa.models = models;
+        sa.score = score; sa.count = count; sa.point_scores = &sc->point_scores;
+        int rc = launch_score(ctx, pose, false, sa, st);
+        if (rc) return rc;
+        pair_bounds_kernel<<<cdiv((long long)P * 32, 256), 256, 0, st>>>(P, nseg, first_cnt, score, count,
+                                                                       B[B_B0].as<int>(), B[B_S0].as<double>());
+        LAUNCHED();
+        // 4b. FP32 bounds for all later models
+        BoundArgs ba;
+        ba.n_groups = P * nseg; ba.grp_stride = 4 * SEG; ba.grp_per_pair = nseg; ba.grp_cnt = seg_count;
+        ba.item_prefix = item_prefix; ba.n_items = &sc->n_items; ba.pairs = pairs; ba.models = models; ba.pts32 = pts32;
+        ba.ub = B[B_UB].as<int>(); ba.lb = B[B_LB].as<float>(); ba.point_scores = &sc->point_scores;
+        rc = launch_bound(ctx, pose, ba, st);
+        if (rc) return rc;
+        // 4c. prune, then score the survivors exactly
+        PruneArgs pa;
+        pa.n_pairs = P; pa.nseg = nseg; pa.seg_count = seg_count; pa.ub = ba.ub; pa.lb = ba.lb;
+        pa.B0 = B[B_B0].as<int>(); pa.S0 = B[B_S0].as<double>(); pa.score = score; pa.count = count;
+        pa.surv_list = B[B_SURVLIST].as<int>(); pa.surv_cnt = B[B_SURVCNT].as<int>(); pa.n_survivors = &sc->n_survivors;
+        prune_kernel<<<cdiv((long long)P * 32, 256), 256, 0, st>>>(pa);
+        LAUNCHED();
+        build_items_kernel<<<1, 1024, 0, st>>>(P, pa.surv_cnt, B[B_SURVPFX].as<int>(), &sc->n_surv_items, nullptr);
+        LAUNCHED();
+        ScoreArgs sv = sa;
+        sv.grp_cnt = pa.surv_cnt; sv.item_prefix = B[B_SURVPFX].as<int>(); sv.n_items = &sc->n_surv_items;
+        sv.slot_list = pa.surv_list; sv.list_stride = (int)slots_pp; sv.point_scores = nullptr;
+        rc = launch_score(ctx, pose, false, sv, st);
         if (rc) return rc;
     }
     CK(cudaEventRecord(ev[4], st));
@@ -321,6 +379,7 @@ int run_chunk(rp_ctx *ctx, int variant, const rp_options &opt, const ChunkIO &io
         build_items_kernel<<<1, 1024, 0, st>>>(P, B[B_LOCOUNT].as<int>(), B[B_LOITEMPFX].as<int>(), &sc->n_lo_items, nullptr);
         LAUNCHED();
         ScoreArgs s2 = sa;
+        s2.slot_list = nullptr; s2.list_stride = 0;
         s2.n_groups = P; s2.grp_stride = EV; s2.grp_per_pair = 1; s2.grp_cnt = B[B_LOCOUNT].as<int>();
         s2.item_prefix = B[B_LOITEMPFX].as<int>(); s2.n_items = &sc->n_lo_items; s2.models = B[B_LOMODELS].as<Model>();
         s2.score = B[B_LOSCORE].as<double>(); s2.count = B[B_LOCNT].as<int>(); s2.point_scores = nullptr;
@@ -399,6 +458,7 @@ int run_chunk(rp_ctx *ctx, int variant, const rp_options &opt, const ChunkIO &io
     ctx->last_cnt[2] += h_sc.n_prob + P;
     ctx->last_cnt[3] += (int64_t)h_sc.lm_iters;
     ctx->last_cnt[4] += 1;
+    ctx->last_cnt[5] += ctx->prune ? (int64_t)h_sc.n_survivors + std::min<int64_t>(h_sc.n_hyp, (int64_t)P * HB) : h_sc.n_hyp;
     if (h_sc.overflow) return fail(ctx, RP_ERR_OVERFLOW, "trigger event list overflowed (EV)");
     *need_more = h_sc.need_more != 0;
     return RP_OK;
@@ -407,7 +467,7 @@ int run_chunk(rp_ctx *ctx, int variant, const rp_options &opt, const ChunkIO &io
 size_t bytes_per_pair(int iters, long long avg_points) {
     const int nseg = std::max(1, cdiv(iters, SEG));
     const size_t slots_pp = (size_t)nseg * 4 * SEG;
-    return slots_pp * (sizeof(Model) + 4 + 8 + 4) + (size_t)iters * 12 + (size_t)EV * (sizeof(Model) + 24) +
+    return slots_pp * (sizeof(Model) + 4 + 8 + 4 + 12) + (size_t)iters * 12 + (size_t)EV * (sizeof(Model) + 24) +
            (size_t)avg_points * (sizeof(Pt64) + 16 + sizeof(Bear) + 1) + 1024;
 }
 
@@ -540,6 +600,7 @@ int rp_create(int device, rp_ctx **out) {
         return RP_ERR_CUDA;
     }
     for (auto &ev : ctx->ev) cudaEventCreate(&ev);
+    if (const char *np = getenv("RP_NO_PRUNE")) ctx->prune = !(np[0] == '1');
     if (const char *gb = getenv("RP_WORKSPACE_GB")) {
         const double v = atof(gb);
         if (v > 0.01) ctx->workspace_budget = (size_t)(v * (double)((size_t)1 << 30));
@@ -688,7 +749,7 @@ int rp_score_batch(rp_ctx *ctx, int variant, int64_t n_models, const rp_model *m
     a.item_prefix = B[B_ITEMPFX].as<int>(); a.n_items = &sc->n_items; a.pairs = B[B_PAIRS].as<PairParams>();
     a.models = B[B_MODELS].as<Model>(); a.pts32 = B[B_PTS32].as<float4>(); a.pts64 = B[B_PTS64].as<Pt64>();
     a.bear = B[B_BEAR].as<Bear>(); a.score = B[B_SCORE].as<double>(); a.count = B[B_COUNT].as<int>();
-    a.mask = nullptr; a.point_scores = nullptr;
+    a.mask = nullptr; a.point_scores = nullptr; a.slot_list = nullptr; a.list_stride = 0;
     rc = launch_score(ctx, pose, false, a, st);
     if (rc) return rc;
     std::vector<int> h_cnt((size_t)n_models);

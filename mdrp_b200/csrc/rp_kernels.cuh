@@ -355,6 +355,8 @@ struct ScoreArgs {
     int *count;              // slots
     unsigned char *mask;     // optional, per correspondence; only with one model per pair
     unsigned long long *point_scores;  // optional counter
+    const int *slot_list;    // optional indirection: model i of group e lives at slot
+    int list_stride;         //   e*grp_stride + slot_list[e*list_stride + i]   (survivor lists)
 };
 
 struct HypConst {
@@ -467,8 +469,10 @@ __global__ void __launch_bounds__(SCORE_THREADS) score_kernel(ScoreArgs a) {
         const size_t slot0 = (size_t)e * a.grp_stride + h0;
         const PairParams pp = a.pairs[pair];
         __syncthreads();  // previous item's shared state fully consumed
+        size_t my_slot = slot0 + tid;
+        if (a.slot_list && tid < nh) my_slot = (size_t)e * a.grp_stride + a.slot_list[(size_t)e * a.list_stride + h0 + tid];
         if (tid < nh) {
-            const Model m = a.models[slot0 + tid];
+            const Model m = a.models[my_slot];
             HypConst c;
             c.E = POSE ? essential_from_motion(m.q, m.t) : fundamental_from_model(m);
             c.q = m.q;
@@ -532,10 +536,221 @@ __global__ void __launch_bounds__(SCORE_THREADS) score_kernel(ScoreArgs a) {
             double s = 0.0;
 #pragma unroll
             for (int w = 0; w < SCORE_WARPS; ++w) { c += sh.pcnt[tid][w]; s += sh.psum[tid][w]; }
-            a.count[slot0 + tid] = c;
-            a.score[slot0 + tid] = s + pp.sq_thr * (double)(n - c);
+            a.count[my_slot] = c;
+            a.score[my_slot] = s + pp.sq_thr * (double)(n - c);
         }
         if (a.point_scores && tid == 0) atomicAdd(a.point_scores, (unsigned long long)nh * (unsigned long long)n);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// bound: hypothesis-level pruning.  RANSAC only ever looks at a minimal model when it has MORE inliers
+// than every earlier one or a LOWER score than every earlier one (score_models so@0x22ebc0); a model
+// that provably does neither can be dropped without changing anything downstream.  After the first
+// HB models of a pair have been scored exactly (B0 = their max count, S0 = their min score, both
+// bounds of the running best at every later position), this kernel computes for every later model,
+// from the FP32 tier alone,
+//     ub = #(correspondences that are not certain outliers)            >= inlier count
+//     lb = sum min(r2_lb, thr^2) over those + thr^2 * #certain outliers <= MSAC score
+// with r2_lb = (|C~|-eps)_+^2 / (1.001 den~ + 1012 delta_a^2) (same error model as certain_outlier32:
+// |C| >= |C~|-eps, sqrt(den) <= sqrt(den~)(1+2.1u) + delta_a, (a+b)^2 <= 1.001 a^2 + 1001 b^2).
+// Only models with ub > B0 or lb < S0 go on to the exact kernel.  Lanes are correspondences, two
+// slices (8 points) per lane per pass; no FP64, no queue.
+struct BoundArgs {
+    int n_groups, grp_stride, grp_per_pair;
+    const int *grp_cnt;
+    const int *item_prefix;
+    const int *n_items;
+    const PairParams *pairs;
+    const Model *models;
+    const float4 *pts32;
+    int *ub;       // slots
+    float *lb;     // slots
+    unsigned long long *point_scores;
+};
+
+constexpr int BSG = 2;  // slices per warp pass in the bound kernel
+
+struct BoundShared {
+    Filter32 hf[HB];
+    float kh[HB];
+    int pub[HB][SCORE_WARPS];
+    float plb[HB][SCORE_WARPS];
+};
+
+template <bool POSE>
+__global__ void __launch_bounds__(SCORE_THREADS) bound_kernel(BoundArgs a) {
+    __shared__ BoundShared sh;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int n_items = *a.n_items;
+    const int per = (n_items + gridDim.x - 1) / gridDim.x;
+    const int item_end = min(n_items, (int)(blockIdx.x + 1) * per);
+    for (int item = blockIdx.x * per; item < item_end; ++item) {
+        int lo = 0, hi = a.n_groups;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (a.item_prefix[mid] <= item) lo = mid; else hi = mid;
+        }
+        const int e = lo;
+        const int chunk = item - a.item_prefix[e];
+        if (e % a.grp_per_pair == 0 && chunk == 0) continue;  // the first HB models of a pair are scored exactly
+        const int pair = e / a.grp_per_pair;
+        const int h0 = chunk * HB;
+        const int nh = min(HB, a.grp_cnt[e] - h0);
+        const size_t slot0 = (size_t)e * a.grp_stride + h0;
+        const PairParams pp = a.pairs[pair];
+        __syncthreads();
+        if (tid < nh) {
+            const Model m = a.models[slot0 + tid];
+            const M3 E = POSE ? essential_from_motion(m.q, m.t) : fundamental_from_model(m);
+            const Filter32 f = make_filter32(E, pp.thr, pp.Mmax, pp.mmax);
+            sh.hf[tid] = f;
+            // 1012 * delta_a^2 with delta_a = 16 u Emax m (the sqrt(den) term of eps)
+            const double emax = fmax(fmax(fmax(fabs(E.r0.x), fabs(E.r0.y)), fmax(fabs(E.r0.z), fabs(E.r1.x))),
+                                     fmax(fmax(fabs(E.r1.y), fabs(E.r1.z)), fmax(fmax(fabs(E.r2.x), fabs(E.r2.y)), fabs(E.r2.z))));
+            const double da = 16.0 * 5.9604644775390625e-08 * emax * pp.mmax;
+            sh.kh[tid] = (float)(1012.0 * da * da * 1.0001);
+        }
+        for (int i = tid; i < HB * SCORE_WARPS; i += SCORE_THREADS) {
+            (&sh.pub[0][0])[i] = 0;
+            (&sh.plb[0][0])[i] = 0.f;
+        }
+        __syncthreads();
+        const int n = pp.n;
+        const float thr2_lo = __double2float_rd(pp.sq_thr);
+        const int group_pts = 32 * PT * BSG;
+        const int n_groups_pts = (n + group_pts - 1) / group_pts;
+        for (int sg = wid; sg < n_groups_pts; sg += SCORE_WARPS) {
+            float4 p[PT * BSG];
+            bool valid[PT * BSG];
+            int nvalid = 0;
+#pragma unroll
+            for (int j = 0; j < PT * BSG; ++j) {
+                const int k = sg * group_pts + j * 32 + lane;
+                valid[j] = k < n;
+                nvalid += valid[j];
+                p[j] = valid[j] ? a.pts32[pp.off + k] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            for (int h = 0; h < nh; ++h) {
+                const Filter32 f = sh.hf[h];
+                const float kh = sh.kh[h];
+                int c = 0;
+                float s = 0.f;
+#pragma unroll
+                for (int j = 0; j < PT * BSG; ++j) {
+                    const float a0 = fmaf_(f.e00, p[j].x, fmaf_(f.e01, p[j].y, f.e02));
+                    const float a1 = fmaf_(f.e10, p[j].x, fmaf_(f.e11, p[j].y, f.e12));
+                    const float a2 = fmaf_(f.e20, p[j].x, fmaf_(f.e21, p[j].y, f.e22));
+                    const float b0 = fmaf_(f.e00, p[j].z, fmaf_(f.e10, p[j].w, f.e20));
+                    const float b1 = fmaf_(f.e01, p[j].z, fmaf_(f.e11, p[j].w, f.e21));
+                    const float C = fmaf_(p[j].z, a0, fmaf_(p[j].w, a1, a2));
+                    const float den = fmaf_(a0, a0, fmaf_(a1, a1, fmaf_(b0, b0, b1 * b1)));
+                    const float tt = fmaxf(fabsf(C) - f.eps, 0.0f);
+                    const float t2 = tt * tt;
+                    const bool cand = valid[j] && !(t2 > f.g * den);
+                    const float r = fminf(__fdividef(t2, fmaf_(den, 1.001f, kh)), thr2_lo);
+                    c += cand;
+                    s += cand ? r : thr2_lo;  // (padding lanes are subtracted below)
+                }
+                c = __reduce_add_sync(0xffffffffu, c);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                if (lane == 0) {
+                    sh.pub[h][wid] += c;
+                    sh.plb[h][wid] += s;
+                }
+            }
+            // padding (k >= n) was added as thr2_lo per model: remove it once per pass
+            const int npad = __reduce_add_sync(0xffffffffu, PT * BSG - nvalid);
+            if (npad && lane == 0)
+                for (int h = 0; h < nh; ++h) sh.plb[h][wid] -= (float)npad * thr2_lo * 1.00001f;
+            __syncwarp();
+        }
+        __syncthreads();
+        if (tid < nh) {
+            int c = 0;
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < SCORE_WARPS; ++w) { c += sh.pub[tid][w]; s += (double)sh.plb[tid][w]; }
+            a.ub[slot0 + tid] = c;
+            // FP32 rounding of the terms, of the rcp, of the partial sums: all covered by 1e-4 relative
+            a.lb[slot0 + tid] = __double2float_rd(s * (1.0 - 1e-4));
+        }
+        if (a.point_scores && tid == 0) atomicAdd(a.point_scores, (unsigned long long)nh * (unsigned long long)n);
+    }
+}
+
+// B0 / S0 of a pair: max count and min score over its first `first_cnt` (<= HB) models, scored exactly
+__global__ void pair_bounds_kernel(int n_pairs, int nseg, const int *first_cnt, const double *score, const int *count,
+                                   int *B0, double *S0) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= n_pairs) return;
+    const size_t slot0 = (size_t)warp * nseg * (4 * SEG);
+    const int cnt = first_cnt[warp];
+    int b = 0;
+    double s = DBL_MAX;
+    for (int h = lane; h < cnt; h += 32) {
+        b = max(b, count[slot0 + h]);
+        const double v = score[slot0 + h];
+        if (v == v) s = fmin(s, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        b = max(b, __shfl_xor_sync(0xffffffffu, b, o));
+        s = fmin(s, __shfl_xor_sync(0xffffffffu, s, o));
+    }
+    if (lane == 0) { B0[warp] = b; S0[warp] = s; }
+}
+
+__global__ void first_count_kernel(int n_pairs, int nseg, const int *seg_count, int *first_cnt) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_pairs) first_cnt[i] = min(seg_count[i * nseg], HB);
+}
+
+// prune: survivors (ub > B0 or lb < S0) are compacted, in order, into a per-pair slot list; everything
+// else gets (count 0, score DBL_MAX), which can never trigger.  One warp per pair.
+struct PruneArgs {
+    int n_pairs, nseg;
+    const int *seg_count;
+    const int *ub;
+    const float *lb;
+    const int *B0;
+    const double *S0;
+    double *score;
+    int *count;
+    int *surv_list;   // [n_pairs * nseg*4*SEG] pair-relative slots
+    int *surv_cnt;    // [n_pairs]
+    unsigned long long *n_survivors;
+};
+
+__global__ void prune_kernel(PruneArgs a) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= a.n_pairs) return;
+    const size_t slots_pp = (size_t)a.nseg * (4 * SEG);
+    const size_t pslot = (size_t)warp * slots_pp;
+    const int B0 = a.B0[warp];
+    const double S0 = a.S0[warp];
+    int ns = 0;
+    for (int seg = 0; seg < a.nseg; ++seg) {
+        const int cnt = a.seg_count[warp * a.nseg + seg];
+        const int rel0 = seg * (4 * SEG);
+        for (int base = (seg == 0 ? HB : 0); base < cnt; base += 32) {
+            const int h = base + lane;
+            bool keep = false;
+            if (h < cnt) {
+                keep = a.ub[pslot + rel0 + h] > B0 || (double)a.lb[pslot + rel0 + h] < S0;
+                if (!keep) { a.count[pslot + rel0 + h] = 0; a.score[pslot + rel0 + h] = DBL_MAX; }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (keep) a.surv_list[pslot + ns + __popc(m & ((1u << lane) - 1u))] = rel0 + h;
+            ns += __popc(m);
+        }
+    }
+    if (lane == 0) {
+        a.surv_cnt[warp] = ns;
+        if (a.n_survivors && ns) atomicAdd(a.n_survivors, (unsigned long long)ns);
     }
 }
 

@@ -335,7 +335,9 @@ RP_HD Model model_step(const Model &m, const double *dp) {
 // selfadjointView<Lower>().llt().solve()); a non-PD matrix propagates NaN like Eigen does.
 template <int NP>
 RP_HD void llt_solve(const double *A, double lambda, const double *b, double *x) {
-    double L[NP * (NP + 1) / 2];
+    // one sqrt and one reciprocal per column; the triangular solves multiply by the reciprocals
+    // (the serial part of an LM iteration: keep the slow FP64 ops off its critical path)
+    double L[NP * (NP + 1) / 2], inv[NP];
 #pragma unroll
     for (int j = 0; j < NP; ++j) {
         double s = A[j * (j + 1) / 2 + j] + lambda;
@@ -343,12 +345,13 @@ RP_HD void llt_solve(const double *A, double lambda, const double *b, double *x)
         for (int k = 0; k < j; ++k) s -= L[j * (j + 1) / 2 + k] * L[j * (j + 1) / 2 + k];
         const double d = sqrt(s);
         L[j * (j + 1) / 2 + j] = d;
+        inv[j] = 1.0 / d;
 #pragma unroll
         for (int i = j + 1; i < NP; ++i) {
             double v = A[i * (i + 1) / 2 + j];
 #pragma unroll
             for (int k = 0; k < j; ++k) v -= L[i * (i + 1) / 2 + k] * L[j * (j + 1) / 2 + k];
-            L[i * (i + 1) / 2 + j] = v / d;
+            L[i * (i + 1) / 2 + j] = v * inv[j];
         }
     }
     double y[NP];
@@ -357,14 +360,14 @@ RP_HD void llt_solve(const double *A, double lambda, const double *b, double *x)
         double v = b[i];
 #pragma unroll
         for (int k = 0; k < i; ++k) v -= L[i * (i + 1) / 2 + k] * y[k];
-        y[i] = v / L[i * (i + 1) / 2 + i];
+        y[i] = v * inv[i];
     }
 #pragma unroll
     for (int i = NP - 1; i >= 0; --i) {
         double v = y[i];
 #pragma unroll
         for (int k = i + 1; k < NP; ++k) v -= L[k * (k + 1) / 2 + i] * x[k];
-        x[i] = v / L[i * (i + 1) / 2 + i];
+        x[i] = v * inv[i];
     }
 }
 
