@@ -48,7 +48,7 @@ struct LMParams {
 struct LMFrame {
     M3 R, E;
     V3 t;
-    double scale, shift1, shift2, f1, f2, if1sq, if2sq;
+    double scale, shift1, shift2, f1, f2, if1, if2, if1sq, if2sq;
 };
 
 RP_HD LMFrame make_frame(const Model &m) {
@@ -58,6 +58,8 @@ RP_HD LMFrame make_frame(const Model &m) {
     F.t = m.t;
     F.scale = m.scale; F.shift1 = m.shift1; F.shift2 = m.shift2;
     F.f1 = m.f1; F.f2 = m.f2;
+    F.if1 = 1.0 / m.f1;
+    F.if2 = 1.0 / m.f2;
     F.if1sq = 1.0 / (m.f1 * m.f1);
     F.if2sq = 1.0 / (m.f2 * m.f2);
     return F;
@@ -98,8 +100,9 @@ RP_HD V3 row(const M3 &M, int i) { return i == 0 ? M.r0 : (i == 1 ? M.r1 : M.r2)
 template <int VARIANT>
 RP_HD double point_cost(const LMFrame &F, const LMParams &P, double x1_0, double x1_1, double x2_0, double x2_1,
                         double d1, double d2) {
-    const V3 p1 = v3(x1_0 / F.f1, x1_1 / F.f1, 1.0);
-    const V3 p2 = v3(x2_0 / F.f2, x2_1 / F.f2, 1.0);
+    constexpr bool FOCAL_ = (VARIANT == RP_SHARED || VARIANT == RP_VARYING);
+    const V3 p1 = FOCAL_ ? v3(x1_0 * F.if1, x1_1 * F.if1, 1.0) : v3(x1_0, x1_1, 1.0);
+    const V3 p2 = FOCAL_ ? v3(x2_0 * F.if2, x2_1 * F.if2, 1.0) : v3(x2_0, x2_1, 1.0);
     double cost = 0.0;
     if (P.weight_sampson > 0.0) {
         const V3 Ep1 = mul(F.E, p1), Etp2 = mulT(F.E, p2);
@@ -145,8 +148,8 @@ RP_HD void point_accumulate(const LMFrame &F, const LMParams &P, double x1_0, do
     constexpr unsigned M_S = M_POSE | M_FOC;
     constexpr unsigned M_12 = M_POSE | M_FOC | (VARIANT == RP_CALIB_SHIFT ? 0x80u : 0u);
     constexpr unsigned M_21 = M_POSE | 0x40u | M_FOC | (VARIANT == RP_CALIB_SHIFT ? 0x100u : 0u);
-    const double px = x1_0 / F.f1, py = x1_1 / F.f1;  // p1 = (px, py, 1)
-    const double qx = x2_0 / F.f2, qy = x2_1 / F.f2;  // p2 = (qx, qy, 1)
+    const double px = FOCAL ? x1_0 * F.if1 : x1_0, py = FOCAL ? x1_1 * F.if1 : x1_1;  // p1 = (px, py, 1)
+    const double qx = FOCAL ? x2_0 * F.if2 : x2_0, qy = FOCAL ? x2_1 * F.if2 : x2_1;  // p2 = (qx, qy, 1)
     const M3 &R = F.R;
     const M3 &E = F.E;
     double J[NP];
@@ -206,13 +209,13 @@ RP_HD void point_accumulate(const LMFrame &F, const LMParams &P, double x1_0, do
             }
             if (FOCAL) {
                 // p1 = (x1/f1, 1): dp1/df1 = -(px, py, 0)/f1 ; den = A/f2^2 + B/f1^2
-                const double dpx = -px / F.f1, dpy = -py / F.f1, dqx = -qx / F.f2, dqy = -qy / F.f2;
+                const double dpx = -px * F.if1, dpy = -py * F.if1, dqx = -qx * F.if2, dqy = -qy * F.if2;
                 const double e1x = E.r0.x * dpx + E.r0.y * dpy, e1y = E.r1.x * dpx + E.r1.y * dpy;
                 const double e2x = E.r0.x * dqx + E.r1.x * dqy, e2y = E.r0.y * dqx + E.r1.y * dqy;
                 const double j1 = (Etp2.x * dpx + Etp2.y * dpy) * inv -
-                                  k * ((Ep1.x * e1x + Ep1.y * e1y) * a2 - B * a1 / F.f1);
+                                  k * ((Ep1.x * e1x + Ep1.y * e1y) * a2 - B * a1 * F.if1);
                 const double j2 = (Ep1.x * dqx + Ep1.y * dqy) * inv -
-                                  k * ((Etp2.x * e2x + Etp2.y * e2y) * a1 - A * a2 / F.f2);
+                                  k * ((Etp2.x * e2x + Etp2.y * e2y) * a1 - A * a2 * F.if2);
                 if (VARIANT == RP_SHARED) J[7] = j1 + j2;
                 else { J[7] = j1; J[CF2] = j2; }
             }
@@ -262,7 +265,7 @@ RP_HD void point_accumulate(const LMFrame &F, const LMParams &P, double x1_0, do
                 }
                 if (FOCAL) {
                     // dZ/df1 = R (-a px/f1, -a py/f1, 0) ; d(pi)/df2 = (u0, u1)
-                    const double ex = -Px / F.f1, ey = -Py / F.f1;
+                    const double ex = -Px * F.if1, ey = -Py * F.if1;
                     const double dx = R.r0.x * ex + R.r0.y * ey, dy = R.r1.x * ex + R.r1.y * ey, dz = R.r2.x * ex + R.r2.y * ey;
                     J0[7] = g * (dx - u0 * dz); J1[7] = g * (dy - u1 * dz);
                     J0[CF2] += u0; J1[CF2] += u1;
@@ -306,7 +309,7 @@ RP_HD void point_accumulate(const LMFrame &F, const LMParams &P, double x1_0, do
                 if (VARIANT == RP_CALIB_SHIFT) { J0[8] = F.scale * m0; J1[8] = F.scale * m1; }
                 if (FOCAL) {
                     // dY/df2 = R^T (-b qx/f2, -b qy/f2, 0) ; d(pi1)/df1 = (u0, u1)
-                    const double ex = -b * qx / F.f2, ey = -b * qy / F.f2;
+                    const double ex = -b * qx * F.if2, ey = -b * qy * F.if2;
                     const double dx = R.r0.x * ex + R.r1.x * ey, dy = R.r0.y * ex + R.r1.y * ey, dz = R.r0.z * ex + R.r1.z * ey;
                     J0[CF2] += g * (dx - u0 * dz); J1[CF2] += g * (dy - u1 * dz);
                     J0[7] += u0; J1[7] += u1;
