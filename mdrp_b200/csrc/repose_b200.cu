@@ -326,6 +326,7 @@ int run_chunk(rp_ctx *ctx, int variant, const rp_options &opt, const ChunkIO &io
         ba.n_groups = P * nseg; ba.grp_stride = 4 * SEG; ba.grp_per_pair = nseg; ba.grp_cnt = seg_count;
         ba.item_prefix = item_prefix; ba.n_items = &sc->n_items; ba.pairs = pairs; ba.models = models; ba.pts32 = pts32;
         ba.ub = B[B_UB].as<int>(); ba.lb = B[B_LB].as<float>(); ba.point_scores = &sc->point_scores;
+        ba.B0 = B[B_B0].as<int>(); ba.S0 = B[B_S0].as<double>();
         rc = launch_bound(ctx, pose, ba, st);
         if (rc) return rc;
         // 4c. prune, then score the survivors exactly

@@ -566,20 +566,28 @@ struct BoundArgs {
     const float4 *pts32;
     int *ub;       // slots
     float *lb;     // slots
+    const int *B0;     // per pair: max inlier count / min score over the exactly scored first HB models
+    const double *S0;
     unsigned long long *point_scores;
 };
 
-constexpr int BSG = 2;  // slices per warp pass in the bound kernel
+constexpr int BSG = 2;                       // slices (of 32*PT points) per pass: 8 points per lane
+constexpr int BHW = HB / SCORE_WARPS;        // models per warp (each warp owns its models over ALL points)
 
 struct BoundShared {
     Filter32 hf[HB];
     float kh[HB];
-    int pub[HB][SCORE_WARPS];
-    float plb[HB][SCORE_WARPS];
+    float sp[SCORE_WARPS][BHW][32];  // per-lane partial lower-bound sums of the warp's models
+    int outc[SCORE_WARPS][BHW];      // certain outliers collected so far by each of the warp's models
 };
 
+// Warps split the MODELS of an item (model h belongs to warp h % SCORE_WARPS) and each walks all
+// correspondences of the pair in groups of 256.  A warp therefore knows, after every group, how many
+// certain outliers each of its models has collected, and abandons a model as soon as
+//     out >= N - B0   (final ub <= B0)   and   thr^2 * out >= S0   (final lb >= S0)
+// i.e. as soon as it is certain to be pruned: bad models (the majority) stop after ~1/3 of the points.
 template <bool POSE>
-__global__ void __launch_bounds__(SCORE_THREADS) bound_kernel(BoundArgs a) {
+__global__ void __launch_bounds__(SCORE_THREADS, 3) bound_kernel(BoundArgs a) {
     __shared__ BoundShared sh;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n_items = *a.n_items;
@@ -603,35 +611,44 @@ __global__ void __launch_bounds__(SCORE_THREADS) bound_kernel(BoundArgs a) {
         if (tid < nh) {
             const Model m = a.models[slot0 + tid];
             const M3 E = POSE ? essential_from_motion(m.q, m.t) : fundamental_from_model(m);
-            const Filter32 f = make_filter32(E, pp.thr, pp.Mmax, pp.mmax);
-            sh.hf[tid] = f;
+            sh.hf[tid] = make_filter32(E, pp.thr, pp.Mmax, pp.mmax);
             // 1012 * delta_a^2 with delta_a = 16 u Emax m (the sqrt(den) term of eps)
             const double emax = fmax(fmax(fmax(fabs(E.r0.x), fabs(E.r0.y)), fmax(fabs(E.r0.z), fabs(E.r1.x))),
                                      fmax(fmax(fabs(E.r1.y), fabs(E.r1.z)), fmax(fmax(fabs(E.r2.x), fabs(E.r2.y)), fabs(E.r2.z))));
             const double da = 16.0 * 5.9604644775390625e-08 * emax * pp.mmax;
             sh.kh[tid] = (float)(1012.0 * da * da * 1.0001);
         }
-        for (int i = tid; i < HB * SCORE_WARPS; i += SCORE_THREADS) {
-            (&sh.pub[0][0])[i] = 0;
-            (&sh.plb[0][0])[i] = 0.f;
-        }
         __syncthreads();
         const int n = pp.n;
         const float thr2_lo = __double2float_rd(pp.sq_thr);
+        // abandonment threshold on the number of certain outliers (see header comment)
+        const int B0 = a.B0[pair];
+        const double S0 = a.S0[pair];
+        double need_d = fmax((double)(n - B0), S0 < 1e300 ? ceil(S0 / ((double)thr2_lo * (1.0 - 2e-4))) : 4.0e9);
+        const int need_out = need_d > 2.0e9 ? 0x7fffffff : max((int)need_d, 1);
+        const int my_nh = (nh - wid + SCORE_WARPS - 1) / SCORE_WARPS;  // models h = wid + i*SCORE_WARPS
+        unsigned alive = my_nh >= 32 ? 0xffffffffu : ((1u << my_nh) - 1u);
+        int *out_cnt = sh.outc[wid];
+#pragma unroll
+        for (int i = 0; i < BHW; ++i) sh.sp[wid][i][lane] = 0.f;
+        if (lane < BHW) out_cnt[lane] = 0;
+        __syncwarp();
         const int group_pts = 32 * PT * BSG;
-        const int n_groups_pts = (n + group_pts - 1) / group_pts;
-        for (int sg = wid; sg < n_groups_pts; sg += SCORE_WARPS) {
+        const int n_pgroups = (n + group_pts - 1) / group_pts;
+        for (int g = 0; g < n_pgroups && alive; ++g) {
             float4 p[PT * BSG];
             bool valid[PT * BSG];
-            int nvalid = 0;
 #pragma unroll
             for (int j = 0; j < PT * BSG; ++j) {
-                const int k = sg * group_pts + j * 32 + lane;
+                const int k = g * group_pts + j * 32 + lane;
                 valid[j] = k < n;
-                nvalid += valid[j];
                 p[j] = valid[j] ? a.pts32[pp.off + k] : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            for (int h = 0; h < nh; ++h) {
+            const int nvalid = min(group_pts, n - g * group_pts);
+#pragma unroll 1
+            for (int i = 0; i < my_nh; ++i) {
+                if (!((alive >> i) & 1u)) continue;
+                const int h = wid + i * SCORE_WARPS;
                 const Filter32 f = sh.hf[h];
                 const float kh = sh.kh[h];
                 int c = 0;
@@ -650,31 +667,32 @@ __global__ void __launch_bounds__(SCORE_THREADS) bound_kernel(BoundArgs a) {
                     const bool cand = valid[j] && !(t2 > f.g * den);
                     const float r = fminf(__fdividef(t2, fmaf_(den, 1.001f, kh)), thr2_lo);
                     c += cand;
-                    s += cand ? r : thr2_lo;  // (padding lanes are subtracted below)
+                    s += cand ? r : 0.f;
                 }
-                c = __reduce_add_sync(0xffffffffu, c);
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                if (lane == 0) {
-                    sh.pub[h][wid] += c;
-                    sh.plb[h][wid] += s;
-                }
+                sh.sp[wid][i][lane] += s;
+                const int nc = __reduce_add_sync(0xffffffffu, c);
+                const int oc = out_cnt[i] + nvalid - nc;
+                __syncwarp();
+                if (lane == 0) out_cnt[i] = oc;
+                if (oc >= need_out) alive &= ~(1u << i);  // certain to be pruned: stop here
             }
-            // padding (k >= n) was added as thr2_lo per model: remove it once per pass
-            const int npad = __reduce_add_sync(0xffffffffu, PT * BSG - nvalid);
-            if (npad && lane == 0)
-                for (int h = 0; h < nh; ++h) sh.plb[h][wid] -= (float)npad * thr2_lo * 1.00001f;
-            __syncwarp();
         }
-        __syncthreads();
-        if (tid < nh) {
-            int c = 0;
-            double s = 0.0;
+        // results: abandoned models can never survive the prune (ub = 0, lb = +inf)
+        __syncwarp();
+#pragma unroll 1
+        for (int i = 0; i < my_nh; ++i) {
+            const int h = wid + i * SCORE_WARPS;
+            float s = sh.sp[wid][i][lane];
 #pragma unroll
-            for (int w = 0; w < SCORE_WARPS; ++w) { c += sh.pub[tid][w]; s += (double)sh.plb[tid][w]; }
-            a.ub[slot0 + tid] = c;
-            // FP32 rounding of the terms, of the rcp, of the partial sums: all covered by 1e-4 relative
-            a.lb[slot0 + tid] = __double2float_rd(s * (1.0 - 1e-4));
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) {
+                const bool dead = !((alive >> i) & 1u);
+                a.ub[slot0 + h] = dead ? 0 : n - out_cnt[i];
+                // lb = thr^2 * (#certain outliers) + sum of candidate lower bounds; FP32 rounding of the
+                // terms, the rcp and the partial sums is covered by 1e-4 relative
+                const double lbv = ((double)thr2_lo * (double)out_cnt[i] + (double)s) * (1.0 - 1e-4);
+                a.lb[slot0 + h] = dead ? INFINITY : __double2float_rd(lbv);
+            }
         }
         if (a.point_scores && tid == 0) atomicAdd(a.point_scores, (unsigned long long)nh * (unsigned long long)n);
     }
