@@ -129,9 +129,13 @@ int launch_bound(rp_ctx *ctx, bool pose, const BoundArgs &a, cudaStream_t st) {
     return RP_OK;
 }
 
-int launch_lm(rp_ctx *ctx, int variant, const LMArgs &a, cudaStream_t st) {
+int launch_lm(rp_ctx *ctx, int variant, const LMArgs &a, long long expected_problems, cudaStream_t st) {
     ctx->launches++;
-    CK((cudaError_t)launch_lm_kernel(ctx->sms, variant, a, st));
+    // enough independent problems to fill the machine with one warp each?
+    // (measured on B200: one warp per problem is no faster for LO batches and 3x slower for the
+    // per-pair final refinements, so it stays an opt-in experiment)
+    const bool warp_per_problem = expected_problems >= (long long)ctx->sms * 8 && getenv("RP_LM_WARP") != nullptr;
+    CK((cudaError_t)launch_lm_kernel(ctx->sms, variant, warp_per_problem, a, st));
     return RP_OK;
 }
 
@@ -371,7 +375,7 @@ int run_chunk(rp_ctx *ctx, int variant, const rp_options &opt, const ChunkIO &io
     {
         la.prob_list = B[B_PROBLIST].as<int>(); la.n_prob = &sc->n_prob; la.prob_per_pair = EV;
         la.models = B[B_LOMODELS].as<Model>(); la.use_final = 0;
-        int rc = launch_lm(ctx, variant, la, st);
+        int rc = launch_lm(ctx, variant, la, (long long)P * 8, st);
         if (rc) return rc;
     }
     CK(cudaEventRecord(ev[6], st));
@@ -400,7 +404,7 @@ int run_chunk(rp_ctx *ctx, int variant, const rp_options &opt, const ChunkIO &io
         // final LO from the best model, rescore, accept when strictly better
         la.prob_list = nullptr; la.n_prob = &sc->n_pairs_scalar; la.prob_per_pair = 1;
         la.models = B[B_FINSTART].as<Model>(); la.use_final = 0;
-        rc = launch_lm(ctx, variant, la, st);
+        rc = launch_lm(ctx, variant, la, P, st);
         if (rc) return rc;
         valid_ones_kernel<<<cdiv(P, 256), 256, 0, st>>>(P, pairs, B[B_ONES].as<int>());
         LAUNCHED();
@@ -434,7 +438,7 @@ int run_chunk(rp_ctx *ctx, int variant, const rp_options &opt, const ChunkIO &io
         la.max_iterations = (int)opt.bundle_max_iterations; la.loss_type = opt.loss_type;
         la.gradient_tol = opt.gradient_tol; la.step_tol = opt.step_tol; la.initial_lambda = opt.initial_lambda;
         la.min_lambda = opt.min_lambda; la.max_lambda = opt.max_lambda;
-        int rc = launch_lm(ctx, variant, la, st);
+        int rc = launch_lm(ctx, variant, la, P, st);
         if (rc) return rc;
         finalize_kernel<<<cdiv(P, 256), 256, 0, st>>>(P, variant, pairs, B[B_BEST].as<Model>());
         LAUNCHED();
@@ -816,7 +820,7 @@ int rp_refine_batch(rp_ctx *ctx, int variant, int64_t n_models, rp_model *models
     la.initial_lambda = opt->initial_lambda; la.min_lambda = opt->min_lambda; la.max_lambda = opt->max_lambda;
     la.loss_scale_override = opt->loss_scale; la.scale_reproj_override = scale_reproj;
     la.stats = B[B_TMP2].as<rp_bundle_stats>(); la.lm_iters = nullptr;
-    rc = launch_lm(ctx, variant, la, st);
+    rc = launch_lm(ctx, variant, la, n_models, st);
     if (rc) return rc;
     CK(cudaMemcpyAsync(models, B[B_MODELS].p, sizeof(Model) * (size_t)n_models, cudaMemcpyDeviceToHost, st));
     if (stats) CK(cudaMemcpyAsync(stats, B[B_TMP2].p, sizeof(rp_bundle_stats) * (size_t)n_models, cudaMemcpyDeviceToHost, st));

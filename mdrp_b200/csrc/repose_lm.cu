@@ -12,20 +12,20 @@ static int occupancy_grid(int sms, K kernel, int threads) {
     return nb * sms;
 }
 
-int launch_lm_kernel(int sms, int variant, const LMArgs &a, cudaStream_t st) {
+template <int VARIANT, int NP>
+static void launch_variant(int sms, bool warp_per_problem, const LMArgs &a, cudaStream_t st) {
+    if (warp_per_problem)
+        lm_kernel<VARIANT, NP, 32><<<occupancy_grid(sms, lm_kernel<VARIANT, NP, 32>, 32), 32, 0, st>>>(a);
+    else
+        lm_kernel<VARIANT, NP, 128><<<occupancy_grid(sms, lm_kernel<VARIANT, NP, 128>, 128), 128, 0, st>>>(a);
+}
+
+int launch_lm_kernel(int sms, int variant, bool warp_per_problem, const LMArgs &a, cudaStream_t st) {
     switch (variant) {
-    case RP_CALIB:
-        lm_kernel<RP_CALIB, 7><<<occupancy_grid(sms, lm_kernel<RP_CALIB, 7>, LM_THREADS), LM_THREADS, 0, st>>>(a);
-        break;
-    case RP_CALIB_SHIFT:
-        lm_kernel<RP_CALIB_SHIFT, 9><<<occupancy_grid(sms, lm_kernel<RP_CALIB_SHIFT, 9>, LM_THREADS), LM_THREADS, 0, st>>>(a);
-        break;
-    case RP_SHARED:
-        lm_kernel<RP_SHARED, 8><<<occupancy_grid(sms, lm_kernel<RP_SHARED, 8>, LM_THREADS), LM_THREADS, 0, st>>>(a);
-        break;
-    default:
-        lm_kernel<RP_VARYING, 9><<<occupancy_grid(sms, lm_kernel<RP_VARYING, 9>, LM_THREADS), LM_THREADS, 0, st>>>(a);
-        break;
+    case RP_CALIB: launch_variant<RP_CALIB, 7>(sms, warp_per_problem, a, st); break;
+    case RP_CALIB_SHIFT: launch_variant<RP_CALIB_SHIFT, 9>(sms, warp_per_problem, a, st); break;
+    case RP_SHARED: launch_variant<RP_SHARED, 8>(sms, warp_per_problem, a, st); break;
+    default: launch_variant<RP_VARYING, 9>(sms, warp_per_problem, a, st); break;
     }
     return (int)cudaGetLastError();
 }

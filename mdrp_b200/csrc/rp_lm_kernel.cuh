@@ -37,8 +37,12 @@ RP_D void warp_reduce_normal(NormalEq<NP> &N) {
     for (int i = 0; i < NP; ++i) N.g[i] = warp_sum(N.g[i]);
 }
 
-template <int VARIANT, int NP>
-__global__ void __launch_bounds__(LM_THREADS) lm_kernel(LMArgs a) {
+// THREADS = 128: one block per problem (few problems, e.g. a single pair); THREADS = 32: one warp per
+// problem (large batches: no block barriers, the serial Cholesky of one problem overlaps the others)
+template <int VARIANT, int NP, int THREADS>
+__global__ void __launch_bounds__(THREADS) lm_kernel(LMArgs a) {
+    constexpr int LM_THREADS = THREADS;
+    constexpr int LM_WARPS = THREADS / 32;
     constexpr int NA = NP * (NP + 1) / 2;
     __shared__ Model cur, trial;
     __shared__ double red[LM_WARPS][NA + NP];
@@ -170,6 +174,6 @@ __global__ void __launch_bounds__(LM_THREADS) lm_kernel(LMArgs a) {
 }
 
 // defined in repose_lm.cu; returns the cudaError_t of the launch
-int launch_lm_kernel(int sms, int variant, const LMArgs &a, cudaStream_t st);
+int launch_lm_kernel(int sms, int variant, bool warp_per_problem, const LMArgs &a, cudaStream_t st);
 
 }  // namespace rp

@@ -12,8 +12,6 @@ constexpr int SCORE_THREADS = 256;
 constexpr int SCORE_WARPS = SCORE_THREADS / 32;
 constexpr int PT = 4;              // correspondences per thread per slice
 constexpr int EV = 128;            // trigger events kept per pair
-constexpr int LM_THREADS = 128;
-constexpr int LM_WARPS = LM_THREADS / 32;
 
 struct PairParams {
     long long off;        // first correspondence of this pair in the packed arrays
