@@ -163,13 +163,15 @@ RP_API int rp_refine_batch(rp_ctx *ctx, int variant, int64_t n_models, rp_model 
  * this device, in TFLOP/s (2 flops per FMA). */
 RP_API int rp_measure_pipes(rp_ctx *ctx, double *fp64_tflops, double *fp32_tflops);
 
-/* per-stage device time of the last rp_estimate_batch_* call on ctx, milliseconds:
- * [0] prepare, [1] sample, [2] solve, [3] score(minimal), [4] scan, [5] LO refine,
- * [6] LO score+merge, [7] final refine, [8] total device, [9] H2D, [10] D2H;
- * counters: [0] hypotheses scored, [1] point-scores, [2] LO problems, [3] LM iterations,
- * [4] chunks (= launches of each pipeline kernel), [5] minimal models that needed the exact scorer
- *     (the rest were proven irrelevant by the FP32 bound kernel) */
-RP_API int rp_last_timing(const rp_ctx *ctx, double *ms11, int64_t *counters6);
+/* per-stage device time of the last rp_estimate_batch_* call on ctx, milliseconds (summed over chunks):
+ * [0] prepare, [1] sample, [2] solve, [3] score(minimal: exact head + bound + prune + exact survivors),
+ * [4] scan, [5] LO refine, [6] LO score+merge+final LO, [7] final refine, [8] total device, [9] H2D,
+ * [10] D2H, [11] bound kernel alone, [12..15] reserved.
+ * counters: [0] minimal models generated, [1] point-scores resolved (models x correspondences),
+ * [2] LM problems, [3] LM iterations, [4] chunks (= launches of each pipeline kernel), [5] minimal models
+ * that needed the exact scorer, [6] point-scores the bound kernel actually evaluated (before abandoning),
+ * [7] reserved */
+RP_API int rp_last_timing(const rp_ctx *ctx, double *ms16, int64_t *counters8);
 
 #ifdef __cplusplus
 }

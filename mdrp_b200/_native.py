@@ -129,8 +129,9 @@ def _ptr(a):
 
 
 TIMING_KEYS = ["prepare", "sample", "solve", "score_minimal", "scan", "lo_refine", "lo_score_merge",
-               "final_refine", "device_total", "h2d", "d2h"]
-COUNTER_KEYS = ["hypotheses", "point_scores", "lm_problems", "lm_iterations", "chunks", "exact_models"]
+               "final_refine", "device_total", "h2d", "d2h", "bound_kernel", "r12", "r13", "r14", "r15"]
+COUNTER_KEYS = ["hypotheses", "point_scores", "lm_problems", "lm_iterations", "chunks", "exact_models",
+                "bound_evaluated", "r7"]
 
 
 class Context:
@@ -166,8 +167,8 @@ class Context:
         return int(self._lib.rp_launch_count(self._h))
 
     def last_timing(self):
-        ms = (C.c_double * 11)()
-        cn = (C.c_int64 * 6)()
+        ms = (C.c_double * 16)()
+        cn = (C.c_int64 * 8)()
         self._check(self._lib.rp_last_timing(self._h, ms, cn))
         return dict(zip(TIMING_KEYS, list(ms))), dict(zip(COUNTER_KEYS, list(cn)))
 

@@ -45,17 +45,19 @@ enum { B_OFFS, B_PAIRS, B_PTS64, B_PTS32, B_BEAR, B_SAMPLES, B_MODELS, B_HYPITER
        B_ITEMPFX, B_SCALARS, B_EVENTS, B_NEVENTS, B_LOMODELS, B_LOOFEV, B_LOCOUNT, B_PROBLIST, B_LOSCORE,
        B_LOCNT, B_LOITEMPFX, B_BEST, B_FINSTART, B_FINSCORE, B_FINCNT, B_ONES, B_ONEPFX, B_ENABLE, B_STATS,
        B_UB, B_LB, B_FIRSTCNT, B_FIRSTPFX, B_B0, B_S0, B_SURVLIST, B_SURVCNT, B_SURVPFX,
-       B_MASK, B_IN_X1, B_IN_X2, B_IN_D1, B_IN_D2, B_IN_CAMS, B_TMP0, B_TMP1, B_TMP2, B_NBUF };
+       B_MASK, B_IN_X1, B_IN_X2, B_IN_D1, B_IN_D2, B_IN_CAMS, B_TMP0, B_TMP1, B_TMP2,
+       // second staging set (double buffering of the host path)
+       B_MASK_B, B_IN_X1_B, B_IN_X2_B, B_IN_D1_B, B_IN_D2_B, B_IN_CAMS_B, B_TMP0_B, B_TMP1_B, B_NBUF };
 
 // device scalars living in B_SCALARS
 struct Scalars {
     int n_items, n_lo_items, n_one_items, n_prob, n_pairs_scalar, overflow, need_more, n_first_items;
     int n_surv_items, pad0, pad1, pad2;
-    unsigned long long point_scores, lm_iters, n_survivors;
+    unsigned long long point_scores, lm_iters, n_survivors, evaluated_ps;
     long long n_hyp;
 };
 
-constexpr int N_EVENTS = 12;
+constexpr int N_EVENTS = 24;
 
 }  // namespace
 
@@ -65,10 +67,11 @@ struct rp_ctx {
     std::string err;
     int64_t launches = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // H2D of chunk c+1 / D2H of chunk c-1 overlap the kernels of chunk c
     DevBuf buf[B_NBUF];
     cudaEvent_t ev[N_EVENTS];
-    double last_ms[11] = {0};
-    int64_t last_cnt[6] = {0};  // [5] = models that went through the exact kernel
+    double last_ms[16] = {0};
+    int64_t last_cnt[8] = {0};  // [5] models through the exact kernel, [6] point-scores the bound kernel evaluated
     size_t workspace_budget = (size_t)12 << 30;
     bool prune = true;  // hypothesis-level pruning (RP_NO_PRUNE=1 scores every minimal model exactly)
     int occ_score[4] = {0}, occ_lm[4] = {0};
@@ -331,8 +334,11 @@ int run_chunk(rp_ctx *ctx, int variant, const rp_options &opt, const ChunkIO &io
         ba.item_prefix = item_prefix; ba.n_items = &sc->n_items; ba.pairs = pairs; ba.models = models; ba.pts32 = pts32;
         ba.ub = B[B_UB].as<int>(); ba.lb = B[B_LB].as<float>(); ba.point_scores = &sc->point_scores;
         ba.B0 = B[B_B0].as<int>(); ba.S0 = B[B_S0].as<double>();
+        ba.evaluated = &sc->evaluated_ps;
+        CK(cudaEventRecord(ev[20], st));
         rc = launch_bound(ctx, pose, ba, st);
         if (rc) return rc;
+        CK(cudaEventRecord(ev[21], st));
         // 4c. prune, then score the survivors exactly
         PruneArgs pa;
         pa.n_pairs = P; pa.nseg = nseg; pa.seg_count = seg_count; pa.ub = ba.ub; pa.lb = ba.lb;
@@ -463,6 +469,12 @@ int run_chunk(rp_ctx *ctx, int variant, const rp_options &opt, const ChunkIO &io
     ctx->last_cnt[2] += h_sc.n_prob + P;
     ctx->last_cnt[3] += (int64_t)h_sc.lm_iters;
     ctx->last_cnt[4] += 1;
+    ctx->last_cnt[6] += (int64_t)h_sc.evaluated_ps;
+    if (ctx->prune) {
+        float msb = 0.f;
+        CK(cudaEventElapsedTime(&msb, ev[20], ev[21]));
+        ctx->last_ms[11] += msb;
+    }
     ctx->last_cnt[5] += ctx->prune ? (int64_t)h_sc.n_survivors + std::min<int64_t>(h_sc.n_hyp, (int64_t)P * HB) : h_sc.n_hyp;
     if (h_sc.overflow) return fail(ctx, RP_ERR_OVERFLOW, "trigger event list overflowed (EV)");
     *need_more = h_sc.need_more != 0;
@@ -510,34 +522,59 @@ int estimate_impl(rp_ctx *ctx, int variant, int64_t n_pairs, const int64_t *offs
     chunk = std::min<int64_t>(chunk, 32768);
     std::vector<long long> rel;
     DevBuf *B = ctx->buf;
-    for (int64_t p0 = 0; p0 < n_pairs; p0 += chunk) {
-        const int64_t p1 = std::min(n_pairs, p0 + chunk);
-        const int P = (int)(p1 - p0);
+    const int64_t n_chunks = (n_pairs + chunk - 1) / chunk;
+    // Host path: double-buffered staging.  The copy stream uploads chunk c+1 and downloads chunk c-1
+    // while the compute stream runs the kernels of chunk c (pinned host memory makes this truly async).
+    static const int IN_X1[2] = {B_IN_X1, B_IN_X1_B}, IN_X2[2] = {B_IN_X2, B_IN_X2_B}, IN_D1[2] = {B_IN_D1, B_IN_D1_B},
+                     IN_D2[2] = {B_IN_D2, B_IN_D2_B}, IN_CAMS[2] = {B_IN_CAMS, B_IN_CAMS_B}, OUT_M[2] = {B_TMP0, B_TMP0_B},
+                     OUT_S[2] = {B_TMP1, B_TMP1_B}, OUT_K[2] = {B_MASK, B_MASK_B};
+    cudaStream_t cs = ctx->copy_stream;
+    cudaEvent_t *in_ready = &ctx->ev[12], *h2d_begin = &ctx->ev[14], *comp_done = &ctx->ev[16], *d2h_begin = &ctx->ev[18];
+    cudaEvent_t d2h_end = ctx->ev[11];
+    auto upload = [&](int64_t c) -> int {
+        const int64_t p0 = c * chunk, p1 = std::min(n_pairs, p0 + chunk);
+        const int P = (int)(p1 - p0), par = (int)(c & 1);
+        const long long o0 = offsets[p0], N = offsets[p1] - o0;
+        const size_t nn = (size_t)std::max<long long>(N, 1);
+        CK(B[IN_X1[par]].reserve(16 * nn)); CK(B[IN_X2[par]].reserve(16 * nn));
+        CK(B[IN_D1[par]].reserve(8 * nn)); CK(B[IN_D2[par]].reserve(8 * nn));
+        CK(B[IN_CAMS[par]].reserve(64 * (size_t)P));
+        CK(B[OUT_M[par]].reserve(sizeof(Model) * P)); CK(B[OUT_S[par]].reserve(sizeof(rp_stats) * P));
+        CK(B[OUT_K[par]].reserve(nn));
+        CK(cudaEventRecord(h2d_begin[par], cs));
+        CK(cudaMemcpyAsync(B[IN_X1[par]].p, x1 + 2 * o0, 16 * (size_t)N, cudaMemcpyHostToDevice, cs));
+        CK(cudaMemcpyAsync(B[IN_X2[par]].p, x2 + 2 * o0, 16 * (size_t)N, cudaMemcpyHostToDevice, cs));
+        CK(cudaMemcpyAsync(B[IN_D1[par]].p, d1 + o0, 8 * (size_t)N, cudaMemcpyHostToDevice, cs));
+        CK(cudaMemcpyAsync(B[IN_D2[par]].p, d2 + o0, 8 * (size_t)N, cudaMemcpyHostToDevice, cs));
+        if (pose) CK(cudaMemcpyAsync(B[IN_CAMS[par]].p, cams + 8 * p0, 64 * (size_t)P, cudaMemcpyHostToDevice, cs));
+        CK(cudaEventRecord(in_ready[par], cs));
+        return RP_OK;
+    };
+    if (host_io) {
+        rc = upload(0);
+        if (rc) return rc;
+    }
+    for (int64_t c = 0; c < n_chunks; ++c) {
+        const int64_t p0 = c * chunk, p1 = std::min(n_pairs, p0 + chunk);
+        const int P = (int)(p1 - p0), par = (int)(c & 1);
         const long long o0 = offsets[p0], N = offsets[p1] - o0;
         rel.resize(P + 1);
         for (int i = 0; i <= P; ++i) rel[i] = offsets[p0 + i] - o0;
         ChunkIO io;
         io.n_pairs = P; io.n_points = N; io.h_offsets_rel = rel.data();
-        cudaEvent_t e0 = ctx->ev[9], e1 = ctx->ev[10], e2 = ctx->ev[11];
         if (host_io) {
-            const size_t nn = (size_t)std::max<long long>(N, 1);
-            CK(B[B_IN_X1].reserve(16 * nn)); CK(B[B_IN_X2].reserve(16 * nn));
-            CK(B[B_IN_D1].reserve(8 * nn)); CK(B[B_IN_D2].reserve(8 * nn));
-            CK(B[B_IN_CAMS].reserve(64 * (size_t)P));
-            CK(B[B_TMP0].reserve(sizeof(Model) * P)); CK(B[B_TMP1].reserve(sizeof(rp_stats) * P));
-            CK(B[B_MASK].reserve(nn));
-            CK(cudaEventRecord(e0, st));
-            CK(cudaMemcpyAsync(B[B_IN_X1].p, x1 + 2 * o0, 16 * (size_t)N, cudaMemcpyHostToDevice, st));
-            CK(cudaMemcpyAsync(B[B_IN_X2].p, x2 + 2 * o0, 16 * (size_t)N, cudaMemcpyHostToDevice, st));
-            CK(cudaMemcpyAsync(B[B_IN_D1].p, d1 + o0, 8 * (size_t)N, cudaMemcpyHostToDevice, st));
-            CK(cudaMemcpyAsync(B[B_IN_D2].p, d2 + o0, 8 * (size_t)N, cudaMemcpyHostToDevice, st));
-            if (pose) CK(cudaMemcpyAsync(B[B_IN_CAMS].p, cams + 8 * p0, 64 * (size_t)P, cudaMemcpyHostToDevice, st));
-            CK(cudaEventRecord(e1, st));
-            io.x1 = B[B_IN_X1].as<double>(); io.x2 = B[B_IN_X2].as<double>();
-            io.d1 = B[B_IN_D1].as<double>(); io.d2 = B[B_IN_D2].as<double>();
-            io.cams = pose ? B[B_IN_CAMS].as<double>() : nullptr;
-            io.models_out = B[B_TMP0].as<Model>(); io.stats_out = B[B_TMP1].as<rp_stats>();
-            io.masks_out = B[B_MASK].as<unsigned char>();
+            // staging set par^1 was last read by the kernels of chunk c-1 (finished: run_chunk synchronises)
+            // and by the D2H of chunk c-1, which is ordered before this upload on the copy stream
+            if (c + 1 < n_chunks) {
+                rc = upload(c + 1);
+                if (rc) return rc;
+            }
+            CK(cudaStreamWaitEvent(st, in_ready[par], 0));
+            io.x1 = B[IN_X1[par]].as<double>(); io.x2 = B[IN_X2[par]].as<double>();
+            io.d1 = B[IN_D1[par]].as<double>(); io.d2 = B[IN_D2[par]].as<double>();
+            io.cams = pose ? B[IN_CAMS[par]].as<double>() : nullptr;
+            io.models_out = B[OUT_M[par]].as<Model>(); io.stats_out = B[OUT_S[par]].as<rp_stats>();
+            io.masks_out = B[OUT_K[par]].as<unsigned char>();
         } else {
             io.x1 = x1 + 2 * o0; io.x2 = x2 + 2 * o0; io.d1 = d1 + o0; io.d2 = d2 + o0;
             io.cams = pose ? cams + 8 * p0 : nullptr;
@@ -557,17 +594,22 @@ int estimate_impl(rp_ctx *ctx, int variant, int64_t n_pairs, const int64_t *offs
             iters = (int)std::min<int64_t>(opt.max_iterations, (int64_t)iters * 4);
         }
         if (host_io) {
+            // run_chunk returned after synchronising the compute stream: results are complete
             float ms = 0.f;
-            CK(cudaEventElapsedTime(&ms, e0, e1));
-            ctx->last_ms[9] += ms;
-            CK(cudaEventRecord(e1, st));
-            CK(cudaMemcpyAsync(models + p0, io.models_out, sizeof(Model) * P, cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync(stats + p0, io.stats_out, sizeof(rp_stats) * P, cudaMemcpyDeviceToHost, st));
-            if (N > 0) CK(cudaMemcpyAsync(masks + o0, io.masks_out, (size_t)N, cudaMemcpyDeviceToHost, st));
-            CK(cudaEventRecord(e2, st));
-            CK(cudaStreamSynchronize(st));
-            CK(cudaEventElapsedTime(&ms, e1, e2));
-            ctx->last_ms[10] += ms;
+            if (cudaEventElapsedTime(&ms, h2d_begin[par], in_ready[par]) == cudaSuccess) ctx->last_ms[9] += ms;
+            CK(cudaEventRecord(d2h_begin[par], cs));
+            CK(cudaMemcpyAsync(models + p0, io.models_out, sizeof(Model) * P, cudaMemcpyDeviceToHost, cs));
+            CK(cudaMemcpyAsync(stats + p0, io.stats_out, sizeof(rp_stats) * P, cudaMemcpyDeviceToHost, cs));
+            if (N > 0) CK(cudaMemcpyAsync(masks + o0, io.masks_out, (size_t)N, cudaMemcpyDeviceToHost, cs));
+            CK(cudaEventRecord(comp_done[par], cs));
+        }
+    }
+    if (host_io) {
+        CK(cudaEventRecord(d2h_end, cs));
+        CK(cudaStreamSynchronize(cs));
+        for (int par = 0; par < 2 && par < n_chunks; ++par) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, d2h_begin[par], comp_done[par]) == cudaSuccess) ctx->last_ms[10] += ms;
         }
     }
     return RP_OK;
@@ -599,7 +641,8 @@ int rp_create(int device, rp_ctx **out) {
     rp_ctx *ctx = new rp_ctx();
     ctx->device = device;
     ctx->sms = prop.multiProcessorCount;
-    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
         g_create_error = "cudaSetDevice / stream creation failed";
         delete ctx;
         return RP_ERR_CUDA;
@@ -622,6 +665,7 @@ void rp_destroy(rp_ctx *ctx) {
     for (auto &b : ctx->buf) b.release();
     for (auto &ev : ctx->ev) cudaEventDestroy(ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
 }
 
@@ -657,10 +701,10 @@ int rp_estimate_batch_dev(rp_ctx *ctx, int variant, int64_t n_pairs, const int64
                          stream ? (cudaStream_t)stream : ctx->stream);
 }
 
-int rp_last_timing(const rp_ctx *ctx, double *ms11, int64_t *counters6) {
+int rp_last_timing(const rp_ctx *ctx, double *ms16, int64_t *counters8) {
     if (!ctx) return RP_ERR_INVALID;
-    if (ms11) memcpy(ms11, ctx->last_ms, sizeof ctx->last_ms);
-    if (counters6) memcpy(counters6, ctx->last_cnt, sizeof ctx->last_cnt);
+    if (ms16) memcpy(ms16, ctx->last_ms, sizeof ctx->last_ms);
+    if (counters8) memcpy(counters8, ctx->last_cnt, sizeof ctx->last_cnt);
     return RP_OK;
 }
 

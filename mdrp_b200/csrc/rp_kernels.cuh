@@ -569,6 +569,7 @@ struct BoundArgs {
     const int *B0;     // per pair: max inlier count / min score over the exactly scored first HB models
     const double *S0;
     unsigned long long *point_scores;
+    unsigned long long *evaluated;  // optional: (model, correspondence) pairs actually evaluated
 };
 
 constexpr int BSG = 2;                       // slices (of 32*PT points) per pass: 8 points per lane
@@ -635,6 +636,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, 3) bound_kernel(BoundArgs a) {
         __syncwarp();
         const int group_pts = 32 * PT * BSG;
         const int n_pgroups = (n + group_pts - 1) / group_pts;
+        unsigned long long evaluated = 0;
         for (int g = 0; g < n_pgroups && alive; ++g) {
             float4 p[PT * BSG];
             bool valid[PT * BSG];
@@ -645,6 +647,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, 3) bound_kernel(BoundArgs a) {
                 p[j] = valid[j] ? a.pts32[pp.off + k] : make_float4(0.f, 0.f, 0.f, 0.f);
             }
             const int nvalid = min(group_pts, n - g * group_pts);
+            evaluated += (unsigned long long)__popc(alive) * nvalid;
 #pragma unroll 1
             for (int i = 0; i < my_nh; ++i) {
                 if (!((alive >> i) & 1u)) continue;
@@ -695,6 +698,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, 3) bound_kernel(BoundArgs a) {
             }
         }
         if (a.point_scores && tid == 0) atomicAdd(a.point_scores, (unsigned long long)nh * (unsigned long long)n);
+        if (a.evaluated && lane == 0) atomicAdd(a.evaluated, evaluated);
     }
 }
 

@@ -226,3 +226,27 @@ def test_python_surface_matches_reference_api(ctx):
     assert ip.pose.R.shape == (3, 3) and ip.camera1.focal() > 0
     assert len(api.monodepth_pose_3pt(np.c_[sc.x1[:3] / 800, np.ones(3)], np.c_[sc.x2[:3] / 800, np.ones(3)],
                                       sc.d1[:3], sc.d2[:3])) <= 4
+
+
+@pytest.mark.parametrize("cfg", ["cfg1_calib_scale", "cfg2_calib_shift", "cfg3_shared_focal", "cfg4_varying_focal", "hard_calib"])
+def test_pruning_does_not_change_results(cfg, monkeypatch):
+    """The FP32 bound kernel only drops minimal models that provably cannot trigger anything in
+    score_models(): with RP_NO_PRUNE=1 every model is scored exactly, and all outputs must be bytewise
+    identical."""
+    c = synth.CONFIGS[cfg]
+    scs, variant, offs, x1, x2, d1, d2, cams = _batch(cfg, range(400, 424), n=700)
+    o = _options(2500, shift=c["shift"])
+    monkeypatch.delenv("RP_NO_PRUNE", raising=False)
+    pruned_ctx = nv.Context(0)
+    a = pruned_ctx.estimate_batch_host(variant, offs, x1, x2, d1, d2, cams, o)
+    _, cnt = pruned_ctx.last_timing()
+    assert cnt["exact_models"] < 0.5 * cnt["hypotheses"]  # pruning is actually on
+    monkeypatch.setenv("RP_NO_PRUNE", "1")
+    full_ctx = nv.Context(0)
+    b = full_ctx.estimate_batch_host(variant, offs, x1, x2, d1, d2, cams, o)
+    _, cnt2 = full_ctx.last_timing()
+    assert cnt2["exact_models"] == cnt2["hypotheses"]
+    for u, v in zip(a, b):
+        assert u.tobytes() == v.tobytes()
+    pruned_ctx.close()
+    full_ctx.close()
