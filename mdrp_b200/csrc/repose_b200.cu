@@ -72,7 +72,7 @@ struct rp_ctx {
     cudaEvent_t ev[N_EVENTS];
     double last_ms[16] = {0};
     int64_t last_cnt[8] = {0};  // [5] models through the exact kernel, [6] point-scores the bound kernel evaluated
-    size_t workspace_budget = (size_t)12 << 30;
+    size_t workspace_budget = (size_t)32 << 30;  // HBM is 180 GB: big chunks amortise kernel tails
     bool prune = true;  // hypothesis-level pruning (RP_NO_PRUNE=1 scores every minimal model exactly)
     int occ_score[4] = {0}, occ_lm[4] = {0};
 };
