@@ -157,6 +157,18 @@ RP_API int rp_refine_batch(rp_ctx *ctx, int variant, int64_t n_models, rp_model 
                            const uint8_t *mask, double scale_reproj, double weight_sampson,
                            const rp_bundle_options *opt, rp_bundle_stats *stats);
 
+/* ---- device-resident front end --------------------------------------
+ * What the reference's callers do on the host between the networks and the estimator
+ * (/root/reference/make_pair.py:97-106): depth lookup at the matched keypoints,
+ * depth_map[(int)y, (int)x], and removal of the rows whose two depths are both infinite.
+ * All pointers are DEVICE memory: depth maps [h,w] float32, keypoints [n,2] float32 (x,y) as the
+ * matcher produces them; outputs are the packed FP64 arrays rp_estimate_batch_dev takes
+ * (capacity n rows), *n_out (host) the number of rows kept, order preserved.  Coordinates outside
+ * the map are clamped to its border. */
+RP_API int rp_gather_depths_dev(rp_ctx *ctx, const float *depth1, int h1, int w1, const float *depth2, int h2, int w2,
+                                const float *kp1, const float *kp2, int64_t n, double *x1, double *x2, double *d1,
+                                double *d2, int64_t *n_out, void *stream);
+
 /* ---- measurement helpers ---------------------------------------------------------
  * Pipe micro-benchmarks for the roofline denominators SURVEY.md §8d asks for (the driver's
  * MEASURED_PEAKS.json has only HBM and bf16): sustained FP64 and FP32 FMA throughput of

@@ -18,7 +18,7 @@ LOSS = {"TRIVIAL": 0, "TRUNCATED": 1, "HUBER": 2, "CAUCHY": 3, "TRUNCATED_CAUCHY
 EXPORTS = [
     "rp_create", "rp_destroy", "rp_last_error", "rp_default_options", "rp_launch_count",
     "rp_estimate_batch_host", "rp_estimate_batch_dev", "rp_sample_batch", "rp_solve_batch",
-    "rp_score_batch", "rp_refine_batch", "rp_measure_pipes", "rp_last_timing",
+    "rp_score_batch", "rp_refine_batch", "rp_measure_pipes", "rp_last_timing", "rp_gather_depths_dev",
 ]
 
 
@@ -106,6 +106,9 @@ def load():
     L.rp_refine_batch.restype = C.c_int
     L.rp_refine_batch.argtypes = [VP, C.c_int, C.c_int64, VP, C.c_int64, VP, VP, VP, VP, VP, C.c_double,
                                   C.c_double, C.POINTER(BundleOptions), VP]
+    L.rp_gather_depths_dev.restype = C.c_int
+    L.rp_gather_depths_dev.argtypes = [VP, VP, C.c_int, C.c_int, VP, C.c_int, C.c_int, VP, VP, C.c_int64, VP, VP, VP, VP,
+                                       C.POINTER(C.c_int64), VP]
     L.rp_measure_pipes.restype = C.c_int
     L.rp_measure_pipes.argtypes = [VP, DP, DP]
     L.rp_last_timing.restype = C.c_int

@@ -872,6 +872,27 @@ int rp_refine_batch(rp_ctx *ctx, int variant, int64_t n_models, rp_model *models
     return RP_OK;
 }
 
+int rp_gather_depths_dev(rp_ctx *ctx, const float *depth1, int h1, int w1, const float *depth2, int h2, int w2,
+                         const float *kp1, const float *kp2, int64_t n, double *x1, double *x2, double *d1, double *d2,
+                         int64_t *n_out, void *stream) {
+    if (!ctx || n < 0 || !n_out || h1 <= 0 || w1 <= 0 || h2 <= 0 || w2 <= 0 ||
+        (n > 0 && (!depth1 || !depth2 || !kp1 || !kp2 || !x1 || !x2 || !d1 || !d2)))
+        return fail(ctx, RP_ERR_INVALID, "bad argument");
+    *n_out = 0;
+    if (n == 0) return RP_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    CK(ctx->buf[B_SCALARS].reserve(sizeof(Scalars)));
+    long long *d_n = (long long *)ctx->buf[B_SCALARS].p;
+    gather_depths_kernel<<<1, 1024, 0, st>>>(depth1, h1, w1, depth2, h2, w2, kp1, kp2, (long long)n, x1, x2, d1, d2, d_n);
+    LAUNCHED();
+    long long h_n = 0;
+    CK(cudaMemcpyAsync(&h_n, d_n, sizeof h_n, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *n_out = h_n;
+    return RP_OK;
+}
+
 int rp_measure_pipes(rp_ctx *ctx, double *fp64_tflops, double *fp32_tflops) {
     if (!ctx) return RP_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));

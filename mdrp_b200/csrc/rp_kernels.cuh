@@ -1004,6 +1004,52 @@ __global__ void fill_int_kernel(int *p, int n, int v) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// front end: the reference's callers look the monocular depth up at the matched
+// keypoints, depth_map[(int)y, (int)x], and drop the rows whose two depths are both infinite
+// (/root/reference/make_pair.py:97-106) on the host after a .cpu().numpy() round trip.  This kernel does
+// the lookup, the mask and the stable compaction on the device, straight into the packed FP64 layout
+// the estimator takes.  One block; rows keep their order.
+__global__ void gather_depths_kernel(const float *depth1, int h1, int w1, const float *depth2, int h2, int w2,
+                                     const float *kp1, const float *kp2, long long n, double *x1, double *x2,
+                                     double *d1, double *d2, long long *n_out) {
+    __shared__ int warp_tot[32];
+    __shared__ long long running;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) running = 0;
+    __syncthreads();
+    for (long long base = 0; base < n; base += blockDim.x) {
+        const long long i = base + tid;
+        bool keep = false;
+        float ax = 0, ay = 0, bx = 0, by = 0, da = 0, db = 0;
+        if (i < n) {
+            ax = kp1[2 * i]; ay = kp1[2 * i + 1]; bx = kp2[2 * i]; by = kp2[2 * i + 1];
+            const int r1 = min(max((int)ay, 0), h1 - 1), c1 = min(max((int)ax, 0), w1 - 1);
+            const int r2 = min(max((int)by, 0), h2 - 1), c2 = min(max((int)bx, 0), w2 - 1);
+            da = depth1[(size_t)r1 * w1 + c1];
+            db = depth2[(size_t)r2 * w2 + c2];
+            keep = !(isinf(da) && isinf(db));
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) warp_tot[wid] = __popc(m);
+        __syncthreads();
+        int wbase = 0, total = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+            if (w < wid) wbase += warp_tot[w];
+            total += warp_tot[w];
+        }
+        if (keep) {
+            const long long o = running + wbase + __popc(m & ((1u << lane) - 1u));
+            x1[2 * o] = ax; x1[2 * o + 1] = ay; x2[2 * o] = bx; x2[2 * o + 1] = by;
+            d1[o] = da; d2[o] = db;
+        }
+        __syncthreads();
+        if (tid == 0) running += total;
+        __syncthreads();
+    }
+    if (tid == 0) *n_out = running;
+}
+
+// ---------------------------------------------------------------------------------------------
 // pipe micro-benchmarks (the FP64 / FP32 FMA peaks are not in MEASURED_PEAKS.json)
 __global__ void fp64_pipe_kernel(double *out, int iters) {
     double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
