@@ -44,7 +44,7 @@ struct DevBuf {
 enum { B_OFFS, B_PAIRS, B_PTS64, B_PTS32, B_BEAR, B_SAMPLES, B_MODELS, B_HYPITER, B_SCORE, B_COUNT, B_SEGCNT,
        B_ITEMPFX, B_SCALARS, B_EVENTS, B_NEVENTS, B_LOMODELS, B_LOOFEV, B_LOCOUNT, B_PROBLIST, B_LOSCORE,
        B_LOCNT, B_LOITEMPFX, B_BEST, B_FINSTART, B_FINSCORE, B_FINCNT, B_ONES, B_ONEPFX, B_ENABLE, B_STATS,
-       B_UB, B_LB, B_FIRSTCNT, B_FIRSTPFX, B_B0, B_S0, B_SURVLIST, B_SURVCNT, B_SURVPFX,
+       B_PTS32P, B_UB, B_LB, B_FIRSTCNT, B_FIRSTPFX, B_B0, B_S0, B_SURVLIST, B_SURVCNT, B_SURVPFX,
        B_MASK, B_IN_X1, B_IN_X2, B_IN_D1, B_IN_D2, B_IN_CAMS, B_TMP0, B_TMP1, B_TMP2,
        // second staging set (double buffering of the host path)
        B_MASK_B, B_IN_X1_B, B_IN_X2_B, B_IN_D1_B, B_IN_D2_B, B_IN_CAMS_B, B_TMP0_B, B_TMP1_B, B_NBUF };
@@ -185,7 +185,7 @@ __global__ void stage_points_kernel(int n, const double *x1, const double *x2, d
         pp.sq_thr = sq_thr;
         pp.thr = sqrt(sq_thr) * (1.0 + 1e-15);  // only feeds the (conservative) FP32 filter bound
         pp.scale_reproj = 0.0; pp.lo_loss_scale = pp.thr; pp.final_loss_scale = pp.thr; pp.nscale = 1.0;
-        pp.Mmax = Mmax * 1.000001; pp.mmax = mmax * 1.000001;
+        pp.Mmax = Mmax * 1.000001; pp.mmax = mmax * 1.000001; pp.pbase = 0;
         *pair = pp;
     }
 }
@@ -215,6 +215,7 @@ int run_chunk(rp_ctx *ctx, int variant, const rp_options &opt, const ChunkIO &io
     CK(B[B_PAIRS].reserve(sizeof(PairParams) * P));
     CK(B[B_PTS64].reserve(sizeof(Pt64) * std::max<long long>(N, 1)));
     CK(B[B_PTS32].reserve(sizeof(float4) * std::max<long long>(N, 1)));
+    CK(B[B_PTS32P].reserve(32 * (size_t)((N + P + 4) / 2 + 1)));
     CK(B[B_BEAR].reserve(sizeof(Bear) * std::max<long long>(N, 1)));
     CK(B[B_SAMPLES].reserve(sizeof(int) * 3 * (size_t)P * std::max(iters, 1)));
     CK(B[B_MODELS].reserve(sizeof(Model) * slots));
@@ -281,7 +282,7 @@ int run_chunk(rp_ctx *ctx, int variant, const rp_options &opt, const ChunkIO &io
         a.x1 = io.x1; a.x2 = io.x2; a.cams = io.cams;
         a.max_epipolar_error = opt.max_epipolar_error; a.max_reproj_error = opt.max_reproj_error;
         a.loss_scale = opt.loss_scale;
-        a.pts64 = pts64; a.pts32 = pts32; a.bear = bear; a.pairs = pairs;
+        a.pts64 = pts64; a.pts32 = pts32; a.bear = bear; a.pairs = pairs; a.pts32p = B[B_PTS32P].as<float>();
         prepare_kernel<<<cdiv((long long)P * 32, 256), 256, 0, st>>>(a);
         LAUNCHED();
     }
@@ -331,7 +332,7 @@ int run_chunk(rp_ctx *ctx, int variant, const rp_options &opt, const ChunkIO &io
         // 4b. FP32 bounds for all later models
         BoundArgs ba;
         ba.n_groups = P * nseg; ba.grp_stride = 4 * SEG; ba.grp_per_pair = nseg; ba.grp_cnt = seg_count;
-        ba.item_prefix = item_prefix; ba.n_items = &sc->n_items; ba.pairs = pairs; ba.models = models; ba.pts32 = pts32;
+        ba.item_prefix = item_prefix; ba.n_items = &sc->n_items; ba.pairs = pairs; ba.models = models; ba.pts32p = B[B_PTS32P].as<ulonglong2>();
         ba.ub = B[B_UB].as<int>(); ba.lb = B[B_LB].as<float>(); ba.point_scores = &sc->point_scores;
         ba.B0 = B[B_B0].as<int>(); ba.S0 = B[B_S0].as<double>();
         ba.evaluated = &sc->evaluated_ps;
@@ -485,7 +486,7 @@ size_t bytes_per_pair(int iters, long long avg_points) {
     const int nseg = std::max(1, cdiv(iters, SEG));
     const size_t slots_pp = (size_t)nseg * 4 * SEG;
     return slots_pp * (sizeof(Model) + 4 + 8 + 4 + 12) + (size_t)iters * 12 + (size_t)EV * (sizeof(Model) + 24) +
-           (size_t)avg_points * (sizeof(Pt64) + 16 + sizeof(Bear) + 1) + 1024;
+           (size_t)avg_points * (sizeof(Pt64) + 32 + sizeof(Bear) + 1) + 1024;
 }
 
 int check_common(rp_ctx *ctx, int variant, int64_t n_pairs, const int64_t *offsets, const rp_options *opt) {

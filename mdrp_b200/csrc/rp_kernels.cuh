@@ -33,9 +33,17 @@ struct PrepareArgs {
     double max_epipolar_error, max_reproj_error, loss_scale;
     Pt64 *pts64;
     float4 *pts32;
+    float *pts32p;  // pair-interleaved copy for the packed-FP32 bound kernel: per two correspondences (a,b)
+                    // [x1x_a,x1x_b, x1y_a,x1y_b, x2x_a,x2x_b, x2y_a,x2y_b]
     Bear *bear;
     PairParams *pairs;
 };
+
+// writes one correspondence into the pair-interleaved layout
+RP_D void store_interleaved(float *pts32p, long long pbase, int k, float x1x, float x1y, float x2x, float x2y) {
+    float *q = pts32p + (pbase + (k >> 1)) * 8 + (k & 1);
+    q[0] = x1x; q[2] = x1y; q[4] = x2x; q[6] = x2y;
+}
 
 __global__ void prepare_kernel(PrepareArgs a) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -49,6 +57,8 @@ __global__ void prepare_kernel(PrepareArgs a) {
     pp.n = n;
     pp.valid = n >= 3;
     pp.nscale = 1.0;
+    pp.pbase = (off + warp + 1) >> 1;  // b_{p+1} - b_p >= ceil(n_p / 2)
+    if ((n & 1) && lane == 0) store_interleaved(a.pts32p, pp.pbase, n, 0.f, 0.f, 0.f, 0.f);  // padding half
     double Mmax = 0.0, mmax = 0.0;
     if (pose) {
         const double *c = a.cams + 8 * (long long)warp;
@@ -69,6 +79,7 @@ __global__ void prepare_kernel(PrepareArgs a) {
             p.x2_1 = (a.x2[2 * g + 1] - cy2) / fy2;
             a.pts64[g] = p;
             a.pts32[g] = make_float4((float)p.x1_0, (float)p.x1_1, (float)p.x2_0, (float)p.x2_1);
+            store_interleaved(a.pts32p, pp.pbase, k0, (float)p.x1_0, (float)p.x1_1, (float)p.x2_0, (float)p.x2_1);
             const V3 b1 = bearing(p.x1_0, p.x1_1), b2 = bearing(p.x2_0, p.x2_1);
             Bear b;
             b.b1x = b1.x; b.b1y = b1.y; b.b1z = b1.z; b.b2x = b2.x; b.b2y = b2.y; b.b2z = b2.z;
@@ -116,6 +127,7 @@ __global__ void prepare_kernel(PrepareArgs a) {
             p.x2_1 = a.x2[2 * g + 1] / nscale;
             a.pts64[g] = p;
             a.pts32[g] = make_float4((float)p.x1_0, (float)p.x1_1, (float)p.x2_0, (float)p.x2_1);
+            store_interleaved(a.pts32p, pp.pbase, k0, (float)p.x1_0, (float)p.x1_1, (float)p.x2_0, (float)p.x2_1);
             const double m1 = fabs(p.x1_0) + fabs(p.x1_1) + 1.0, m2 = fabs(p.x2_0) + fabs(p.x2_1) + 1.0;
             Mmax = fmax(Mmax, m1 * m2);
             mmax = fmax(mmax, fmax(m1, m2));
@@ -563,7 +575,7 @@ struct BoundArgs {
     const int *n_items;
     const PairParams *pairs;
     const Model *models;
-    const float4 *pts32;
+    const ulonglong2 *pts32p;  // pair-interleaved FP32 correspondences (see PrepareArgs)
     int *ub;       // slots
     float *lb;     // slots
     const int *B0;     // per pair: max inlier count / min score over the exactly scored first HB models
@@ -572,15 +584,82 @@ struct BoundArgs {
     unsigned long long *evaluated;  // optional: (model, correspondence) pairs actually evaluated
 };
 
+#ifndef RP_BOUND_MIN_BLOCKS
+#define RP_BOUND_MIN_BLOCKS 2
+#endif
 constexpr int BSG = 2;                       // slices (of 32*PT points) per pass: 8 points per lane
 constexpr int BHW = HB / SCORE_WARPS;        // models per warp (each warp owns its models over ALL points)
 
+// Packed FP32 arithmetic of sm_100a: fma.rn.f32x2 / mul.rn.f32x2 (SASS FFMA2 / FMUL2) do two FP32
+// operations per lane per instruction.  Measured on B200 (tools/ffma2_bench.cu): same FLOP/s as FFMA,
+// i.e. half the issue slots — exactly what an issue-bound FP32 kernel needs.  The bound kernel evaluates
+// correspondences two at a time with them.
+typedef unsigned long long f32x2;
+RP_D f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+RP_D void unpack2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+RP_D f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+RP_D float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+RP_D f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
+// per-model constants of the bound kernel, every scalar duplicated into both halves of a packed register
+struct alignas(16) BoundFilter {
+    f32x2 e[9];   // E / F, row-major
+    f32x2 g;      // thr^2 (1+1e-5)
+    f32x2 kh;     // 1012 delta_a^2
+    f32x2 eps;    // eps (filter disabled: +inf)
+};
+
 struct BoundShared {
-    Filter32 hf[HB];
-    float kh[HB];
+    BoundFilter hf[HB];
     float sp[SCORE_WARPS][BHW][32];  // per-lane partial lower-bound sums of the warp's models
     int outc[SCORE_WARPS][BHW];      // certain outliers collected so far by each of the warp's models
 };
+
+// one model against the 8 correspondences a lane holds (4 packed pairs).  FULL: all 256 correspondences
+// of the group exist (no validity predicates).  CHEAP: count certain outliers only (the model already
+// looks hopeless; its lower bound is given up, see bound_kernel).
+template <bool FULL, bool CHEAP>
+RP_D void bound_eval(const BoundFilter &f, const f32x2 (&X1x)[PT * BSG / 2], const f32x2 (&X1y)[PT * BSG / 2],
+                     const f32x2 (&X2x)[PT * BSG / 2], const f32x2 (&X2y)[PT * BSG / 2], unsigned vmask, float thr2_lo,
+                     int &c, float &s) {
+    float eps, eps_hi;
+    unpack2(f.eps, eps, eps_hi);
+    const f32x2 k1001 = pack2(1.001f, 1.001f);
+#pragma unroll
+    for (int q = 0; q < PT * BSG / 2; ++q) {
+        const f32x2 a0 = fma2(f.e[0], X1x[q], fma2(f.e[1], X1y[q], f.e[2]));
+        const f32x2 a1 = fma2(f.e[3], X1x[q], fma2(f.e[4], X1y[q], f.e[5]));
+        const f32x2 a2 = fma2(f.e[6], X1x[q], fma2(f.e[7], X1y[q], f.e[8]));
+        const f32x2 b0 = fma2(f.e[0], X2x[q], fma2(f.e[3], X2y[q], f.e[6]));
+        const f32x2 b1 = fma2(f.e[1], X2x[q], fma2(f.e[4], X2y[q], f.e[7]));
+        const f32x2 C = fma2(X2x[q], a0, fma2(X2y[q], a1, a2));
+        const f32x2 den = fma2(a0, a0, fma2(a1, a1, fma2(b0, b0, mul2(b1, b1))));
+        float c0, c1;
+        unpack2(C, c0, c1);
+        const float tt0 = fmaxf(fabsf(c0) - eps, 0.0f), tt1 = fmaxf(fabsf(c1) - eps, 0.0f);
+        const f32x2 TT = pack2(tt0, tt1);
+        const f32x2 T2 = mul2(TT, TT), GD = mul2(f.g, den);
+        float t20, t21, gd0, gd1;
+        unpack2(T2, t20, t21);
+        unpack2(GD, gd0, gd1);
+        bool cand0 = !(t20 > gd0), cand1 = !(t21 > gd1);
+        if (!FULL) {
+            cand0 = cand0 && ((vmask >> (2 * q)) & 1u);
+            cand1 = cand1 && ((vmask >> (2 * q + 1)) & 1u);
+        }
+        c += (int)cand0 + (int)cand1;
+        if (!CHEAP) {
+            // r2_lb = t2 / (1.001 den + kh); kh >= 1e-29 for every enabled filter and +inf for disabled
+            // ones, so the approximate reciprocal never sees a denormal (its 1-ulp error is inside the
+            // 1e-4 slack of lb)
+            const f32x2 DU = fma2(den, k1001, f.kh);
+            float du0, du1;
+            unpack2(DU, du0, du1);
+            const float r0 = fminf(t20 * rcp_approx(du0), thr2_lo), r1 = fminf(t21 * rcp_approx(du1), thr2_lo);
+            s += (cand0 ? r0 : 0.f) + (cand1 ? r1 : 0.f);
+        }
+    }
+}
 
 // Warps split the MODELS of an item (model h belongs to warp h % SCORE_WARPS) and each walks all
 // correspondences of the pair in groups of 256.  A warp therefore knows, after every group, how many
@@ -588,7 +667,7 @@ struct BoundShared {
 //     out >= N - B0   (final ub <= B0)   and   thr^2 * out >= S0   (final lb >= S0)
 // i.e. as soon as it is certain to be pruned: bad models (the majority) stop after ~1/3 of the points.
 template <bool POSE>
-__global__ void __launch_bounds__(SCORE_THREADS, 3) bound_kernel(BoundArgs a) {
+__global__ void __launch_bounds__(SCORE_THREADS, RP_BOUND_MIN_BLOCKS) bound_kernel(BoundArgs a) {
     __shared__ BoundShared sh;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n_items = *a.n_items;
@@ -612,12 +691,19 @@ __global__ void __launch_bounds__(SCORE_THREADS, 3) bound_kernel(BoundArgs a) {
         if (tid < nh) {
             const Model m = a.models[slot0 + tid];
             const M3 E = POSE ? essential_from_motion(m.q, m.t) : fundamental_from_model(m);
-            sh.hf[tid] = make_filter32(E, pp.thr, pp.Mmax, pp.mmax);
+            const Filter32 f = make_filter32(E, pp.thr, pp.Mmax, pp.mmax);
             // 1012 * delta_a^2 with delta_a = 16 u Emax m (the sqrt(den) term of eps)
             const double emax = fmax(fmax(fmax(fabs(E.r0.x), fabs(E.r0.y)), fmax(fabs(E.r0.z), fabs(E.r1.x))),
                                      fmax(fmax(fabs(E.r1.y), fabs(E.r1.z)), fmax(fmax(fabs(E.r2.x), fabs(E.r2.y)), fabs(E.r2.z))));
             const double da = 16.0 * 5.9604644775390625e-08 * emax * pp.mmax;
-            sh.kh[tid] = (float)(1012.0 * da * da * 1.0001);
+            // disabled filter (eps = +inf): kh = +inf makes every r2_lb exactly 0
+            const float kh = isinf(f.eps) ? INFINITY : fmaxf((float)(1012.0 * da * da * 1.0001), 1e-29f);
+            BoundFilter bf;
+            bf.e[0] = pack2(f.e00, f.e00); bf.e[1] = pack2(f.e01, f.e01); bf.e[2] = pack2(f.e02, f.e02);
+            bf.e[3] = pack2(f.e10, f.e10); bf.e[4] = pack2(f.e11, f.e11); bf.e[5] = pack2(f.e12, f.e12);
+            bf.e[6] = pack2(f.e20, f.e20); bf.e[7] = pack2(f.e21, f.e21); bf.e[8] = pack2(f.e22, f.e22);
+            bf.g = pack2(f.g, f.g); bf.kh = pack2(kh, kh); bf.eps = pack2(f.eps, f.eps);
+            sh.hf[tid] = bf;
         }
         __syncthreads();
         const int n = pp.n;
@@ -629,6 +715,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, 3) bound_kernel(BoundArgs a) {
         const int need_out = need_d > 2.0e9 ? 0x7fffffff : max((int)need_d, 1);
         const int my_nh = (nh - wid + SCORE_WARPS - 1) / SCORE_WARPS;  // models h = wid + i*SCORE_WARPS
         unsigned alive = my_nh >= 32 ? 0xffffffffu : ((1u << my_nh) - 1u);
+        unsigned cheap = 0;  // models that switched to count-only evaluation (their lb is void)
         int *out_cnt = sh.outc[wid];
 #pragma unroll
         for (int i = 0; i < BHW; ++i) sh.sp[wid][i][lane] = 0.f;
@@ -638,46 +725,45 @@ __global__ void __launch_bounds__(SCORE_THREADS, 3) bound_kernel(BoundArgs a) {
         const int n_pgroups = (n + group_pts - 1) / group_pts;
         unsigned long long evaluated = 0;
         for (int g = 0; g < n_pgroups && alive; ++g) {
-            float4 p[PT * BSG];
-            bool valid[PT * BSG];
+            // lane owns the correspondence pairs (2m, 2m+1), m = g*128 + q*32 + lane: two 128-bit loads give
+            // the four packed operands directly in aligned register pairs
+            f32x2 X1x[PT * BSG / 2], X1y[PT * BSG / 2], X2x[PT * BSG / 2], X2y[PT * BSG / 2];
+            unsigned vmask = 0;
 #pragma unroll
-            for (int j = 0; j < PT * BSG; ++j) {
-                const int k = g * group_pts + j * 32 + lane;
-                valid[j] = k < n;
-                p[j] = valid[j] ? a.pts32[pp.off + k] : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int q = 0; q < PT * BSG / 2; ++q) {
+                const int m = g * (group_pts / 2) + q * 32 + lane;
+                const int k0 = 2 * m, k1 = k0 + 1;
+                ulonglong2 A = make_ulonglong2(0ull, 0ull), Bq = make_ulonglong2(0ull, 0ull);
+                if (k0 < n) {
+                    A = a.pts32p[(pp.pbase + m) * 2];
+                    Bq = a.pts32p[(pp.pbase + m) * 2 + 1];
+                }
+                vmask |= (k0 < n ? 1u : 0u) << (2 * q) | (k1 < n ? 1u : 0u) << (2 * q + 1);
+                X1x[q] = A.x; X1y[q] = A.y; X2x[q] = Bq.x; X2y[q] = Bq.y;
             }
             const int nvalid = min(group_pts, n - g * group_pts);
+            const bool full = nvalid == group_pts;
             evaluated += (unsigned long long)__popc(alive) * nvalid;
 #pragma unroll 1
             for (int i = 0; i < my_nh; ++i) {
                 if (!((alive >> i) & 1u)) continue;
                 const int h = wid + i * SCORE_WARPS;
-                const Filter32 f = sh.hf[h];
-                const float kh = sh.kh[h];
+                const BoundFilter f = sh.hf[h];
                 int c = 0;
                 float s = 0.f;
-#pragma unroll
-                for (int j = 0; j < PT * BSG; ++j) {
-                    const float a0 = fmaf_(f.e00, p[j].x, fmaf_(f.e01, p[j].y, f.e02));
-                    const float a1 = fmaf_(f.e10, p[j].x, fmaf_(f.e11, p[j].y, f.e12));
-                    const float a2 = fmaf_(f.e20, p[j].x, fmaf_(f.e21, p[j].y, f.e22));
-                    const float b0 = fmaf_(f.e00, p[j].z, fmaf_(f.e10, p[j].w, f.e20));
-                    const float b1 = fmaf_(f.e01, p[j].z, fmaf_(f.e11, p[j].w, f.e21));
-                    const float C = fmaf_(p[j].z, a0, fmaf_(p[j].w, a1, a2));
-                    const float den = fmaf_(a0, a0, fmaf_(a1, a1, fmaf_(b0, b0, b1 * b1)));
-                    const float tt = fmaxf(fabsf(C) - f.eps, 0.0f);
-                    const float t2 = tt * tt;
-                    const bool cand = valid[j] && !(t2 > f.g * den);
-                    const float r = fminf(__fdividef(t2, fmaf_(den, 1.001f, kh)), thr2_lo);
-                    c += cand;
-                    s += cand ? r : 0.f;
-                }
-                sh.sp[wid][i][lane] += s;
+                const bool is_cheap = (cheap >> i) & 1u;
+                if (!full) bound_eval<false, false>(f, X1x, X1y, X2x, X2y, vmask, thr2_lo, c, s);
+                else if (is_cheap) bound_eval<true, true>(f, X1x, X1y, X2x, X2y, vmask, thr2_lo, c, s);
+                else bound_eval<true, false>(f, X1x, X1y, X2x, X2y, vmask, thr2_lo, c, s);
+                if (!is_cheap) sh.sp[wid][i][lane] += s;
                 const int nc = __reduce_add_sync(0xffffffffu, c);
                 const int oc = out_cnt[i] + nvalid - nc;
                 __syncwarp();
                 if (lane == 0) out_cnt[i] = oc;
                 if (oc >= need_out) alive &= ~(1u << i);  // certain to be pruned: stop here
+                // more than half certain outliers so far: this model will almost surely be abandoned, stop
+                // paying for its score bound (if it does stay alive it simply goes to the exact kernel)
+                else if (2 * oc >= (g + 1) * group_pts) cheap |= 1u << i;
             }
         }
         // results: abandoned models can never survive the prune (ub = 0, lb = +inf)
@@ -694,7 +780,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, 3) bound_kernel(BoundArgs a) {
                 // lb = thr^2 * (#certain outliers) + sum of candidate lower bounds; FP32 rounding of the
                 // terms, the rcp and the partial sums is covered by 1e-4 relative
                 const double lbv = ((double)thr2_lo * (double)out_cnt[i] + (double)s) * (1.0 - 1e-4);
-                a.lb[slot0 + h] = dead ? INFINITY : __double2float_rd(lbv);
+                a.lb[slot0 + h] = dead ? INFINITY : (((cheap >> i) & 1u) ? -INFINITY : __double2float_rd(lbv));
             }
         }
         if (a.point_scores && tid == 0) atomicAdd(a.point_scores, (unsigned long long)nh * (unsigned long long)n);

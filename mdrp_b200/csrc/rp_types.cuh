@@ -24,6 +24,7 @@ struct PairParams {
     double final_loss_scale;
     double nscale;        // focal variants: normalize_points scale (1 for calibrated)
     double Mmax, mmax;    // bounds used by the FP32 filter
+    long long pbase;      // first entry of this pair in the pair-interleaved FP32 layout (units of 2 points)
 };
 
 struct alignas(16) Pt64 {

@@ -246,7 +246,12 @@ def test_pruning_does_not_change_results(cfg, monkeypatch):
     b = full_ctx.estimate_batch_host(variant, offs, x1, x2, d1, d2, cams, o)
     _, cnt2 = full_ctx.last_timing()
     assert cnt2["exact_models"] == cnt2["hypotheses"]
-    for u, v in zip(a, b):
-        assert u.tobytes() == v.tobytes()
+    # models, masks, counters: bytewise.  model_score: the order in which the exact kernel sums the inlier
+    # residuals of a model depends on which other models share its work item, so the two modes may differ in
+    # the last bits (tie rule)
+    assert a[0].tobytes() == b[0].tobytes() and a[2].tobytes() == b[2].tobytes()
+    for f in ("refinements", "iterations", "num_inliers", "inlier_ratio"):
+        assert np.array_equal(a[1][f], b[1][f]), f
+    assert np.allclose(a[1]["model_score"], b[1]["model_score"], rtol=1e-12, atol=0)
     pruned_ctx.close()
     full_ctx.close()
