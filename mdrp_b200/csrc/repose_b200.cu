@@ -899,7 +899,7 @@ int rp_measure_pipes(rp_ctx *ctx, double *fp64_tflops, double *fp32_tflops) {
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     DevBuf *B = ctx->buf;
-    const int blocks = ctx->sms * 8, threads = 256, iters = 1 << 14;
+    const int blocks = ctx->sms * 8, threads = 256, iters = 1 << 13;
     CK(B[B_TMP0].reserve(sizeof(double) * (size_t)blocks * threads));
     cudaEvent_t e0 = ctx->ev[9], e1 = ctx->ev[10];
     for (int pass = 0; pass < 2; ++pass) {
@@ -913,7 +913,7 @@ int rp_measure_pipes(rp_ctx *ctx, double *fp64_tflops, double *fp32_tflops) {
             CK(cudaStreamSynchronize(st));
             float ms = 0.f;
             CK(cudaEventElapsedTime(&ms, e0, e1));
-            const double flops = 2.0 * 8.0 * (double)iters * (double)blocks * threads;
+            const double flops = 2.0 * 16.0 * (double)iters * (double)blocks * threads;
             if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
         }
         if (pass == 0 && fp64_tflops) *fp64_tflops = best;

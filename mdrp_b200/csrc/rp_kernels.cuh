@@ -226,7 +226,7 @@ struct SolveArgs {
 };
 
 template <int VARIANT>
-__global__ void __launch_bounds__(SOLVE_THREADS) solve_kernel(SolveArgs a) {
+__global__ void __launch_bounds__(SOLVE_THREADS, RP_SOLVE_MIN_BLOCKS) solve_kernel(SolveArgs a) {
     const int seg = blockIdx.x, pair = blockIdx.y;
     const PairParams pp = a.pairs[pair];
     __shared__ int warp_tot[SOLVE_THREADS / 32];
@@ -584,6 +584,9 @@ struct BoundArgs {
     unsigned long long *evaluated;  // optional: (model, correspondence) pairs actually evaluated
 };
 
+#ifndef RP_SOLVE_MIN_BLOCKS
+#define RP_SOLVE_MIN_BLOCKS 1
+#endif
 #ifndef RP_BOUND_MIN_BLOCKS
 #define RP_BOUND_MIN_BLOCKS 2
 #endif
@@ -1137,23 +1140,32 @@ __global__ void gather_depths_kernel(const float *depth1, int h1, int w1, const 
 
 // ---------------------------------------------------------------------------------------------
 // pipe micro-benchmarks (the FP64 / FP32 FMA peaks are not in MEASURED_PEAKS.json)
+// 16 independent FMA chains per thread, 8 blocks of 256 threads per SM: enough ILP x TLP to saturate either pipe
 __global__ void fp64_pipe_kernel(double *out, int iters) {
-    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    double a[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = threadIdx.x * 1e-3 + i;
     const double b = 1.0000001, c = 1e-9;
-    for (int i = 0; i < iters; ++i) {
-        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
-        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
-    }
-    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    for (int it = 0; it < iters; ++it)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a[i] = fma(a[i], b, c);
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += a[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 __global__ void fp32_pipe_kernel(float *out, int iters) {
-    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    float a[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = threadIdx.x * 1e-3f + i;
     const float b = 1.0000001f, c = 1e-9f;
-    for (int i = 0; i < iters; ++i) {
-        a0 = fmaf(a0, b, c); a1 = fmaf(a1, b, c); a2 = fmaf(a2, b, c); a3 = fmaf(a3, b, c);
-        a4 = fmaf(a4, b, c); a5 = fmaf(a5, b, c); a6 = fmaf(a6, b, c); a7 = fmaf(a7, b, c);
-    }
-    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    for (int it = 0; it < iters; ++it)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a[i] = fmaf(a[i], b, c);
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += a[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
 }  // namespace rp

@@ -11,7 +11,7 @@ constexpr int HB = 128;            // hypotheses per scoring work item
 constexpr int SCORE_THREADS = 256;
 constexpr int SCORE_WARPS = SCORE_THREADS / 32;
 constexpr int PT = 4;              // correspondences per thread per slice
-constexpr int EV = 128;            // trigger events kept per pair
+constexpr int EV = 256;            // trigger events kept per pair (expected ~2 ln H ~ 20)
 
 struct PairParams {
     long long off;        // first correspondence of this pair in the packed arrays
