@@ -177,15 +177,17 @@ def reference_arm(args, c, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def _ncu_traffic(kernel):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed
-    `ncu --set full` capture (profiles/rNN_dram_traffic_bytes.json, chunk of 1 700 pairs), or None."""
+def _ncu_traffic(kernel, pairs_per_launch):
+    """dram__bytes_read.sum + dram__bytes_write.sum of `kernel` from the committed `ncu --set full` capture
+    (profiles/rNN_dram_traffic_bytes.json: one launch over `pairs_in_launch` pairs of this workload), scaled
+    to the pairs one launch of this run processes; None when no capture is committed."""
     import glob
     files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_dram_traffic_bytes.json")))
     if not files:
         return None
     try:
-        return json.load(open(files[-1])).get(kernel)
+        d = json.load(open(files[-1]))
+        return d[kernel] / d["pairs_in_launch"] * pairs_per_launch
     except Exception:
         return None
 
@@ -338,7 +340,7 @@ def main():
                 "bound": "fp64_pipe", "achieved": achieved_tf, "peak": fp64_tf, "unit": "TFLOP/s",
                 "frac": achieved_tf / fp64_tf if (fp64_tf and achieved_tf) else None,
                 "peak_source": "rp_measure_pipes on this device (FP64 FMA chain; MEASURED_PEAKS.json has no FP64 figure)",
-                "traffic": _ncu_traffic("bound"),
+                "traffic": _ncu_traffic("bound", P * args.steps / n_chunk_launches),
                 "executed": {"pipe": "fp32", "tflops": executed_tf, "peak_tflops": fp32_tf,
                              "frac": executed_tf / fp32_tf if (fp32_tf and executed_tf) else None,
                              "point_scores_evaluated_per_s": evaluated / bound_s if bound_s > 0 else None,

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Turns the ncu captures under gpurun_out/ into the small text summaries committed under profiles/.
 
-    python tools/summarize_profiles.py r01          # reads gpurun_out/r01_*.{csv,ncu-rep,json}
+    python tools/summarize_profiles.py r01 4500     # reads gpurun_out/r01_*.{csv,ncu-rep,json}; 4500 = --pairs of the
+                                                    # `ncu --set full` captures (one launch = one chunk of that many pairs)
 """
 import collections
 import csv
@@ -100,6 +101,7 @@ def main():
     for f in (f"{tag}_bench.json", f"{tag}_bench_reference.json"):
         if os.path.exists(os.path.join(GO, f)):
             subprocess.run(["cp", os.path.join(GO, f), os.path.join(PR, f)])
+    traffic["pairs_in_launch"] = int(sys.argv[2]) if len(sys.argv) > 2 else 4500  # --pairs of the ncu captures
     json.dump(traffic, open(os.path.join(PR, f"{tag}_dram_traffic_bytes.json"), "w"), indent=1)
     print("\n\n".join(parts))
     print(traffic)
