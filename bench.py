@@ -157,7 +157,7 @@ def reference_arm(args, c, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n_sample = args.cpu_sample or max(4 * cores, 16)
+    n_sample = args.cpu_sample or max(16 * cores, 64)   # ~3 s of wall clock per step on 16 cores
     for _ in range(args.warmup):
         cpu_pairs_per_s(args.config, max(2, min(n_sample, cores)), seed=1)
     t_tot, n_tot, kind = 0.0, 0, "port"
@@ -365,7 +365,7 @@ def main():
             "gpu_launches": int(launches), "clocks": clk, "roofline": roofline}
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        n_sample = args.cpu_sample or max(4 * cores, 16)
+        n_sample = args.cpu_sample or max(64 * cores, 256)   # ~11 s of wall clock on 16 cores
         pps, cores, kind, dt = cpu_pairs_per_s(args.config, n_sample)
         line["cpu_baseline"] = {"value": pps, "unit": "pairs/s", "cores": cores, "kind": kind,
                                 "sample": f"{n_sample} pairs of the workload, per-pair calls from a {cores}-thread pool, {dt:.1f} s"}
