@@ -138,9 +138,12 @@ RP_HD double point_cost(const LMFrame &F, const LMParams &P, double x1_0, double
 //   Sampson          : w, t            (+ f | f1, f2)
 //   reprojection 1->2: w, t, shift1    (+ f | f1, f2)         (no scale, no shift2)
 //   reprojection 2->1: w, t, scale, shift2 (+ f | f1, f2)     (no shift1)
+// point_eval returns the cost contribution of the same correspondence as well (the value point_cost
+// computes), so one pass over the data serves both the accept test of the trial step and — when it is
+// accepted, the usual case — the normal equations of the next iteration.
 template <int VARIANT, int NP>
-RP_HD void point_accumulate(const LMFrame &F, const LMParams &P, double x1_0, double x1_1, double x2_0,
-                            double x2_1, double d1, double d2, NormalEq<NP> &N) {
+RP_HD double point_eval(const LMFrame &F, const LMParams &P, double x1_0, double x1_1, double x2_0,
+                        double x2_1, double d1, double d2, NormalEq<NP> &N) {
     constexpr bool FOCAL = (VARIANT == RP_SHARED || VARIANT == RP_VARYING);
     constexpr int CF2 = (VARIANT == RP_SHARED) ? 7 : 8;  // column of f2 (== f column when shared)
     constexpr unsigned M_POSE = 0x3Fu;                    // w (0-2), t (3-5)
@@ -153,6 +156,7 @@ RP_HD void point_accumulate(const LMFrame &F, const LMParams &P, double x1_0, do
     const M3 &R = F.R;
     const M3 &E = F.E;
     double J[NP];
+    double cost = 0.0;
 
     // ---- Sampson row ----
     if (P.weight_sampson > 0.0) {
@@ -164,6 +168,7 @@ RP_HD void point_accumulate(const LMFrame &F, const LMParams &P, double x1_0, do
         const double A = Ep1.x * Ep1.x + Ep1.y * Ep1.y, B = Etp2.x * Etp2.x + Etp2.y * Etp2.y;
         const double inv = 1.0 / sqrt(A * F.if2sq + B * F.if1sq);
         const double rs = C * inv;
+        cost += P.weight_sampson * loss_eval(P.loss_type, P.loss_scale, rs * rs);
         const double w = P.weight_sampson * loss_weight(P.loss_type, P.loss_scale, rs * rs);
         if (w != 0.0) {
 #pragma unroll
@@ -222,7 +227,7 @@ RP_HD void point_accumulate(const LMFrame &F, const LMParams &P, double x1_0, do
             N.template add_row<M_S>(w, J, rs);
         }
     }
-    if (!(P.scale_reproj > 0.0)) return;
+    if (!(P.scale_reproj > 0.0)) return cost;
 
     // ---- reprojection 1 -> 2 : Z = R (a p1) + t ----
     {
@@ -234,6 +239,7 @@ RP_HD void point_accumulate(const LMFrame &F, const LMParams &P, double x1_0, do
             const double iz = 1.0 / Z.z;
             const double u0 = Z.x * iz, u1 = Z.y * iz;
             const double r0 = F.f2 * u0 - x2_0, r1 = F.f2 * u1 - x2_1;
+            cost += loss_eval(P.loss_type, P.loss_scale, P.scale_reproj * (r0 * r0 + r1 * r1));
             const double w = P.scale_reproj *
                              loss_weight(P.loss_type, P.loss_scale, P.scale_reproj * (r0 * r0 + r1 * r1));
             if (w != 0.0) {
@@ -286,6 +292,7 @@ RP_HD void point_accumulate(const LMFrame &F, const LMParams &P, double x1_0, do
             const double iz = 1.0 / Y.z;
             const double u0 = Y.x * iz, u1 = Y.y * iz;
             const double r0 = F.f1 * u0 - x1_0, r1 = F.f1 * u1 - x1_1;
+            cost += loss_eval(P.loss_type, P.loss_scale, P.scale_reproj * (r0 * r0 + r1 * r1));
             const double w = P.scale_reproj *
                              loss_weight(P.loss_type, P.loss_scale, P.scale_reproj * (r0 * r0 + r1 * r1));
             if (w != 0.0) {
@@ -319,6 +326,13 @@ RP_HD void point_accumulate(const LMFrame &F, const LMParams &P, double x1_0, do
             }
         }
     }
+    return cost;
+}
+
+template <int VARIANT, int NP>
+RP_HD void point_accumulate(const LMFrame &F, const LMParams &P, double x1_0, double x1_1, double x2_0,
+                            double x2_1, double d1, double d2, NormalEq<NP> &N) {
+    (void)point_eval<VARIANT, NP>(F, P, x1_0, x1_1, x2_0, x2_1, d1, d2, N);
 }
 
 // parameter update of lm_impl's problem.step(): R <- R exp([dw]x), everything else additive

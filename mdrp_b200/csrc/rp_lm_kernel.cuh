@@ -98,7 +98,54 @@ __global__ void __launch_bounds__(THREADS, RP_LM_MIN_BLOCKS) lm_kernel(LMArgs a)
             return tot;
         };
 
-        double cost = block_cost(cur);
+        // one pass over the correspondences: cost of `m` (block total) and, in the caller's registers, the
+        // per-thread partial normal equations at `m`
+        auto block_eval = [&](const Model &m, NormalEq<NP> &N) -> double {
+            const LMFrame F = make_frame(m);
+            double c = 0.0;
+            N.clear();
+            for (int k = tid; k < n; k += LM_THREADS) {
+                if (mask && !mask[k]) continue;
+                const Pt64 p = pts[k];
+                c += point_eval<VARIANT, NP>(F, P, p.x1_0, p.x1_1, p.x2_0, p.x2_1, d1[k], d2[k], N);
+            }
+            c = warp_sum(c);
+            __syncthreads();
+            if (lane == 0) cred[wid] = c;
+            __syncthreads();
+            double tot = 0.0;
+#pragma unroll
+            for (int w = 0; w < LM_WARPS; ++w) tot += cred[w];
+            return tot;
+        };
+        // per-thread partials -> sA / sg (fixed order: deterministic)
+        auto reduce_normal = [&](NormalEq<NP> &N) {
+            warp_reduce_normal<NP>(N);
+            __syncthreads();
+            if (lane == 0) {
+#pragma unroll
+                for (int i = 0; i < NA; ++i) red[wid][i] = N.A[i];
+#pragma unroll
+                for (int i = 0; i < NP; ++i) red[wid][NA + i] = N.g[i];
+            }
+            __syncthreads();
+            if (tid < NA + NP) {
+                double v = 0.0;
+#pragma unroll
+                for (int w = 0; w < LM_WARPS; ++w) v += red[w][tid];
+                if (tid < NA) sA[tid] = v; else sg[tid - NA] = v;
+            }
+            __syncthreads();
+        };
+
+        // lm_impl evaluates the cost of a trial step and, if it is accepted, the Jacobians at the new point.
+        // Both walk the same residuals, so they are fused: the trial pass accumulates the normal equations
+        // speculatively and they are reduced only when the step is accepted (the last iteration, whose
+        // Jacobians nobody would read, is a cost-only pass).
+        NormalEq<NP> N;
+        double cost;
+        if (max_it > 0) { cost = block_eval(cur, N); reduce_normal(N); }
+        else cost = block_cost(cur);
         const double initial_cost = cost;
         double lambda = a.initial_lambda;
         double grad_norm = -1.0, step_norm = -1.0;
@@ -107,29 +154,6 @@ __global__ void __launch_bounds__(THREADS, RP_LM_MIN_BLOCKS) lm_kernel(LMArgs a)
         int it = 0;
         for (; it < max_it; ++it) {
             if (recompute) {
-                const LMFrame F = make_frame(cur);
-                NormalEq<NP> N;
-                N.clear();
-                for (int k = tid; k < n; k += LM_THREADS) {
-                    if (mask && !mask[k]) continue;
-                    const Pt64 p = pts[k];
-                    point_accumulate<VARIANT, NP>(F, P, p.x1_0, p.x1_1, p.x2_0, p.x2_1, d1[k], d2[k], N);
-                }
-                warp_reduce_normal<NP>(N);
-                if (lane == 0) {
-#pragma unroll
-                    for (int i = 0; i < NA; ++i) red[wid][i] = N.A[i];
-#pragma unroll
-                    for (int i = 0; i < NP; ++i) red[wid][NA + i] = N.g[i];
-                }
-                __syncthreads();
-                if (tid < NA + NP) {
-                    double v = 0.0;
-#pragma unroll
-                    for (int w = 0; w < LM_WARPS; ++w) v += red[w][tid];
-                    if (tid < NA) sA[tid] = v; else sg[tid - NA] = v;
-                }
-                __syncthreads();
                 double g2 = 0.0;
 #pragma unroll
                 for (int i = 0; i < NP; ++i) g2 += sg[i] * sg[i];
@@ -149,12 +173,14 @@ __global__ void __launch_bounds__(THREADS, RP_LM_MIN_BLOCKS) lm_kernel(LMArgs a)
             __syncthreads();
             step_norm = cred[0];
             if (stop_s) break;
-            const double cost_new = block_cost(trial);
+            const bool last = it == max_it - 1;
+            const double cost_new = last ? block_cost(trial) : block_eval(trial, N);
             if (cost_new < cost) {
                 __syncthreads();
                 if (tid == 0) cur = trial;
                 lambda = fmax(a.min_lambda, lambda / 10);
                 cost = cost_new;
+                if (!last) reduce_normal(N);
                 recompute = true;
             } else {
                 ++invalid_steps;
