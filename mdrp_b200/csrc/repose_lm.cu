@@ -3,6 +3,10 @@
 // reference bit for bit lives in repose_b200.cu, which is built with -fmad=false.
 #include "rp_lm_kernel.cuh"
 
+#ifndef RP_LM_THREADS
+#define RP_LM_THREADS 128   // block-per-problem variant; registers per thread = 65536 / (threads x blocks per SM)
+#endif
+
 namespace rp {
 
 template <class K>
@@ -17,7 +21,8 @@ static void launch_variant(int sms, bool warp_per_problem, const LMArgs &a, cuda
     if (warp_per_problem)
         lm_kernel<VARIANT, NP, 32><<<occupancy_grid(sms, lm_kernel<VARIANT, NP, 32>, 32), 32, 0, st>>>(a);
     else
-        lm_kernel<VARIANT, NP, 128><<<occupancy_grid(sms, lm_kernel<VARIANT, NP, 128>, 128), 128, 0, st>>>(a);
+        lm_kernel<VARIANT, NP, RP_LM_THREADS><<<occupancy_grid(sms, lm_kernel<VARIANT, NP, RP_LM_THREADS>, RP_LM_THREADS),
+                                                  RP_LM_THREADS, 0, st>>>(a);
 }
 
 int launch_lm_kernel(int sms, int variant, bool warp_per_problem, const LMArgs &a, cudaStream_t st) {

@@ -33,6 +33,8 @@ struct LMArgs {
     unsigned long long *lm_iters;
 };
 
+constexpr int LM_LIST_CAP = 8192;
+
 template <int NP>
 RP_D void warp_reduce_normal(NormalEq<NP> &N) {
 #pragma unroll
@@ -53,6 +55,11 @@ __global__ void __launch_bounds__(THREADS, RP_LM_MIN_BLOCKS) lm_kernel(LMArgs a)
     __shared__ double sA[NA], sg[NP];
     __shared__ double cred[LM_WARPS];
     __shared__ int stop_s;
+    // masked problems (the final refinement on the inlier set): the inlier indices, compacted once per
+    // problem so that every lane of the evaluation passes has work (problems with more than LM_LIST_CAP
+    // correspondences test the mask on the fly instead)
+    __shared__ unsigned short list_s[LM_LIST_CAP];
+    __shared__ int wcount[LM_WARPS];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n_prob = *a.n_prob;
     for (int pj = blockIdx.x; pj < n_prob; pj += gridDim.x) {
@@ -80,11 +87,38 @@ __global__ void __launch_bounds__(THREADS, RP_LM_MIN_BLOCKS) lm_kernel(LMArgs a)
         if (tid == 0) { cur = a.models[prob]; stop_s = 0; }
         __syncthreads();
 
+        const bool use_list = mask != nullptr && n <= LM_LIST_CAP;
+        int m_work = n;
+        if (use_list) {
+            // ordered compaction: warp w counts, then writes, the inliers of its contiguous range
+            const int lo = (int)(((long long)n * wid) / LM_WARPS), hi = (int)(((long long)n * (wid + 1)) / LM_WARPS);
+            int cnt = 0;
+            for (int b0 = lo; b0 < hi; b0 += 32) {
+                const int k = b0 + lane;
+                cnt += __popc(__ballot_sync(0xffffffffu, k < hi && mask[k]));
+            }
+            if (lane == 0) wcount[wid] = cnt;
+            __syncthreads();
+            int start = 0;
+            m_work = 0;
+#pragma unroll
+            for (int w = 0; w < LM_WARPS; ++w) { if (w < wid) start += wcount[w]; m_work += wcount[w]; }
+            for (int b0 = lo; b0 < hi; b0 += 32) {
+                const int k = b0 + lane;
+                const bool in = k < hi && mask[k];
+                const unsigned bal = __ballot_sync(0xffffffffu, in);
+                if (in) list_s[start + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)k;
+                start += __popc(bal);
+            }
+            __syncthreads();
+        }
+
         auto block_cost = [&](const Model &m) -> double {
             const LMFrame F = make_frame(m);
             double c = 0.0;
-            for (int k = tid; k < n; k += LM_THREADS) {
-                if (mask && !mask[k]) continue;
+            for (int i = tid; i < m_work; i += LM_THREADS) {
+                const int k = use_list ? (int)list_s[i] : i;
+                if (!use_list && mask && !mask[k]) continue;
                 const Pt64 p = pts[k];
                 c += point_cost<VARIANT>(F, P, p.x1_0, p.x1_1, p.x2_0, p.x2_1, d1[k], d2[k]);
             }
@@ -104,8 +138,9 @@ __global__ void __launch_bounds__(THREADS, RP_LM_MIN_BLOCKS) lm_kernel(LMArgs a)
             const LMFrame F = make_frame(m);
             double c = 0.0;
             N.clear();
-            for (int k = tid; k < n; k += LM_THREADS) {
-                if (mask && !mask[k]) continue;
+            for (int i = tid; i < m_work; i += LM_THREADS) {
+                const int k = use_list ? (int)list_s[i] : i;
+                if (!use_list && mask && !mask[k]) continue;
                 const Pt64 p = pts[k];
                 c += point_eval<VARIANT, NP>(F, P, p.x1_0, p.x1_1, p.x2_0, p.x2_1, d1[k], d2[k], N);
             }
