@@ -72,13 +72,14 @@ typedef struct {
     double max_reproj_error, max_epipolar_error;
     uint64_t seed;
     int32_t estimate_shift; /* monodepth_estimate_shift (calibrated variants) */
-    int32_t reserved0;
+    int32_t progressive_sampling; /* PROSAC sampling: correspondences sorted by decreasing quality */
     double weight_sampson;  /* monodepth_weight_sampson */
     /* final refinement (bundle_opt) */
     int64_t bundle_max_iterations;
     int32_t loss_type;
     int32_t reserved1;
     double loss_scale, gradient_tol, step_tol, initial_lambda, min_lambda, max_lambda;
+    int64_t max_prosac_iterations; /* RansacOptions::max_prosac_iterations (default 100000) */
 } rp_options;
 
 /* LM options for the stage entry point rp_refine_batch (BundleOptions) */
@@ -135,6 +136,10 @@ RP_API int rp_estimate_batch_dev(rp_ctx *ctx, int variant, int64_t n_pairs, cons
 /* R2: RandomSampler::generate_sample so@0x4f8970 — `iters` consecutive 3-samples out of n
  * points from `seed`; samples: [iters,3] int32. */
 RP_API int rp_sample_batch(rp_ctx *ctx, int64_t n, uint64_t seed, int64_t iters, int32_t *samples);
+/* the same with the sampler's PROSAC branch (initialize_prosac so@0x4f8a20): progressive_sampling != 0
+ * draws from a growing prefix of the (quality-sorted) points for the first max_prosac_iterations-1 samples */
+RP_API int rp_sample_batch_prosac(rp_ctx *ctx, int64_t n, uint64_t seed, int64_t iters, int32_t progressive_sampling,
+                                  int64_t max_prosac_iterations, int32_t *samples);
 
 /* S1-S4: minimal solvers on n_problems independent triplets.  x1h,x2h: [n,3,3] homogeneous
  * (x,y,1) points, d1,d2: [n,3].  models: [n,4], counts: [n] (solutions per problem). */

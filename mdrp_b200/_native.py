@@ -17,7 +17,7 @@ LOSS = {"TRIVIAL": 0, "TRUNCATED": 1, "HUBER": 2, "CAUCHY": 3, "TRUNCATED_CAUCHY
 
 EXPORTS = [
     "rp_create", "rp_destroy", "rp_last_error", "rp_default_options", "rp_launch_count",
-    "rp_estimate_batch_host", "rp_estimate_batch_dev", "rp_sample_batch", "rp_solve_batch",
+    "rp_estimate_batch_host", "rp_estimate_batch_dev", "rp_sample_batch", "rp_sample_batch_prosac", "rp_solve_batch",
     "rp_score_batch", "rp_refine_batch", "rp_measure_pipes", "rp_last_timing", "rp_gather_depths_dev",
 ]
 
@@ -40,11 +40,11 @@ class Options(C.Structure):
     _fields_ = [("max_iterations", C.c_int64), ("min_iterations", C.c_int64),
                 ("dyn_num_trials_mult", C.c_double), ("success_prob", C.c_double),
                 ("max_reproj_error", C.c_double), ("max_epipolar_error", C.c_double),
-                ("seed", C.c_uint64), ("estimate_shift", C.c_int32), ("reserved0", C.c_int32),
+                ("seed", C.c_uint64), ("estimate_shift", C.c_int32), ("progressive_sampling", C.c_int32),
                 ("weight_sampson", C.c_double), ("bundle_max_iterations", C.c_int64),
                 ("loss_type", C.c_int32), ("reserved1", C.c_int32), ("loss_scale", C.c_double),
                 ("gradient_tol", C.c_double), ("step_tol", C.c_double), ("initial_lambda", C.c_double),
-                ("min_lambda", C.c_double), ("max_lambda", C.c_double)]
+                ("min_lambda", C.c_double), ("max_lambda", C.c_double), ("max_prosac_iterations", C.c_int64)]
 
 
 class BundleOptions(C.Structure):
@@ -99,6 +99,8 @@ def load():
     L.rp_estimate_batch_dev.argtypes = est_args + [VP]
     L.rp_sample_batch.restype = C.c_int
     L.rp_sample_batch.argtypes = [VP, C.c_int64, C.c_uint64, C.c_int64, VP]
+    L.rp_sample_batch_prosac.restype = C.c_int
+    L.rp_sample_batch_prosac.argtypes = [VP, C.c_int64, C.c_uint64, C.c_int64, C.c_int32, C.c_int64, VP]
     L.rp_solve_batch.restype = C.c_int
     L.rp_solve_batch.argtypes = [VP, C.c_int, C.c_int64, VP, VP, VP, VP, VP, VP]
     L.rp_score_batch.restype = C.c_int
@@ -209,9 +211,12 @@ class Context:
             cams_ptr, C.byref(opt), models_ptr, stats_ptr, masks_ptr, stream or None))
 
     # ---- stage entry points -----------------------------------------------------------------
-    def sample(self, n, seed, iters):
+    def sample(self, n, seed, iters, progressive_sampling=False, max_prosac_iterations=100000):
         out = np.zeros((iters, 3), dtype=np.int32)
-        self._check(self._lib.rp_sample_batch(self._h, n, seed, iters, _ptr(out)))
+        if progressive_sampling:
+            self._check(self._lib.rp_sample_batch_prosac(self._h, n, seed, iters, 1, max_prosac_iterations, _ptr(out)))
+        else:
+            self._check(self._lib.rp_sample_batch(self._h, n, seed, iters, _ptr(out)))
         return out
 
     def solve(self, variant, x1h, x2h, d1, d2):

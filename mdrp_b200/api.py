@@ -141,8 +141,11 @@ def make_options(ransac_opt=None, bundle_opt=None, focal_variant=False) -> nv.Op
     for k in _RANSAC_KEYS:
         if k in ransac_opt:
             setattr(o, k, type(getattr(o, k))(ransac_opt[k]))
-    if ransac_opt.get("progressive_sampling", False):
-        raise NotImplementedError("PROSAC sampling is outside this build (SURVEY.md §8f item 4)")
+    # PROSAC (RandomSampler::initialize_prosac so@0x4f8a20): the caller passes correspondences sorted by
+    # decreasing quality, exactly as with the reference
+    o.progressive_sampling = int(bool(ransac_opt.get("progressive_sampling", False)))
+    if "max_prosac_iterations" in ransac_opt:
+        o.max_prosac_iterations = int(ransac_opt["max_prosac_iterations"])
     o.estimate_shift = int(bool(ransac_opt.get("monodepth_estimate_shift", False)))
     o.weight_sampson = float(np.float32(ransac_opt.get("monodepth_weight_sampson", 1.0)))
     if "max_iterations" in bundle_opt:

@@ -289,7 +289,11 @@ int run_chunk(rp_ctx *ctx, int variant, const rp_options &opt, const ChunkIO &io
     CK(cudaEventRecord(ev[1], st));
     // 2. sample
     if (iters > 0) {
-        sample_kernel<<<cdiv((long long)P * 32, 256), 256, 0, st>>>(P, iters, pairs, opt.seed, samples);
+        if (opt.progressive_sampling)
+            sample_prosac_kernel<<<cdiv((long long)P * 32, 256), 256, 0, st>>>(
+                P, iters, pairs, opt.seed, (unsigned long long)std::max<int64_t>(opt.max_prosac_iterations, 0), samples);
+        else
+            sample_kernel<<<cdiv((long long)P * 32, 256), 256, 0, st>>>(P, iters, pairs, opt.seed, samples);
         LAUNCHED();
     }
     CK(cudaEventRecord(ev[2], st));
@@ -679,6 +683,7 @@ void rp_default_options(rp_options *o) {
     memset(o, 0, sizeof *o);
     o->max_iterations = 100000; o->min_iterations = 1000; o->dyn_num_trials_mult = 3.0; o->success_prob = 0.9999;
     o->max_reproj_error = 12.0; o->max_epipolar_error = 1.0; o->seed = 0; o->estimate_shift = 0; o->weight_sampson = 1.0;
+    o->progressive_sampling = 0; o->max_prosac_iterations = 100000;
     o->bundle_max_iterations = 100; o->loss_type = RP_LOSS_CAUCHY; o->loss_scale = 1.0; o->gradient_tol = 1e-10;
     o->step_tol = 1e-8; o->initial_lambda = 1e-3; o->min_lambda = 1e-10; o->max_lambda = 1e10;
 }
@@ -711,7 +716,12 @@ int rp_last_timing(const rp_ctx *ctx, double *ms16, int64_t *counters8) {
 
 // ---- stage entry points -----------------------------------------------------------------------
 int rp_sample_batch(rp_ctx *ctx, int64_t n, uint64_t seed, int64_t iters, int32_t *samples) {
-    if (!ctx || !samples || n < 3 || iters < 0) return fail(ctx, RP_ERR_INVALID, "bad argument");
+    return rp_sample_batch_prosac(ctx, n, seed, iters, 0, 0, samples);
+}
+
+int rp_sample_batch_prosac(rp_ctx *ctx, int64_t n, uint64_t seed, int64_t iters, int32_t progressive_sampling,
+                           int64_t max_prosac_iterations, int32_t *samples) {
+    if (!ctx || !samples || n < 3 || iters < 0 || max_prosac_iterations < 0) return fail(ctx, RP_ERR_INVALID, "bad argument");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     DevBuf *B = ctx->buf;
@@ -722,7 +732,11 @@ int rp_sample_batch(rp_ctx *ctx, int64_t n, uint64_t seed, int64_t iters, int32_
     pp.n = (int)n; pp.valid = 1;
     CK(cudaMemcpyAsync(B[B_PAIRS].p, &pp, sizeof pp, cudaMemcpyHostToDevice, st));
     if (iters > 0) {
-        sample_kernel<<<1, 32, 0, st>>>(1, (int)iters, B[B_PAIRS].as<PairParams>(), seed, B[B_SAMPLES].as<int>());
+        if (progressive_sampling)
+            sample_prosac_kernel<<<1, 32, 0, st>>>(1, (int)iters, B[B_PAIRS].as<PairParams>(), seed,
+                                                   (unsigned long long)max_prosac_iterations, B[B_SAMPLES].as<int>());
+        else
+            sample_kernel<<<1, 32, 0, st>>>(1, (int)iters, B[B_PAIRS].as<PairParams>(), seed, B[B_SAMPLES].as<int>());
         LAUNCHED();
         CK(cudaMemcpyAsync(samples, B[B_SAMPLES].p, sizeof(int) * 3 * (size_t)iters, cudaMemcpyDeviceToHost, st));
     }

@@ -211,6 +211,111 @@ __global__ void sample_kernel(int n_pairs, int iters, const PairParams *pairs, u
     }
 }
 
+// PROSAC branch of the same sampler (generate_sample so@0x4f8970 with use_prosac, growth table of
+// initialize_prosac so@0x4f8a20).  Iteration j (sample_k = j+1 on entry) is a PROSAC draw while
+// j+1 < max_prosac: two distinct indices out of the first subset_sz-1 points plus the point subset_sz-1;
+// afterwards the uniform 3-draw.  subset_sz does not depend on the random numbers: it grows by one
+// whenever sample_k passes growth[subset_sz-1], and growth[] is a running sum that only ever has to be
+// advanced by one entry at a time, so no table is stored: every lane of the warp tracks
+// (subset_sz, T_n, growth[subset_sz-1]) through the 32 iterations of a step and keeps the value of its own
+// iteration.  The random state is then speculated exactly as in sample_kernel (2 draws per PROSAC
+// iteration, 3 per uniform one) with a sequential replay of the first lane that hits a duplicate.
+struct ProsacState {
+    unsigned long long subset_sz;   // current subset size (>= 3)
+    unsigned long long gidx;        // index n for which gval == growth[n] (recurrence advanced so far)
+    unsigned long long gval;        // growth[gidx] ("T_n_prime")
+    double T_n;
+};
+
+RP_D void prosac_init(ProsacState &ps, unsigned long long num_data, unsigned long long max_prosac) {
+    double T_n = (double)max_prosac;
+    for (unsigned long long i = 0; i < 3; ++i) T_n *= (double)(3 - i) / (double)(num_data - i);
+    ps.subset_sz = 3; ps.gidx = 2; ps.gval = 1; ps.T_n = T_n;
+}
+// state update at the end of a PROSAC generate_sample call; k = sample_k after its increment
+RP_D void prosac_advance(ProsacState &ps, unsigned long long k, unsigned long long num_data, unsigned long long max_prosac) {
+    if (k < max_prosac && k > ps.gval && ps.subset_sz < num_data) {
+        // subset_sz + 1 <= num_data: growth[subset_sz] is the next entry of the recurrence
+        const unsigned long long n = ps.subset_sz;  // == gidx + 1 whenever n >= 3
+        const double T_next = ((double)n + 1.0) * ps.T_n / (((double)n + 1.0) - 3.0);
+        ps.gval = (unsigned long long)((double)ps.gval + ceil(T_next - ps.T_n));
+        ps.T_n = T_next;
+        ps.gidx = n;
+        ps.subset_sz = n + 1;
+    }
+}
+
+__global__ void sample_prosac_kernel(int n_pairs, int iters, const PairParams *pairs, uint64_t seed,
+                                     unsigned long long max_prosac, int *samples) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= n_pairs) return;
+    const PairParams pp = pairs[warp];
+    if (!pp.valid) return;
+    const uint64_t n = (uint64_t)pp.n;
+    const uint64_t G = 0x9e3779b97f4a7c15ULL;
+    int *out = samples + (size_t)warp * iters * 3;
+    uint64_t base = seed;
+    ProsacState ps;
+    prosac_init(ps, n, max_prosac);
+    for (int it0 = 0; it0 < iters; it0 += 32) {
+        const int group = min(32, iters - it0);
+        // PROSAC iterations of this step: j + 1 < max_prosac
+        const long long np_ll = (long long)max_prosac - 1 - (long long)it0;
+        const int n_prosac = (int)max(0ll, min((long long)group, np_ll));
+        unsigned long long my_sz = 3;
+        for (int l = 0; l < n_prosac; ++l) {
+            if (l == lane) my_sz = ps.subset_sz;
+            prosac_advance(ps, (unsigned long long)(it0 + l) + 2ull, n, max_prosac);
+        }
+        const bool prosac = lane < n_prosac;
+        const uint64_t mod = prosac ? my_sz - 1 : n;
+        int done = 0;
+        while (done < group) {
+            // draws consumed by the lanes done..lane-1 of this round
+            const int lp = max(lane, done);
+            const int pro_before = max(0, min(lp, n_prosac) - min(done, n_prosac));
+            const uint64_t draws_before = 2ULL * (uint64_t)pro_before + 3ULL * (uint64_t)(lp - done - pro_before);
+            uint64_t st = base + G * draws_before;
+            const uint64_t st0 = st;
+            const uint32_t i0 = draw_index(st, mod), i1 = draw_index(st, mod);
+            const uint32_t i2 = prosac ? (uint32_t)(my_sz - 1) : draw_index(st, mod);
+            const bool active = lane >= done && lane < group;
+            const bool dup = active && (i1 == i0 || (!prosac && (i2 == i0 || i2 == i1)));
+            const unsigned m = __ballot_sync(0xffffffffu, dup);
+            const int first = m ? (__ffs(m) - 1) : group;
+            if (active && lane < first) {
+                int *o = out + (size_t)(it0 + lane) * 3;
+                o[0] = (int)i0; o[1] = (int)i1; o[2] = (int)i2;
+            }
+            if (first < group) {
+                uint64_t s2 = st0;
+                if (lane == first) {
+                    uint32_t s[3];
+                    const int nd = prosac ? 2 : 3;
+                    for (int i = 0; i < nd; ++i) {
+                        bool ok = false;
+                        while (!ok) {
+                            s[i] = draw_index(s2, mod);
+                            ok = true;
+                            for (int j = 0; j < i; ++j) if (s[i] == s[j]) ok = false;
+                        }
+                    }
+                    if (prosac) s[2] = (uint32_t)(my_sz - 1);
+                    int *o = out + (size_t)(it0 + lane) * 3;
+                    o[0] = (int)s[0]; o[1] = (int)s[1]; o[2] = (int)s[2];
+                }
+                base = __shfl_sync(0xffffffffu, s2, first);
+                done = first + 1;
+            } else {
+                const int pro_rest = max(0, min(group, n_prosac) - min(done, n_prosac));
+                base = base + G * (2ULL * (uint64_t)pro_rest + 3ULL * (uint64_t)(group - done - pro_rest));
+                done = group;
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // solve: one thread per RANSAC iteration, block = (segment of SEG iterations, pair).  Solutions
 // are compacted in (iteration, solution) order with a block-wide exclusive scan per round.

@@ -51,7 +51,8 @@ class RansacOpt(C.Structure):
     _fields_ = [("max_iterations", C.c_int64), ("min_iterations", C.c_int64),
                 ("dyn_num_trials_mult", C.c_double), ("success_prob", C.c_double),
                 ("max_reproj_error", C.c_double), ("max_epipolar_error", C.c_double),
-                ("seed", C.c_uint64), ("estimate_shift", C.c_int), ("weight_sampson", C.c_double)]
+                ("seed", C.c_uint64), ("estimate_shift", C.c_int), ("weight_sampson", C.c_double),
+                ("progressive_sampling", C.c_int), ("max_prosac_iterations", C.c_int64)]
 
 
 class RansacStats(C.Structure):
@@ -68,9 +69,10 @@ def bundle_opt(max_iterations=100, loss_type="CAUCHY", loss_scale=1.0, gradient_
 
 def ransac_opt(max_iterations=100000, min_iterations=1000, dyn_num_trials_mult=3.0,
                success_prob=0.9999, max_reproj_error=12.0, max_epipolar_error=1.0, seed=0,
-               estimate_shift=False, weight_sampson=1.0):
+               estimate_shift=False, weight_sampson=1.0, progressive_sampling=False, max_prosac_iterations=100000):
     return RansacOpt(max_iterations, min_iterations, dyn_num_trials_mult, success_prob,
-                     max_reproj_error, max_epipolar_error, seed, int(estimate_shift), weight_sampson)
+                     max_reproj_error, max_epipolar_error, seed, int(estimate_shift), weight_sampson,
+                     int(progressive_sampling), max_prosac_iterations)
 
 
 def build(force=False):
@@ -101,6 +103,11 @@ def lib():
         L.ro_random_int.argtypes = [C.POINTER(C.c_uint64)]
         L.ro_draw_sample.restype = None
         L.ro_draw_sample.argtypes = [C.c_size_t, C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(C.c_size_t)]
+        L.ro_prosac_growth.restype = None
+        L.ro_prosac_growth.argtypes = [C.c_size_t, C.c_size_t, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.ro_generate_samples.restype = None
+        L.ro_generate_samples.argtypes = [C.c_size_t, C.c_size_t, C.c_uint64, C.c_int, C.c_size_t, C.c_size_t,
+                                          C.POINTER(C.c_size_t)]
         L.ro_essential_from_motion.argtypes = [DP, DP, DP]
         L.ro_msac_score_pose.restype = C.c_double
         L.ro_msac_score_pose.argtypes = [DP, DP, DP, DP, C.c_size_t, C.c_double, C.POINTER(C.c_size_t)]
@@ -160,6 +167,18 @@ def draw_sample(sample_sz, n, state):
     out = (C.c_size_t * sample_sz)()
     lib().ro_draw_sample(sample_sz, n, C.byref(s), out)
     return np.array(list(out), dtype=np.int64), s.value
+
+
+def prosac_growth(num_data, sample_sz, max_prosac_iterations):
+    out = (C.c_size_t * max(num_data, sample_sz))()
+    lib().ro_prosac_growth(num_data, sample_sz, max_prosac_iterations, out)
+    return np.array(list(out), dtype=np.int64)
+
+
+def generate_samples(num_data, sample_sz, seed, use_prosac, max_prosac_iterations, iters):
+    out = (C.c_size_t * (iters * sample_sz))()
+    lib().ro_generate_samples(num_data, sample_sz, seed, int(bool(use_prosac)), max_prosac_iterations, iters, out)
+    return np.array(list(out), dtype=np.int64).reshape(iters, sample_sz)
 
 
 def essential_from_motion(q, t):

@@ -192,6 +192,41 @@ def draw_sample(sample_sz: int, n: int, state: int):
     return out.astype(np.int64), s.value
 
 
+class RandomSamplerBuf(C.Structure):
+    """poselib::RandomSampler (SURVEY.md Appendix A.2): num_data@0, sample_sz@8, state@0x10, use_prosac@0x18,
+    max_prosac_iterations@0x20, sample_k@0x28, subset_sz@0x30, growth vector@0x38."""
+    _fields_ = [("num_data", C.c_size_t), ("sample_sz", C.c_size_t), ("state", C.c_uint64),
+                ("use_prosac", C.c_uint8), ("_pad", C.c_uint8 * 7), ("max_prosac_iterations", C.c_size_t),
+                ("sample_k", C.c_size_t), ("subset_sz", C.c_size_t), ("growth", StdVec)]
+
+
+def generate_samples(num_data: int, sample_sz: int, seed: int, use_prosac: bool, max_prosac_iterations: int,
+                     iters: int):
+    """`iters` calls of RandomSampler::generate_sample so@0x4f8970 on a sampler set up like the constructor does
+    (initialize_prosac so@0x4f8a20 when use_prosac).  Returns (samples [iters, sample_sz], growth table)."""
+    L = lib()
+    init = L._ZN7poselib13RandomSampler17initialize_prosacEv
+    init.restype = None
+    init.argtypes = [C.POINTER(RandomSamplerBuf)]
+    gen = L._ZN7poselib13RandomSampler15generate_sampleEPSt6vectorImSaImEE
+    gen.restype = None
+    gen.argtypes = [C.POINTER(RandomSamplerBuf), C.POINTER(StdVec)]
+    growth = np.zeros(max(num_data, sample_sz), dtype=np.uint64)  # pre-sized: the binary must not reallocate it
+    sb = RandomSamplerBuf()
+    sb.num_data, sb.sample_sz, sb.state = num_data, sample_sz, seed
+    sb.use_prosac, sb.max_prosac_iterations = int(bool(use_prosac)), max_prosac_iterations
+    sb.growth = vec_of(growth)
+    if use_prosac:
+        init(C.byref(sb))
+    out = np.zeros((iters, sample_sz), dtype=np.int64)
+    cur = np.zeros(sample_sz, dtype=np.uint64)
+    v = vec_of(cur)
+    for i in range(iters):
+        gen(C.byref(sb), C.byref(v))
+        out[i] = cur
+    return out, growth.astype(np.int64)
+
+
 def _pts(x):
     return np.ascontiguousarray(x, dtype=np.float64)
 

@@ -64,6 +64,8 @@ typedef struct {
     uint64_t seed;
     int estimate_shift;
     double weight_sampson;
+    int progressive_sampling;          /* RansacOptions::progressive_sampling (PROSAC) */
+    int64_t max_prosac_iterations;     /* RansacOptions::max_prosac_iterations (default 100000) */
 } ro_ransac_opt;
 
 typedef struct {
@@ -93,6 +95,68 @@ RO_API void ro_draw_sample(size_t sample_sz, size_t n, uint64_t *state, size_t *
                 if (out[i] == out[j]) { done = 0; break; }
         }
     }
+}
+
+/* RandomSampler (robust/sampling.cc): the PROSAC branch of generate_sample so@0x4f8970 and the growth
+ * table of initialize_prosac so@0x4f8a20.  The data are assumed sorted by decreasing quality.  While
+ * sample_k < max_prosac_iterations a sample is sample_sz-1 distinct indices out of the first subset_sz-1
+ * points plus the point subset_sz-1 itself; the subset grows by one whenever sample_k passes
+ * growth[subset_sz-1].  Afterwards (or with use_prosac = 0) it is the uniform draw_sample.          */
+typedef struct {
+    size_t num_data, sample_sz;
+    uint64_t state;
+    int use_prosac;
+    size_t max_prosac_iterations, sample_k, subset_sz;
+    size_t *growth;
+} ro_sampler;
+
+RO_API void ro_prosac_growth(size_t num_data, size_t sample_sz, size_t max_prosac_iterations, size_t *growth) {
+    double T_n = (double)max_prosac_iterations;
+    for (size_t i = 0; i < sample_sz; ++i) T_n *= (double)(sample_sz - i) / (double)(num_data - i);
+    for (size_t i = 0; i < sample_sz; ++i) growth[i] = 1;
+    size_t T_n_prime = 1;
+    for (size_t n = sample_sz; n < num_data; ++n) {
+        const double T_n_next = ((double)n + 1.0) * T_n / (((double)n + 1.0) - (double)sample_sz);
+        T_n_prime = (size_t)((double)T_n_prime + ceil(T_n_next - T_n));
+        growth[n] = T_n_prime;
+        T_n = T_n_next;
+    }
+}
+
+static void ro_sampler_init(ro_sampler *s, size_t num_data, size_t sample_sz, uint64_t seed, int use_prosac,
+                            size_t max_prosac_iterations) {
+    s->num_data = num_data; s->sample_sz = sample_sz; s->state = seed;
+    s->use_prosac = use_prosac; s->max_prosac_iterations = max_prosac_iterations;
+    s->sample_k = 0; s->subset_sz = 0; s->growth = NULL;
+    if (use_prosac) {
+        const size_t len = num_data > sample_sz ? num_data : sample_sz;
+        s->growth = (size_t *)calloc(len, sizeof(size_t));
+        ro_prosac_growth(num_data, sample_sz, max_prosac_iterations, s->growth);
+        s->sample_k = 1;
+        s->subset_sz = sample_sz;
+    }
+}
+
+static void ro_sampler_generate(ro_sampler *s, size_t *sample) {
+    if (s->use_prosac && s->sample_k < s->max_prosac_iterations) {
+        ro_draw_sample(s->sample_sz - 1, s->subset_sz - 1, &s->state, sample);
+        sample[s->sample_sz - 1] = s->subset_sz - 1;
+        s->sample_k++;
+        if (s->sample_k < s->max_prosac_iterations && s->sample_k > s->growth[s->subset_sz - 1]) {
+            if (++s->subset_sz > s->num_data) s->subset_sz = s->num_data;
+        }
+    } else {
+        ro_draw_sample(s->sample_sz, s->num_data, &s->state, sample);
+    }
+}
+
+/* `iters` consecutive samples of a fresh sampler: out [iters, sample_sz] */
+RO_API void ro_generate_samples(size_t num_data, size_t sample_sz, uint64_t seed, int use_prosac,
+                                size_t max_prosac_iterations, size_t iters, size_t *out) {
+    ro_sampler s;
+    ro_sampler_init(&s, num_data, sample_sz, seed, use_prosac, max_prosac_iterations);
+    for (size_t i = 0; i < iters; ++i) ro_sampler_generate(&s, out + i * sample_sz);
+    free(s.growth);
 }
 
 /* ------------------------------------------------------------------------- */
@@ -1126,14 +1190,14 @@ typedef struct {
     size_t n;
     const double *x1, *x2, *d1, *d2;
     const ro_ransac_opt *opt;
-    uint64_t rng;
+    ro_sampler sampler;
     double sq_thr, scale_reproj;
     ro_bundle_opt lo;
 } estimator;
 
 static int est_generate(estimator *e, ro_model *models) {
     size_t s[3];
-    ro_draw_sample(3, e->n, &e->rng, s);
+    ro_sampler_generate(&e->sampler, s);
     double x1h[9], x2h[9], d1[3], d2[3];
     for (int i = 0; i < 3; ++i) {
         x1h[3 * i] = e->x1[2 * s[i]]; x1h[3 * i + 1] = e->x1[2 * s[i] + 1]; x1h[3 * i + 2] = 1.0;
@@ -1167,7 +1231,6 @@ RO_API void ro_ransac(int variant, const double *x1, const double *x2, const dou
                       char *inliers) {
     estimator e;
     e.variant = variant; e.n = n; e.x1 = x1; e.x2 = x2; e.d1 = d1; e.d2 = d2; e.opt = opt;
-    e.rng = opt->seed;
     e.sq_thr = opt->max_epipolar_error * opt->max_epipolar_error;
     e.scale_reproj = opt->max_reproj_error > 0.0
                          ? (opt->max_epipolar_error * opt->max_epipolar_error) /
@@ -1186,6 +1249,7 @@ RO_API void ro_ransac(int variant, const double *x1, const double *x2, const dou
     stats->inlier_ratio = 0.0; stats->model_score = DBL_MAX;
     if (inliers) memset(inliers, 0, n);
     if (n < 3) return;
+    ro_sampler_init(&e.sampler, n, 3, opt->seed, opt->progressive_sampling, (size_t)opt->max_prosac_iterations);
 
     size_t best_minimal_inliers = 0;
     double best_minimal_score = DBL_MAX;
@@ -1240,6 +1304,7 @@ RO_API void ro_ransac(int variant, const double *x1, const double *x2, const dou
         *best = refined;
     }
     stats->inlier_ratio = (double)stats->num_inliers / (double)n;
+    free(e.sampler.growth);
     if (inliers) {
         if (variant == RO_CALIB || variant == RO_CALIB_SHIFT)
             ro_get_inliers_pose(best->q, best->t, x1, x2, n, e.sq_thr, inliers);

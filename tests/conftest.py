@@ -24,6 +24,11 @@ def e2e_golden():
 
 
 @pytest.fixture(scope="session")
+def prosac_golden():
+    return np.load(os.path.join(ROOT, "tests", "golden", "prosac.npz"))
+
+
+@pytest.fixture(scope="session")
 def port():
     from oracle import port as p
     p.build()

@@ -39,7 +39,8 @@ def test_library_is_sm100a_and_has_no_oracle_dependency(lib_path):
 def test_struct_layouts_match_header():
     from mdrp_b200 import _native as nv
     assert C.sizeof(nv.Model) == 96 and C.sizeof(nv.Stats) == 40
-    assert C.sizeof(nv.Options) == 8 * 2 + 8 * 4 + 8 + 8 + 8 + 8 + 8 + 8 * 6
+    assert C.sizeof(nv.Options) == 8 * 2 + 8 * 4 + 8 + 8 + 8 + 8 + 8 + 8 * 6 + 8
+    assert nv.Options.progressive_sampling.offset == 60 and nv.Options.max_prosac_iterations.offset == 136
     assert C.sizeof(nv.BundleOptions) == 8 + 8 + 8 * 6
     assert C.sizeof(nv.BundleStats) == 56
 
@@ -51,6 +52,7 @@ def test_default_options_are_poselib_defaults(lib_path):
     assert (o.dyn_num_trials_mult, o.success_prob) == (3.0, 0.9999)
     assert (o.max_reproj_error, o.max_epipolar_error) == (12.0, 1.0)
     assert o.bundle_max_iterations == 100 and o.loss_type == nv.LOSS["CAUCHY"]
+    assert (o.progressive_sampling, o.max_prosac_iterations) == (0, 100000)
     assert (o.gradient_tol, o.step_tol, o.initial_lambda, o.min_lambda, o.max_lambda) == (1e-10, 1e-8, 1e-3, 1e-10, 1e10)
 
 
@@ -80,6 +82,9 @@ def test_option_dict_mapping(lib_path):
     # focal variants default loss_scale to half the epipolar threshold (whl:METADATA:143)
     assert api.make_options({"max_epipolar_error": 2.0}, {}, focal_variant=True).loss_scale == 1.0
     assert api.make_options({"max_epipolar_error": 2.0}, {"loss_scale": 0.3}, focal_variant=True).loss_scale == 0.3
+    p = api.make_options({"progressive_sampling": True, "max_prosac_iterations": 5000}, {})
+    assert (p.progressive_sampling, p.max_prosac_iterations) == (1, 5000)
+    assert api.make_options({"progressive_sampling": False}, {}).progressive_sampling == 0
     # fork flags of eval.py:105-123
     r = api._fork_ransac({"use_ours": True, "solver_shift": True, "use_p3p": False, "weight_sampson": 1.0})
     assert r["monodepth_estimate_shift"] is True

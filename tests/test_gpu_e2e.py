@@ -61,6 +61,51 @@ def test_golden_end_to_end(ctx, e2e_golden):
         assert models_close(models[0], g[key + "_model"], rtol=1e-6, atol=1e-8), key  # north_star: 1e-6 relative
 
 
+def test_prosac_golden_end_to_end(ctx, prosac_golden):
+    """progressive_sampling=True: outputs of the reference binary on committed, quality-sorted inputs."""
+    g = prosac_golden
+    keys = sorted(k[:-6] for k in g.files if k.endswith("_model"))
+    assert len(keys) >= 12
+    for key in keys:
+        name = key.split("_cfg")[0].split("_hard")[0]
+        variant = {"calib": 0, "calib_shift": 1, "shared": 2, "varying": 3}[name]
+        iters, mp = (int(v) for v in g[key + "_opts"])
+        o = _options(iters, shift=variant == 1, seed=int(key[-1]))
+        o.progressive_sampling, o.max_prosac_iterations = 1, mp
+        n = len(g[key + "_d1"])
+        f1, f2 = g[key + "_f"]
+        cams = np.array([[f1, f1, 640, 480, f2, f2, 640, 480]]) if variant < 2 else None
+        models, stats, masks = ctx.estimate_batch_host(variant, [0, n], g[key + "_x1"], g[key + "_x2"], g[key + "_d1"],
+                                                       g[key + "_d2"], cams, o)
+        ref = g[key + "_stats"]
+        assert (stats[0]["refinements"], stats[0]["iterations"], stats[0]["num_inliers"]) == tuple(ref), key
+        assert abs(stats[0]["model_score"] - g[key + "_fstats"][1]) <= 1e-11 * g[key + "_fstats"][1], key
+        assert np.array_equal(masks, g[key + "_mask"]), key
+        assert models_close(models[0], g[key + "_model"], rtol=1e-6, atol=1e-8), key
+
+
+def test_prosac_batch_vs_oracle_with_early_termination(ctx, port):
+    """PROSAC in a ragged batch with the default early-termination mode (min_iterations < max_iterations)."""
+    sizes = [300, 64, 1000, 3, 517]
+    scs = [synth.scene_for("cfg1_calib_scale", 90 + i, n=n) for i, n in enumerate(sizes)]
+    offs = np.r_[0, np.cumsum(sizes)]
+    x1, x2 = np.concatenate([s.x1 for s in scs]), np.concatenate([s.x2 for s in scs])
+    d1, d2 = np.concatenate([s.d1 for s in scs]), np.concatenate([s.d2 for s in scs])
+    cams = np.array([[s.f1, s.f1, 640, 480, s.f2, s.f2, 640, 480] for s in scs], dtype=np.float64)
+    o = _options(3000, seed=5, min_iters=100)
+    o.progressive_sampling, o.max_prosac_iterations = 1, 400
+    models, stats, masks = ctx.estimate_batch_host(0, offs, x1, x2, d1, d2, cams, o)
+    ro = port.ransac_opt(max_iterations=3000, min_iterations=100, max_epipolar_error=2.0, max_reproj_error=16.0, seed=5,
+                         progressive_sampling=True, max_prosac_iterations=400)
+    bo = port.bundle_opt(loss_type="TRUNCATED_CAUCHY", loss_scale=1.0)
+    for i, s in enumerate(scs):
+        m, st, mask = port.estimate(0, s.x1, s.x2, s.d1, s.d2, [s.f1, s.f1, 640, 480], [s.f2, s.f2, 640, 480], ro, bo)
+        assert (stats[i]["refinements"], stats[i]["iterations"], stats[i]["num_inliers"]) == \
+            (st.refinements, st.iterations, st.num_inliers), i
+        assert np.array_equal(masks[offs[i]:offs[i + 1]].astype(bool), mask), i
+        assert models_close(models[i], m, rtol=1e-6, atol=1e-8), i
+
+
 @pytest.mark.parametrize("cfg", ["cfg1_calib_scale", "cfg2_calib_shift", "cfg3_shared_focal", "cfg4_varying_focal"])
 def test_batch_vs_oracle(ctx, port, cfg):
     """A ragged batch (different N per pair) against the oracle run pair by pair."""

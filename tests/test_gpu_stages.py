@@ -24,6 +24,21 @@ def test_sampler_bit_exact(ctx, port, stages):
             assert (s == got[k]).all(), (n, k)
 
 
+def test_prosac_sampler_bit_exact(ctx, port, prosac_golden):
+    """PROSAC branch of the sampler against the reference binary's sequences and, on longer runs (including the
+    switch back to uniform sampling after max_prosac_iterations), against the oracle."""
+    g = prosac_golden
+    for k in [k for k in g.files if k.startswith("sampler_")]:
+        n, seed, mp = (int(p[1:]) for p in k.split("_")[1:])
+        got = ctx.sample(n, seed, len(g[k]), progressive_sampling=True, max_prosac_iterations=mp)
+        assert np.array_equal(got, g[k]), k
+    for n, seed, mp, iters in ((3, 1, 100000, 200), (5, 2, 100000, 4000), (2000, 42, 100000, 10000), (2000, 42, 777, 3000),
+                               (40, 3, 33, 100), (1000, 8, 1, 64), (1000, 8, 0, 64), (100000, 4, 5000, 6000)):
+        got = ctx.sample(n, seed, iters, progressive_sampling=True, max_prosac_iterations=mp)
+        ref = port.generate_samples(n, 3, seed, True, mp, iters)
+        assert np.array_equal(got, ref), (n, seed, mp)
+
+
 @pytest.mark.parametrize("variant", VARIANTS)
 def test_solvers_vs_golden_and_oracle(ctx, port, stages, variant):
     v = VARIANT_ID[variant]

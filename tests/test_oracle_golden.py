@@ -98,3 +98,45 @@ def test_end_to_end_matches_reference(e2e_golden, port):
         assert abs(st.model_score - g[key + "_fstats"][1]) <= 1e-12 * abs(g[key + "_fstats"][1]), key
         assert (mask == g[key + "_mask"].astype(bool)).all(), key
         assert models_close(m, g[key + "_model"], rtol=1e-8, atol=1e-10), key
+
+
+# ---- PROSAC (progressive_sampling=True): golden vectors of tests/golden/make_golden_prosac.py ----------------
+def _prosac_keys(g):
+    return sorted(k[:-6] for k in g.files if k.endswith("_model"))
+
+
+def test_prosac_sampler_and_growth_bit_exact(prosac_golden, port):
+    g = prosac_golden
+    cases = [k for k in g.files if k.startswith("sampler_")]
+    assert len(cases) >= 7
+    for k in cases:
+        n, seed, mp = (int(p[1:]) for p in k.split("_")[1:])
+        ref = g[k]
+        got = port.generate_samples(n, 3, seed, True, mp, len(ref))
+        assert np.array_equal(got, ref), k
+        assert np.array_equal(port.prosac_growth(n, 3, mp), g[f"growth_n{n}_m{mp}"]), k
+        # the last index of a PROSAC sample is the newest point of the subset: non-decreasing while PROSAC is on
+        on = min(len(ref), mp - 1)
+        assert (np.diff(ref[:on, 2]) >= 0).all() and (np.diff(ref[:on, 2]) <= 1).all(), k
+
+
+def test_prosac_end_to_end_matches_reference(prosac_golden, port):
+    g = prosac_golden
+    keys = _prosac_keys(g)
+    assert len(keys) >= 12
+    for key in keys:
+        name = key.split("_cfg")[0].split("_hard")[0]
+        variant = {"calib": 0, "calib_shift": 1, "shared": 2, "varying": 3}[name]
+        iters, mp = (int(v) for v in g[key + "_opts"])
+        idx = int(key[-1])
+        ro = port.ransac_opt(max_iterations=iters, min_iterations=iters, max_epipolar_error=2.0, max_reproj_error=16.0,
+                             seed=idx, estimate_shift=variant == 1, progressive_sampling=True, max_prosac_iterations=mp)
+        bo = port.bundle_opt(loss_type="TRUNCATED_CAUCHY", loss_scale=1.0)
+        f1, f2 = g[key + "_f"]
+        cams = ([f1, f1, 640, 480], [f2, f2, 640, 480]) if variant < 2 else (None, None)
+        m, st, mask = port.estimate(variant, g[key + "_x1"], g[key + "_x2"], g[key + "_d1"], g[key + "_d2"],
+                                    cams[0], cams[1], ro, bo)
+        assert (st.refinements, st.iterations, st.num_inliers) == tuple(int(v) for v in g[key + "_stats"]), key
+        assert abs(st.model_score - g[key + "_fstats"][1]) <= 1e-12 * abs(g[key + "_fstats"][1]), key
+        assert (mask == g[key + "_mask"].astype(bool)).all(), key
+        assert models_close(m, g[key + "_model"], rtol=1e-8, atol=1e-10), key

@@ -28,6 +28,18 @@ def test_sampler(ref, port):
     assert (v1, s1) == (v2, s2)
 
 
+def test_prosac_sampler(ref, port):
+    """RandomSampler::generate_sample so@0x4f8970 / initialize_prosac so@0x4f8a20 on a hand-built sampler struct."""
+    for n, mp, iters, seed in ((3, 100000, 50, 0), (4, 1000, 300, 5), (10, 100000, 500, 3), (50, 100000, 3000, 0),
+                               (300, 200, 600, 1), (2000, 100000, 5000, 7), (100000, 100000, 1500, 9)):
+        a, growth = ref.generate_samples(n, 3, seed, True, mp, iters)
+        b = port.generate_samples(n, 3, seed, True, mp, iters)
+        assert np.array_equal(a, b), (n, mp)
+        assert np.array_equal(growth, port.prosac_growth(n, 3, mp)), (n, mp)
+    a, _ = ref.generate_samples(100, 3, 5, False, 100000, 500)
+    assert np.array_equal(a, port.generate_samples(100, 3, 5, False, 100000, 500))
+
+
 def test_scorer_and_essential_bit_exact(ref, port):
     rng = np.random.default_rng(1)
     sc = synth.scene_for("cfg2_calib_shift", 3, n=700)
@@ -81,16 +93,19 @@ def test_solvers(ref, port, variant):
 
 @pytest.mark.parametrize("variant,cfg", [(0, "cfg1_calib_scale"), (1, "cfg2_calib_shift"), (2, "cfg3_shared_focal"),
                                          (3, "cfg4_varying_focal"), (0, "hard_calib")])
-def test_end_to_end(ref, port, variant, cfg):
+@pytest.mark.parametrize("prosac", [False, True])
+def test_end_to_end(ref, port, variant, cfg, prosac):
     pl = ref.poselib()
     for idx in range(2):
         sc = synth.scene_for(cfg, 40 + idx, n=500)
         iters = 400
+        mp = 100000 if idx == 0 else 250  # second scene: PROSAC switches to uniform sampling mid-run
         ro = {"max_iterations": iters, "min_iterations": iters, "max_epipolar_error": 2.0, "max_reproj_error": 16.0,
-              "seed": 3, "monodepth_estimate_shift": variant == 1}
+              "seed": 3, "monodepth_estimate_shift": variant == 1, "progressive_sampling": prosac,
+              "max_prosac_iterations": mp}
         bo = {"loss_type": "TRUNCATED_CAUCHY"}
         rop = port.ransac_opt(max_iterations=iters, min_iterations=iters, max_epipolar_error=2.0, max_reproj_error=16.0,
-                              seed=3, estimate_shift=variant == 1)
+                              seed=3, estimate_shift=variant == 1, progressive_sampling=prosac, max_prosac_iterations=mp)
         bop = port.bundle_opt(loss_type="TRUNCATED_CAUCHY", loss_scale=1.0)
         if variant < 2:
             c1, c2 = sc.camera_dicts()
