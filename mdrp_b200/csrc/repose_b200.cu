@@ -146,7 +146,10 @@ int launch_solve(rp_ctx *ctx, int variant, const SolveArgs &a, int n_pairs, cuda
     dim3 grid(a.nseg, n_pairs);
     switch (variant) {
     case RP_CALIB: solve_kernel<RP_CALIB><<<grid, SOLVE_THREADS, 0, st>>>(a); break;
-    case RP_CALIB_SHIFT: solve_kernel<RP_CALIB_SHIFT><<<grid, SOLVE_THREADS, 0, st>>>(a); break;
+    case RP_CALIB_SHIFT:
+        if (getenv("RP_SOLVE_GENERIC")) solve_kernel<RP_CALIB_SHIFT><<<grid, SOLVE_THREADS, 0, st>>>(a);
+        else solve_shift_kernel<<<grid, SOLVE_THREADS, 0, st>>>(a);
+        break;
     case RP_SHARED: solve_kernel<RP_SHARED><<<grid, SOLVE_THREADS, 0, st>>>(a); break;
     default: solve_kernel<RP_VARYING><<<grid, SOLVE_THREADS, 0, st>>>(a); break;
     }

@@ -394,6 +394,93 @@ __global__ void __launch_bounds__(SOLVE_THREADS, RP_SOLVE_MIN_BLOCKS) solve_kern
     if (tid == 0) a.seg_count[pair * a.nseg + seg] = running_s;
 }
 
+// RP_CALIB_SHIFT specialisation of solve_kernel, two phases per block.  Phase A (thread per iteration):
+// equations, quartic and root filter -> 0..4 candidate roots, appended IN ORDER to a shared-memory queue
+// (block-wide exclusive scan).  Phase B (thread per queued root, 256 at a time, so every lane works):
+// Newton polish + triangle alignment, model written straight to its final slot (queue position = slot).
+// Same arithmetic as solve_calib_shift, hence bit-identical models; the thread-per-iteration loop over the
+// roots ran at 12.8 of 32 active lanes (ncu).
+constexpr int SHIFT_QCAP = 4 * SOLVE_THREADS + SOLVE_THREADS;  // one round of appends on top of < 256 leftovers
+
+RP_D Triplet load_triplet(const SolveArgs &a, const PairParams &pp, int pair, int it) {
+    const int *s = a.samples + ((size_t)pair * a.iters + it) * 3;
+    Triplet t;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const long long g = pp.off + s[i];
+        const Pt64 p = a.pts64[g];
+        t.p1[i] = v3(p.x1_0, p.x1_1, 1.0);
+        t.p2[i] = v3(p.x2_0, p.x2_1, 1.0);
+        t.d1[i] = a.d1[g];
+        t.d2[i] = a.d2[g];
+    }
+    return t;
+}
+
+__global__ void __launch_bounds__(SOLVE_THREADS, RP_SOLVE_MIN_BLOCKS) solve_shift_kernel(SolveArgs a) {
+    const int seg = blockIdx.x, pair = blockIdx.y;
+    const PairParams pp = a.pairs[pair];
+    __shared__ int warp_tot[SOLVE_THREADS / 32];
+    __shared__ ShiftCand qc[SHIFT_QCAP];
+    __shared__ int qit[SHIFT_QCAP];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const size_t slot0 = ((size_t)pair * a.nseg + seg) * (size_t)(4 * SEG);
+    if (!pp.valid) {
+        if (tid == 0) a.seg_count[pair * a.nseg + seg] = 0;
+        return;
+    }
+    int head = 0, tail = 0;  // queue positions == slot indices of the segment (uniform across the block)
+    auto drain = [&](int upto) {  // finish the queued roots [head, upto)
+        for (int q = head + tid; q < upto; q += SOLVE_THREADS) {
+            const int it = qit[q % SHIFT_QCAP];
+            const ShiftCand c = qc[q % SHIFT_QCAP];
+            const Triplet t = load_triplet(a, pp, pair, it);
+            const ShiftSystem S = shift_system(t);
+            a.models[slot0 + q] = solve_calib_shift_finish(t, S, c);
+            a.hyp_iter[slot0 + q] = it;
+        }
+        head = upto;
+    };
+    for (int round = 0; round < SEG / SOLVE_THREADS; ++round) {
+        const int it = seg * SEG + round * SOLVE_THREADS + tid;
+        ShiftCand c0, c1, c2, c3;
+        int n = 0;
+        if (it < a.iters) {
+            const Triplet t = load_triplet(a, pp, pair, it);
+            const ShiftSystem S = shift_system(t);
+            n = solve_calib_shift_roots(t, S, c0, c1, c2, c3);
+        }
+        int incl = n;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        __syncthreads();  // the previous drain has read its queue entries
+        if (lane == 31) warp_tot[wid] = incl;
+        __syncthreads();
+        int wbase = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < SOLVE_THREADS / 32; ++w) {
+            const int v = warp_tot[w];
+            if (w < wid) wbase += v;
+            total += v;
+        }
+        const int pos = tail + wbase + (incl - n);
+        if (n > 0) { qc[pos % SHIFT_QCAP] = c0; qit[pos % SHIFT_QCAP] = it; }
+        if (n > 1) { qc[(pos + 1) % SHIFT_QCAP] = c1; qit[(pos + 1) % SHIFT_QCAP] = it; }
+        if (n > 2) { qc[(pos + 2) % SHIFT_QCAP] = c2; qit[(pos + 2) % SHIFT_QCAP] = it; }
+        if (n > 3) { qc[(pos + 3) % SHIFT_QCAP] = c3; qit[(pos + 3) % SHIFT_QCAP] = it; }
+        tail += total;
+        __syncthreads();
+        // full batches only; the remainder waits for the next round (or the final drain)
+        const int full = head + ((tail - head) / SOLVE_THREADS) * SOLVE_THREADS;
+        if (full > head) drain(full);
+    }
+    drain(tail);
+    if (tid == 0) a.seg_count[pair * a.nseg + seg] = tail;
+}
+
 // stage entry point helper: independent triplets, one thread each (rp_solve_batch)
 __global__ void solve_problems_kernel(int variant, long long n, const double *x1h, const double *x2h,
                                       const double *d1, const double *d2, Model *models, int *counts) {
@@ -715,6 +802,8 @@ struct alignas(16) BoundFilter {
     f32x2 g;      // thr^2 (1+1e-5)
     f32x2 kh;     // 1012 delta_a^2
     f32x2 eps;    // eps (filter disabled: +inf)
+    f32x2 ng1;    // -(1.001 g): count-only test C^2 > 1.001 g den + 1001 eps^2  (see bound_eval)
+    f32x2 nk;     // -(1001 eps^2) (filter disabled: -inf)
 };
 
 struct BoundShared {
@@ -742,6 +831,21 @@ RP_D void bound_eval(const BoundFilter &f, const f32x2 (&X1x)[PT * BSG / 2], con
         const f32x2 b1 = fma2(f.e[1], X2x[q], fma2(f.e[4], X2y[q], f.e[7]));
         const f32x2 C = fma2(X2x[q], a0, fma2(X2y[q], a1, a2));
         const f32x2 den = fma2(a0, a0, fma2(a1, a1, fma2(b0, b0, mul2(b1, b1))));
+        if (CHEAP) {
+            // count-only: |C| - eps > sqrt(g den)  <=  C^2 > (1+a) g den + (1+1/a) eps^2  with a = 1e-3
+            // ((x+y)^2 <= (1+a) x^2 + (1+1/a) y^2), evaluated as the sign of one packed FMA chain; the
+            // 1e-5 slack folded into ng1 / nk covers its two roundings.  NaN compares false: candidate.
+            const f32x2 D = fma2(C, C, fma2(f.ng1, den, f.nk));
+            float dd0, dd1;
+            unpack2(D, dd0, dd1);
+            bool cand0 = !(dd0 > 0.f), cand1 = !(dd1 > 0.f);
+            if (!FULL) {
+                cand0 = cand0 && ((vmask >> (2 * q)) & 1u);
+                cand1 = cand1 && ((vmask >> (2 * q + 1)) & 1u);
+            }
+            c += (int)cand0 + (int)cand1;
+            continue;
+        }
         float c0, c1;
         unpack2(C, c0, c1);
         const float tt0 = fmaxf(fabsf(c0) - eps, 0.0f), tt1 = fmaxf(fabsf(c1) - eps, 0.0f);
@@ -811,6 +915,9 @@ __global__ void __launch_bounds__(SCORE_THREADS, RP_BOUND_MIN_BLOCKS) bound_kern
             bf.e[3] = pack2(f.e10, f.e10); bf.e[4] = pack2(f.e11, f.e11); bf.e[5] = pack2(f.e12, f.e12);
             bf.e[6] = pack2(f.e20, f.e20); bf.e[7] = pack2(f.e21, f.e21); bf.e[8] = pack2(f.e22, f.e22);
             bf.g = pack2(f.g, f.g); bf.kh = pack2(kh, kh); bf.eps = pack2(f.eps, f.eps);
+            const float ng1 = -__double2float_ru((double)f.g * 1.001 * 1.00001);
+            const float nk = isinf(f.eps) ? -INFINITY : -__double2float_ru(1001.0 * (double)f.eps * (double)f.eps * 1.00001);
+            bf.ng1 = pack2(ng1, ng1); bf.nk = pack2(nk, nk);
             sh.hf[tid] = bf;
         }
         __syncthreads();

@@ -318,11 +318,29 @@ RP_HD ShiftEq shift_equation(V3 p1i, V3 p1j, V3 p2i, V3 p2j, double ai, double a
     return e;
 }
 
-RP_HD void solve_calib_shift(const Triplet &t, ModelSet &out) {
-    out.n = 0;
-    const ShiftEq e0 = shift_equation(t.p1[0], t.p1[1], t.p2[0], t.p2[1], t.d1[0], t.d1[1], t.d2[0], t.d2[1]);
-    const ShiftEq e1 = shift_equation(t.p1[0], t.p1[2], t.p2[0], t.p2[2], t.d1[0], t.d1[2], t.d2[0], t.d2[2]);
-    const ShiftEq e2 = shift_equation(t.p1[1], t.p1[2], t.p2[1], t.p2[2], t.d1[1], t.d1[2], t.d2[1], t.d2[2]);
+// The solver is split in two so that the RANSAC kernel can run the cheap, uniform part (equations, quartic,
+// root filter) with one thread per sample and the expensive per-root part (Newton polish + triangle
+// alignment) with one thread per surviving root (solve_shift_kernel): a sample has 0..4 roots, and a
+// thread-per-sample loop over them leaves most lanes idle.
+struct ShiftSystem {
+    ShiftEq e0, e1, e2;
+};
+struct ShiftCand {
+    double u, s, v;  // shift1, scale^2, shift2 before the polish
+};
+
+RP_HD ShiftSystem shift_system(const Triplet &t) {
+    ShiftSystem S;
+    S.e0 = shift_equation(t.p1[0], t.p1[1], t.p2[0], t.p2[1], t.d1[0], t.d1[1], t.d2[0], t.d2[1]);
+    S.e1 = shift_equation(t.p1[0], t.p1[2], t.p2[0], t.p2[2], t.d1[0], t.d1[2], t.d2[0], t.d2[2]);
+    S.e2 = shift_equation(t.p1[1], t.p1[2], t.p2[1], t.p2[2], t.d1[1], t.d1[2], t.d2[1], t.d2[2]);
+    return S;
+}
+
+// roots of the quartic in u = shift1 that pass the sign filters, in root order; returns their number
+RP_HD int solve_calib_shift_roots(const Triplet &t, const ShiftSystem &S, ShiftCand &c0, ShiftCand &c1, ShiftCand &c2,
+                                  ShiftCand &c3) {
+    const ShiftEq &e0 = S.e0, &e1 = S.e1, &e2 = S.e2;
     M3 A;
     A.r0 = v3(e0.c0, e0.c2, e0.c3);
     A.r1 = v3(e1.c0, e1.c2, e1.c3);
@@ -330,7 +348,7 @@ RP_HD void solve_calib_shift(const Triplet &t, ModelSet &out) {
     const double c00 = A.r1.y * A.r2.z - A.r1.z * A.r2.y;
     const double c01 = A.r1.z * A.r2.x - A.r1.x * A.r2.z;
     const double c02 = A.r1.x * A.r2.y - A.r1.y * A.r2.x;
-    if (A.r0.x * c00 + A.r0.y * c01 + A.r0.z * c02 == 0.0) return;
+    if (A.r0.x * c00 + A.r0.y * c01 + A.r0.z * c02 == 0.0) return 0;
     const M3 Ai = inverse(A);
     // rows of P: s v^2, s v, s as quadratics in u (coefficients of u^2, u, 1)
     const V3 q2 = v3(e0.c1, e1.c1, e2.c1), q1 = v3(e0.c4, e1.c4, e2.c4), q0 = v3(e0.c5, e1.c5, e2.c5);
@@ -344,46 +362,73 @@ RP_HD void solve_calib_shift(const Triplet &t, ModelSet &out) {
     const double k0 = a2 * a2 - b2 * g2;
     double r0 = 0, r1 = 0, r2 = 0, r3 = 0;
     const int nr = solve_quartic_real(k3 / k4, k2 / k4, k1 / k4, k0 / k4, r0, r1, r2, r3);
+    int n = 0;
 #pragma unroll
     for (int ir = 0; ir < 4; ++ir) {
         if (ir >= nr) break;
-        double u = ir == 0 ? r0 : (ir == 1 ? r1 : (ir == 2 ? r2 : r3));
-        double s = (g0 * u + g1) * u + g2;
+        const double u = ir == 0 ? r0 : (ir == 1 ? r1 : (ir == 2 ? r2 : r3));
+        const double s = (g0 * u + g1) * u + g2;
         const double sv = (a0 * u + a1) * u + a2;
-        double v = sv / s;
+        const double v = sv / s;
         if (!(s > 0)) continue;
         if (!(t.d1[0] + u > 0 && t.d1[1] + u > 0 && t.d1[2] + u > 0)) continue;
         if (!(t.d2[0] + v > 0 && t.d2[1] + v > 0 && t.d2[2] + v > 0)) continue;
-        for (int it = 0; it < 5; ++it) {
-            const double ra = e0.c0 * s * v * v + e0.c1 * u * u + e0.c2 * s * v + e0.c3 * s + e0.c4 * u + e0.c5;
-            const double rb = e1.c0 * s * v * v + e1.c1 * u * u + e1.c2 * s * v + e1.c3 * s + e1.c4 * u + e1.c5;
-            const double rc = e2.c0 * s * v * v + e2.c1 * u * u + e2.c2 * s * v + e2.c3 * s + e2.c4 * u + e2.c5;
-            if (fabs(ra) + fabs(rb) + fabs(rc) < 1e-10) break;
-            M3 J;
-            J.r0 = v3(e0.c0 * v * v + e0.c2 * v + e0.c3, 2.0 * e0.c1 * u + e0.c4, 2.0 * e0.c0 * s * v + e0.c2 * s);
-            J.r1 = v3(e1.c0 * v * v + e1.c2 * v + e1.c3, 2.0 * e1.c1 * u + e1.c4, 2.0 * e1.c0 * s * v + e1.c2 * s);
-            J.r2 = v3(e2.c0 * v * v + e2.c2 * v + e2.c3, 2.0 * e2.c1 * u + e2.c4, 2.0 * e2.c0 * s * v + e2.c2 * s);
-            const double j00 = J.r1.y * J.r2.z - J.r1.z * J.r2.y;
-            const double j01 = J.r1.z * J.r2.x - J.r1.x * J.r2.z;
-            const double j02 = J.r1.x * J.r2.y - J.r1.y * J.r2.x;
-            if (J.r0.x * j00 + J.r0.y * j01 + J.r0.z * j02 == 0.0) break;
-            const V3 dx = mul(inverse(J), v3(ra, rb, rc));
-            s -= dx.x; u -= dx.y; v -= dx.z;
-        }
-        Model m = identity_model();
-        m.scale = sqrt(s);
-        m.shift1 = u;
-        m.shift2 = v;
-        V3 X[3], Y[3];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            const double a = t.d1[i] + u, bb = t.d2[i] + v;
-            X[i] = v3(a * t.p1[i].x, a * t.p1[i].y, a * t.p1[i].z);
-            Y[i] = v3(m.scale * bb * t.p2[i].x, m.scale * bb * t.p2[i].y, m.scale * bb * t.p2[i].z);
-        }
-        align_triangles(X[0], X[1], X[2], Y[0], Y[1], Y[2], m.q, m.t);
-        set_model(out, m);
+        ShiftCand c;
+        c.u = u; c.s = s; c.v = v;
+        // static indexing keeps the candidates in registers
+        if (n == 0) c0 = c;
+        else if (n == 1) c1 = c;
+        else if (n == 2) c2 = c;
+        else c3 = c;
+        ++n;
     }
+    return n;
+}
+
+// Newton polish of (s, u, v) on the three distance equations, then the exact 3-point alignment
+RP_HD Model solve_calib_shift_finish(const Triplet &t, const ShiftSystem &S, const ShiftCand &c) {
+    const ShiftEq &e0 = S.e0, &e1 = S.e1, &e2 = S.e2;
+    double u = c.u, s = c.s, v = c.v;
+    for (int it = 0; it < 5; ++it) {
+        const double ra = e0.c0 * s * v * v + e0.c1 * u * u + e0.c2 * s * v + e0.c3 * s + e0.c4 * u + e0.c5;
+        const double rb = e1.c0 * s * v * v + e1.c1 * u * u + e1.c2 * s * v + e1.c3 * s + e1.c4 * u + e1.c5;
+        const double rc = e2.c0 * s * v * v + e2.c1 * u * u + e2.c2 * s * v + e2.c3 * s + e2.c4 * u + e2.c5;
+        if (fabs(ra) + fabs(rb) + fabs(rc) < 1e-10) break;
+        M3 J;
+        J.r0 = v3(e0.c0 * v * v + e0.c2 * v + e0.c3, 2.0 * e0.c1 * u + e0.c4, 2.0 * e0.c0 * s * v + e0.c2 * s);
+        J.r1 = v3(e1.c0 * v * v + e1.c2 * v + e1.c3, 2.0 * e1.c1 * u + e1.c4, 2.0 * e1.c0 * s * v + e1.c2 * s);
+        J.r2 = v3(e2.c0 * v * v + e2.c2 * v + e2.c3, 2.0 * e2.c1 * u + e2.c4, 2.0 * e2.c0 * s * v + e2.c2 * s);
+        const double j00 = J.r1.y * J.r2.z - J.r1.z * J.r2.y;
+        const double j01 = J.r1.z * J.r2.x - J.r1.x * J.r2.z;
+        const double j02 = J.r1.x * J.r2.y - J.r1.y * J.r2.x;
+        if (J.r0.x * j00 + J.r0.y * j01 + J.r0.z * j02 == 0.0) break;
+        const V3 dx = mul(inverse(J), v3(ra, rb, rc));
+        s -= dx.x; u -= dx.y; v -= dx.z;
+    }
+    Model m = identity_model();
+    m.scale = sqrt(s);
+    m.shift1 = u;
+    m.shift2 = v;
+    V3 X[3], Y[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const double a = t.d1[i] + u, bb = t.d2[i] + v;
+        X[i] = v3(a * t.p1[i].x, a * t.p1[i].y, a * t.p1[i].z);
+        Y[i] = v3(m.scale * bb * t.p2[i].x, m.scale * bb * t.p2[i].y, m.scale * bb * t.p2[i].z);
+    }
+    align_triangles(X[0], X[1], X[2], Y[0], Y[1], Y[2], m.q, m.t);
+    return m;
+}
+
+RP_HD void solve_calib_shift(const Triplet &t, ModelSet &out) {
+    out.n = 0;
+    const ShiftSystem S = shift_system(t);
+    ShiftCand c0, c1, c2, c3;
+    const int n = solve_calib_shift_roots(t, S, c0, c1, c2, c3);
+    if (n > 0) set_model(out, solve_calib_shift_finish(t, S, c0));
+    if (n > 1) set_model(out, solve_calib_shift_finish(t, S, c1));
+    if (n > 2) set_model(out, solve_calib_shift_finish(t, S, c2));
+    if (n > 3) set_model(out, solve_calib_shift_finish(t, S, c3));
 }
 
 // S4: linear 3x3 in (a = 1/f1^2, b = scale^2, c = scale^2/f2^2); valid iff a,b,c > 0.
