@@ -52,7 +52,7 @@ enum { B_OFFS, B_PAIRS, B_PTS64, B_PTS32, B_BEAR, B_SAMPLES, B_MODELS, B_HYPITER
 // device scalars living in B_SCALARS
 struct Scalars {
     int n_items, n_lo_items, n_one_items, n_prob, n_pairs_scalar, overflow, need_more, n_first_items;
-    int n_surv_items, pad0, pad1, pad2;
+    int n_surv_items, bound_work, pad1, pad2;
     unsigned long long point_scores, lm_iters, n_survivors, evaluated_ps;
     long long n_hyp;
 };
@@ -343,6 +343,7 @@ int run_chunk(rp_ctx *ctx, int variant, const rp_options &opt, const ChunkIO &io
         ba.ub = B[B_UB].as<int>(); ba.lb = B[B_LB].as<float>(); ba.point_scores = &sc->point_scores;
         ba.B0 = B[B_B0].as<int>(); ba.S0 = B[B_S0].as<double>();
         ba.evaluated = &sc->evaluated_ps;
+        ba.work_counter = &sc->bound_work;
         CK(cudaEventRecord(ev[20], st));
         rc = launch_bound(ctx, pose, ba, st);
         if (rc) return rc;
