@@ -811,7 +811,7 @@ struct alignas(16) BoundFilter {
 };
 
 struct BoundShared {
-    BoundFilter hf[HB];
+    BoundFilter hf[SCORE_WARPS][BHW];  // per warp: the filters of the models of its current work unit
     float sp[SCORE_WARPS][BHW][32];  // per-lane partial lower-bound sums of the warp's models
     int outc[SCORE_WARPS][BHW];      // certain outliers collected so far by each of the warp's models
 };
@@ -887,13 +887,14 @@ __global__ void __launch_bounds__(SCORE_THREADS, RP_BOUND_MIN_BLOCKS) bound_kern
     __shared__ BoundShared sh;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n_items = *a.n_items;
-    __shared__ int item_s;
-    // items differ a lot in cost (abandonment): blocks take them one at a time from a global counter
+    // Work unit = the models h = w, w+8, w+16, ... (at most BHW) of one item; units differ a lot in cost
+    // (abandonment), so every WARP takes them one at a time from a global counter and nothing in this kernel
+    // synchronises across warps: a warp with many good models never holds up the other seven.
     for (;;) {
-        __syncthreads();
-        if (tid == 0) item_s = atomicAdd(a.work_counter, 1);
-        __syncthreads();
-        const int item = item_s;
+        int unit = 0;
+        if (lane == 0) unit = atomicAdd(a.work_counter, 1);
+        unit = __shfl_sync(0xffffffffu, unit, 0);
+        const int item = unit / SCORE_WARPS, w = unit % SCORE_WARPS;
         if (item >= n_items) break;
         int lo = 0, hi = a.n_groups;
         while (hi - lo > 1) {
@@ -908,9 +909,11 @@ __global__ void __launch_bounds__(SCORE_THREADS, RP_BOUND_MIN_BLOCKS) bound_kern
         const int nh = min(HB, a.grp_cnt[e] - h0);
         const size_t slot0 = (size_t)e * a.grp_stride + h0;
         const PairParams pp = a.pairs[pair];
-        __syncthreads();
-        if (tid < nh) {
-            const Model m = a.models[slot0 + tid];
+        const int my_nh = (nh - w + SCORE_WARPS - 1) / SCORE_WARPS;  // models h = w + i*SCORE_WARPS
+        if (my_nh <= 0) continue;
+        __syncwarp();
+        if (lane < my_nh) {
+            const Model m = a.models[slot0 + w + lane * SCORE_WARPS];
             const M3 E = POSE ? essential_from_motion(m.q, m.t) : fundamental_from_model(m);
             const Filter32 f = make_filter32(E, pp.thr, pp.Mmax, pp.mmax);
             // 1012 * delta_a^2 with delta_a = 16 u Emax m (the sqrt(den) term of eps)
@@ -927,9 +930,9 @@ __global__ void __launch_bounds__(SCORE_THREADS, RP_BOUND_MIN_BLOCKS) bound_kern
             const float ng1 = -__double2float_ru((double)f.g * 1.001 * 1.00001);
             const float nk = isinf(f.eps) ? -INFINITY : -__double2float_ru(1001.0 * (double)f.eps * (double)f.eps * 1.00001);
             bf.ng1 = pack2(ng1, ng1); bf.nk = pack2(nk, nk);
-            sh.hf[tid] = bf;
+            sh.hf[wid][lane] = bf;
         }
-        __syncthreads();
+        __syncwarp();
         const int n = pp.n;
         const float thr2_lo = __double2float_rd(pp.sq_thr);
         // abandonment threshold on the number of certain outliers (see header comment)
@@ -937,7 +940,6 @@ __global__ void __launch_bounds__(SCORE_THREADS, RP_BOUND_MIN_BLOCKS) bound_kern
         const double S0 = a.S0[pair];
         double need_d = fmax((double)(n - B0), S0 < 1e300 ? ceil(S0 / ((double)thr2_lo * (1.0 - 2e-4))) : 4.0e9);
         const int need_out = need_d > 2.0e9 ? 0x7fffffff : max((int)need_d, 1);
-        const int my_nh = (nh - wid + SCORE_WARPS - 1) / SCORE_WARPS;  // models h = wid + i*SCORE_WARPS
         unsigned alive = my_nh >= 32 ? 0xffffffffu : ((1u << my_nh) - 1u);
         unsigned cheap = 0;  // models that switched to count-only evaluation (their lb is void)
         int *out_cnt = sh.outc[wid];
@@ -971,8 +973,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, RP_BOUND_MIN_BLOCKS) bound_kern
 #pragma unroll 1
             for (int i = 0; i < my_nh; ++i) {
                 if (!((alive >> i) & 1u)) continue;
-                const int h = wid + i * SCORE_WARPS;
-                const BoundFilter f = sh.hf[h];
+                const BoundFilter f = sh.hf[wid][i];
                 int c = 0;
                 float s = 0.f;
                 const bool is_cheap = (cheap >> i) & 1u;
@@ -994,7 +995,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, RP_BOUND_MIN_BLOCKS) bound_kern
         __syncwarp();
 #pragma unroll 1
         for (int i = 0; i < my_nh; ++i) {
-            const int h = wid + i * SCORE_WARPS;
+            const int h = w + i * SCORE_WARPS;
             float s = sh.sp[wid][i][lane];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -1007,8 +1008,9 @@ __global__ void __launch_bounds__(SCORE_THREADS, RP_BOUND_MIN_BLOCKS) bound_kern
                 a.lb[slot0 + h] = dead ? INFINITY : (((cheap >> i) & 1u) ? -INFINITY : __double2float_rd(lbv));
             }
         }
-        if (a.point_scores && tid == 0) atomicAdd(a.point_scores, (unsigned long long)nh * (unsigned long long)n);
+        if (a.point_scores && lane == 0) atomicAdd(a.point_scores, (unsigned long long)my_nh * (unsigned long long)n);
         if (a.evaluated && lane == 0) atomicAdd(a.evaluated, evaluated);
+        __syncwarp();  // the unit's shared-memory rows are free for the next one
     }
 }
 
