@@ -52,7 +52,7 @@ enum { B_OFFS, B_PAIRS, B_PTS64, B_PTS32, B_BEAR, B_SAMPLES, B_MODELS, B_HYPITER
 // device scalars living in B_SCALARS
 struct Scalars {
     int n_items, n_lo_items, n_one_items, n_prob, n_pairs_scalar, overflow, need_more, n_first_items;
-    int n_surv_items, bound_work, pad1, pad2;
+    int n_surv_items, bound_work, lm_work, pad2;  // *_work: counters the persistent kernels draw work from
     unsigned long long point_scores, lm_iters, n_survivors, evaluated_ps;
     long long n_hyp;
 };
@@ -138,7 +138,11 @@ int launch_lm(rp_ctx *ctx, int variant, const LMArgs &a, long long expected_prob
     // (measured on B200: one warp per problem is no faster for LO batches and 3x slower for the
     // per-pair final refinements, so it stays an opt-in experiment)
     const bool warp_per_problem = expected_problems >= (long long)ctx->sms * 8 && getenv("RP_LM_WARP") != nullptr;
-    CK((cudaError_t)launch_lm_kernel(ctx->sms, variant, warp_per_problem, a, st));
+    // problems differ in cost (1..max_iterations LM iterations): blocks draw them from a counter
+    LMArgs la = a;
+    la.work_counter = &ctx->buf[B_SCALARS].as<Scalars>()->lm_work;
+    CK(cudaMemsetAsync(la.work_counter, 0, sizeof(int), st));
+    CK((cudaError_t)launch_lm_kernel(ctx->sms, variant, warp_per_problem, la, st));
     return RP_OK;
 }
 

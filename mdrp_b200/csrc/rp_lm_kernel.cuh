@@ -31,6 +31,7 @@ struct LMArgs {
     double scale_reproj_override;
     rp_bundle_stats *stats;      // optional, per problem index
     unsigned long long *lm_iters;
+    int *work_counter;           // zeroed before the launch: blocks take problems dynamically
 };
 
 constexpr int LM_LIST_CAP = 8192;
@@ -62,7 +63,13 @@ __global__ void __launch_bounds__(THREADS, RP_LM_MIN_BLOCKS) lm_kernel(LMArgs a)
     __shared__ int wcount[LM_WARPS];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n_prob = *a.n_prob;
-    for (int pj = blockIdx.x; pj < n_prob; pj += gridDim.x) {
+    __shared__ int pj_s;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) pj_s = atomicAdd(a.work_counter, 1);
+        __syncthreads();
+        const int pj = pj_s;
+        if (pj >= n_prob) break;
         const int prob = a.prob_list ? a.prob_list[pj] : pj;
         const int pair = prob / a.prob_per_pair;
         const PairParams pp = a.pairs[pair];
