@@ -52,7 +52,7 @@ enum { B_OFFS, B_PAIRS, B_PTS64, B_PTS32, B_BEAR, B_SAMPLES, B_MODELS, B_HYPITER
 // device scalars living in B_SCALARS
 struct Scalars {
     int n_items, n_lo_items, n_one_items, n_prob, n_pairs_scalar, overflow, need_more, n_first_items;
-    int n_surv_items, bound_work, lm_work, pad2;  // *_work: counters the persistent kernels draw work from
+    int n_surv_items, bound_work, lm_work, score_work;  // *_work: counters the persistent kernels draw work from
     unsigned long long point_scores, lm_iters, n_survivors, evaluated_ps;
     long long n_hyp;
 };
@@ -112,8 +112,11 @@ int occupancy_grid(rp_ctx *ctx, K kernel, int threads) {
 }
 
 // ---- kernel launch helpers ---------------------------------------------------------------------
-int launch_score(rp_ctx *ctx, bool pose, bool mask, const ScoreArgs &a, cudaStream_t st) {
+int launch_score(rp_ctx *ctx, bool pose, bool mask, const ScoreArgs &args, cudaStream_t st) {
     int grid;
+    ScoreArgs a = args;
+    a.work_counter = &ctx->buf[B_SCALARS].as<Scalars>()->score_work;
+    CK(cudaMemsetAsync(a.work_counter, 0, sizeof(int), st));
     if (pose) {
         if (mask) { grid = occupancy_grid(ctx, score_kernel<true, true>, SCORE_THREADS); score_kernel<true, true><<<grid, SCORE_THREADS, 0, st>>>(a); }
         else { grid = occupancy_grid(ctx, score_kernel<true, false>, SCORE_THREADS); score_kernel<true, false><<<grid, SCORE_THREADS, 0, st>>>(a); }

@@ -564,6 +564,7 @@ struct ScoreArgs {
     unsigned long long *point_scores;  // optional counter
     const int *slot_list;    // optional indirection: model i of group e lives at slot
     int list_stride;         //   e*grp_stride + slot_list[e*list_stride + i]   (survivor lists)
+    int *work_counter;       // zeroed before the launch: blocks take items dynamically
 };
 
 struct HypConst {
@@ -659,10 +660,15 @@ __global__ void __launch_bounds__(SCORE_THREADS) score_kernel(ScoreArgs a) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     const int n_items = *a.n_items;
-    const int per = (n_items + gridDim.x - 1) / gridDim.x;
-    const int item_end = min(n_items, (int)(blockIdx.x + 1) * per);
     unsigned *q = sh.queue[wid];
-    for (int item = blockIdx.x * per; item < item_end; ++item) {
+    __shared__ int item_s;
+    // items differ in cost (share of candidates that reach the exact tier): blocks draw them from a counter
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) item_s = atomicAdd(a.work_counter, 1);
+        __syncthreads();
+        const int item = item_s;
+        if (item >= n_items) break;
         // group of this item: last e with item_prefix[e] <= item
         int lo = 0, hi = a.n_groups;
         while (hi - lo > 1) {
