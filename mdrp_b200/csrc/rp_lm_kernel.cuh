@@ -5,7 +5,7 @@
 #include "rp_lm.cuh"
 
 #ifndef RP_LM_MIN_BLOCKS
-#define RP_LM_MIN_BLOCKS 2
+#define RP_LM_MIN_BLOCKS 3   // blocks of 128 threads per SM, i.e. 12 warps: 168 registers per thread
 #endif
 
 namespace rp {
@@ -47,7 +47,7 @@ RP_D void warp_reduce_normal(NormalEq<NP> &N) {
 // THREADS = 128: one block per problem (few problems, e.g. a single pair); THREADS = 32: one warp per
 // problem (large batches: no block barriers, the serial Cholesky of one problem overlaps the others)
 template <int VARIANT, int NP, int THREADS>
-__global__ void __launch_bounds__(THREADS, RP_LM_MIN_BLOCKS) lm_kernel(LMArgs a) {
+__global__ void __launch_bounds__(THREADS, RP_LM_MIN_BLOCKS * 128 / THREADS) lm_kernel(LMArgs a) {
     constexpr int LM_THREADS = THREADS;
     constexpr int LM_WARPS = THREADS / 32;
     constexpr int NA = NP * (NP + 1) / 2;
