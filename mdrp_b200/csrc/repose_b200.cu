@@ -538,7 +538,19 @@ int estimate_impl(rp_ctx *ctx, int variant, int64_t n_pairs, const int64_t *offs
     chunk = std::min<int64_t>(chunk, 32768);
     std::vector<long long> rel;
     DevBuf *B = ctx->buf;
-    const int64_t n_chunks = (n_pairs + chunk - 1) / chunk;
+    // Chunk boundaries.  The remainder is split evenly (no tiny last chunk); on the host path a small first
+    // chunk goes ahead so that the kernels start after ~1/8 of a chunk's upload instead of a whole one — every
+    // later upload hides behind the previous chunk's kernels.
+    std::vector<int64_t> bounds(1, 0);
+    {
+        int64_t first = 0;
+        if (host_io && n_pairs >= 1024 && !getenv("RP_NO_LEAD_CHUNK")) first = std::min<int64_t>(n_pairs, std::max<int64_t>(256, chunk / 8));
+        if (first > 0) bounds.push_back(first);
+        const int64_t rest = n_pairs - first;
+        const int64_t k = (rest + chunk - 1) / chunk;
+        for (int64_t i = 1; i <= k; ++i) bounds.push_back(first + (rest * i) / k);
+    }
+    const int64_t n_chunks = (int64_t)bounds.size() - 1;
     // Host path: double-buffered staging.  The copy stream uploads chunk c+1 and downloads chunk c-1
     // while the compute stream runs the kernels of chunk c (pinned host memory makes this truly async).
     static const int IN_X1[2] = {B_IN_X1, B_IN_X1_B}, IN_X2[2] = {B_IN_X2, B_IN_X2_B}, IN_D1[2] = {B_IN_D1, B_IN_D1_B},
@@ -548,7 +560,7 @@ int estimate_impl(rp_ctx *ctx, int variant, int64_t n_pairs, const int64_t *offs
     cudaEvent_t *in_ready = &ctx->ev[12], *h2d_begin = &ctx->ev[14], *comp_done = &ctx->ev[16], *d2h_begin = &ctx->ev[18];
     cudaEvent_t d2h_end = ctx->ev[11];
     auto upload = [&](int64_t c) -> int {
-        const int64_t p0 = c * chunk, p1 = std::min(n_pairs, p0 + chunk);
+        const int64_t p0 = bounds[c], p1 = bounds[c + 1];
         const int P = (int)(p1 - p0), par = (int)(c & 1);
         const long long o0 = offsets[p0], N = offsets[p1] - o0;
         const size_t nn = (size_t)std::max<long long>(N, 1);
@@ -571,7 +583,7 @@ int estimate_impl(rp_ctx *ctx, int variant, int64_t n_pairs, const int64_t *offs
         if (rc) return rc;
     }
     for (int64_t c = 0; c < n_chunks; ++c) {
-        const int64_t p0 = c * chunk, p1 = std::min(n_pairs, p0 + chunk);
+        const int64_t p0 = bounds[c], p1 = bounds[c + 1];
         const int P = (int)(p1 - p0), par = (int)(c & 1);
         const long long o0 = offsets[p0], N = offsets[p1] - o0;
         rel.resize(P + 1);
