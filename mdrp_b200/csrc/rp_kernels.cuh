@@ -512,33 +512,53 @@ __global__ void solve_problems_kernel(int variant, long long n, const double *x1
 // ceil(cnt/HB) over the groups; single block.
 __global__ void build_items_kernel(int n_groups, const int *grp_cnt, int *item_prefix, int *n_items,
                                    long long *n_hyp_total) {
-    __shared__ int sh[1024];
-    __shared__ int carry;
-    __shared__ long long hyps;
-    if (threadIdx.x == 0) { carry = 0; hyps = 0; }
-    __syncthreads();
+    // tiles of 1024 groups: shuffle scan inside each warp, the 32 warp totals scanned by warp 0
+    __shared__ int wtot[32];
+    __shared__ long long whyp[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int carry = 0;          // items before this tile (uniform)
+    long long hyps = 0;     // per-thread partial of the model count
     for (int base = 0; base < n_groups; base += 1024) {
         const int e = base + threadIdx.x;
         const int c = e < n_groups ? grp_cnt[e] : 0;
         const int v = (c + HB - 1) / HB;
-        sh[threadIdx.x] = v;
-        __syncthreads();
-        for (int o = 1; o < 1024; o <<= 1) {
-            const int t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
-            __syncthreads();
-            sh[threadIdx.x] += t;
-            __syncthreads();
+        hyps += c;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
         }
-        if (e < n_groups) item_prefix[e] = carry + sh[threadIdx.x] - v;
-        if (c) atomicAdd((unsigned long long *)&hyps, (unsigned long long)c);
+        __syncthreads();  // wtot of the previous tile has been read
+        if (lane == 31) wtot[wid] = incl;
         __syncthreads();
-        if (threadIdx.x == 0) carry += sh[1023];
+        if (wid == 0) {
+            const int w = wtot[lane];
+            int wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += t;
+            }
+            wtot[lane] = wi - w;  // exclusive
+            if (lane == 31) whyp[0] = wi;  // tile total (reuses the 64-bit scratch)
+        }
         __syncthreads();
+        if (e < n_groups) item_prefix[e] = carry + wtot[wid] + incl - v;
+        carry += (int)whyp[0];
     }
+    // model count: warp sums, then thread 0
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) hyps += __shfl_xor_sync(0xffffffffu, hyps, o);
+    __syncthreads();
+    if (lane == 0) whyp[wid] = hyps;
+    __syncthreads();
     if (threadIdx.x == 0) {
+        long long tot = 0;
+        for (int w = 0; w < 32; ++w) tot += whyp[w];
         item_prefix[n_groups] = carry;
         *n_items = carry;
-        if (n_hyp_total) *n_hyp_total = hyps;
+        if (n_hyp_total) *n_hyp_total = tot;
     }
 }
 

@@ -85,7 +85,7 @@ def main():
         subprocess.run(["cp", os.path.join(GO, f"{tag}_launches.csv"), os.path.join(PR, f"{tag}_launches.csv")])
         parts.append(txt)
     traffic = {}
-    for name in ("bound", "lm", "score_survivors"):
+    for name in ("bound", "lm", "score_survivors", "solve"):
         rep = os.path.join(GO, f"{tag}_{name}.ncu-rep")
         if os.path.exists(rep):
             txt, d = ncu_raw(rep)
