@@ -44,7 +44,7 @@ struct DevBuf {
 enum { B_OFFS, B_PAIRS, B_PTS64, B_PTS32, B_BEAR, B_SAMPLES, B_MODELS, B_HYPITER, B_SCORE, B_COUNT, B_SEGCNT,
        B_ITEMPFX, B_SCALARS, B_EVENTS, B_NEVENTS, B_LOMODELS, B_LOOFEV, B_LOCOUNT, B_PROBLIST, B_LOSCORE,
        B_LOCNT, B_LOITEMPFX, B_BEST, B_FINSTART, B_FINSCORE, B_FINCNT, B_ONES, B_ONEPFX, B_ENABLE, B_STATS,
-       B_PTS32P, B_UB, B_LB, B_FIRSTCNT, B_FIRSTPFX, B_B0, B_S0, B_SURVLIST, B_SURVCNT, B_SURVPFX,
+       B_PTS32P, B_UB, B_LB, B_FIRSTCNT, B_FIRSTPFX, B_B0, B_S0, B_SURVLIST, B_SURVCNT, B_SURVPFX, B_WAVECUR, B_WAVECNT,
        B_MASK, B_IN_X1, B_IN_X2, B_IN_D1, B_IN_D2, B_IN_CAMS, B_TMP0, B_TMP1, B_TMP2,
        // second staging set (double buffering of the host path)
        B_MASK_B, B_IN_X1_B, B_IN_X2_B, B_IN_D1_B, B_IN_D2_B, B_IN_CAMS_B, B_TMP0_B, B_TMP1_B, B_NBUF };
@@ -74,6 +74,7 @@ struct rp_ctx {
     int64_t last_cnt[8] = {0};  // [5] models through the exact kernel, [6] point-scores the bound kernel evaluated
     size_t workspace_budget = (size_t)32 << 30;  // HBM is 180 GB: big chunks amortise kernel tails
     bool prune = true;  // hypothesis-level pruning (RP_NO_PRUNE=1 scores every minimal model exactly)
+    bool waves = true;  // survivors of the prune scored in waves (RP_NO_WAVES=1: all at once)
     int occ_score[4] = {0}, occ_lm[4] = {0};
 };
 
@@ -261,6 +262,7 @@ int run_chunk(rp_ctx *ctx, int variant, const rp_options &opt, const ChunkIO &io
         CK(B[B_B0].reserve(sizeof(int) * P));
         CK(B[B_S0].reserve(sizeof(double) * P));
         CK(B[B_SURVCNT].reserve(sizeof(int) * P));
+        CK(B[B_WAVECUR].reserve(sizeof(int) * P)); CK(B[B_WAVECNT].reserve(sizeof(int) * P));
         CK(B[B_SURVPFX].reserve(sizeof(int) * (P + 1)));
     }
 
@@ -359,16 +361,40 @@ int run_chunk(rp_ctx *ctx, int variant, const rp_options &opt, const ChunkIO &io
         PruneArgs pa;
         pa.n_pairs = P; pa.nseg = nseg; pa.seg_count = seg_count; pa.ub = ba.ub; pa.lb = ba.lb;
         pa.B0 = B[B_B0].as<int>(); pa.S0 = B[B_S0].as<double>(); pa.score = score; pa.count = count;
-        pa.surv_list = B[B_SURVLIST].as<int>(); pa.surv_cnt = B[B_SURVCNT].as<int>(); pa.n_survivors = &sc->n_survivors;
+        pa.surv_list = B[B_SURVLIST].as<int>(); pa.surv_cnt = B[B_SURVCNT].as<int>();
+        pa.n_survivors = ctx->waves ? nullptr : &sc->n_survivors;
         prune_kernel<<<cdiv((long long)P * 32, 256), 256, 0, st>>>(pa);
         LAUNCHED();
-        build_items_kernel<<<1, 1024, 0, st>>>(P, pa.surv_cnt, B[B_SURVPFX].as<int>(), &sc->n_surv_items, nullptr);
-        LAUNCHED();
         ScoreArgs sv = sa;
-        sv.grp_cnt = pa.surv_cnt; sv.item_prefix = B[B_SURVPFX].as<int>(); sv.n_items = &sc->n_surv_items;
+        sv.item_prefix = B[B_SURVPFX].as<int>(); sv.n_items = &sc->n_surv_items;
         sv.slot_list = pa.surv_list; sv.list_stride = (int)slots_pp; sv.point_scores = nullptr;
-        rc = launch_score(ctx, pose, false, sv, st);
-        if (rc) return rc;
+        if (!ctx->waves) {
+            // all survivors at once (RP_NO_WAVES=1: the check that the waves below change nothing)
+            build_items_kernel<<<1, 1024, 0, st>>>(P, pa.surv_cnt, B[B_SURVPFX].as<int>(), &sc->n_surv_items, nullptr);
+            LAUNCHED();
+            sv.grp_cnt = pa.surv_cnt;
+            rc = launch_score(ctx, pose, false, sv, st);
+            if (rc) return rc;
+        } else {
+            // survivors in waves of growing size, each raising the bar for the next (wave_select_kernel)
+            WaveArgs wa;
+            wa.n_pairs = P; wa.slots_pp = slots_pp; wa.surv_list = pa.surv_list; wa.surv_cnt = pa.surv_cnt;
+            wa.cursor = B[B_WAVECUR].as<int>(); wa.wave_cnt = B[B_WAVECNT].as<int>(); wa.ub = ba.ub; wa.lb = ba.lb;
+            wa.B = B[B_B0].as<int>(); wa.S = B[B_S0].as<double>(); wa.score = score; wa.count = count;
+            wa.n_exact = &sc->n_survivors;
+            CK(cudaMemsetAsync(wa.cursor, 0, sizeof(int) * P, st));
+            static const int WAVES[] = {8, 16, 32, 64, 0x7fffffff};
+            for (int k = 0; k < 5; ++k) {
+                wa.wave_size = WAVES[k]; wa.first = k == 0;
+                wave_select_kernel<<<cdiv((long long)P * 32, 256), 256, 0, st>>>(wa);
+                LAUNCHED();
+                build_items_kernel<<<1, 1024, 0, st>>>(P, wa.wave_cnt, B[B_SURVPFX].as<int>(), &sc->n_surv_items, nullptr);
+                LAUNCHED();
+                sv.grp_cnt = wa.wave_cnt;
+                rc = launch_score(ctx, pose, false, sv, st);
+                if (rc) return rc;
+            }
+        }
     }
     CK(cudaEventRecord(ev[4], st));
     // 5. scan + LO problem list
@@ -677,6 +703,7 @@ int rp_create(int device, rp_ctx **out) {
     }
     for (auto &ev : ctx->ev) cudaEventCreate(&ev);
     if (const char *np = getenv("RP_NO_PRUNE")) ctx->prune = !(np[0] == '1');
+    if (const char *nw = getenv("RP_NO_WAVES")) ctx->waves = !(nw[0] == '1');
     if (const char *gb = getenv("RP_WORKSPACE_GB")) {
         const double v = atof(gb);
         if (v > 0.01) ctx->workspace_budget = (size_t)(v * (double)((size_t)1 << 30));

@@ -1114,6 +1114,83 @@ __global__ void prune_kernel(PruneArgs a) {
     }
 }
 
+// Survivors are scored exactly in WAVES.  The prune above compares against (B0, S0) of the first HB models
+// only, so every later model that beats the head's best survives (~200 per pair on the benchmark) although only
+// the ~10 prefix records among them matter.  The survivor list is in sequence order: score its first few
+// entries exactly, raise (B, S) to what they achieved, re-test the following entries' (ub, lb) against the new
+// bar, and so on with growing wave sizes.  A survivor dropped by the re-test has ub <= B and lb >= S for exact
+// values B, S of EARLIER models, hence can neither trigger nor move the running best: the result is unchanged
+// while ~10x fewer models reach the exact kernel.  One warp per pair; the wave is compacted in place at the
+// front of the pair's survivor list (entries before the cursor are already consumed).
+struct WaveArgs {
+    int n_pairs;
+    size_t slots_pp;
+    int wave_size;        // models to select per pair in this wave
+    int first;            // first wave: nothing to fold into (B, S) yet
+    int *surv_list;       // [n_pairs * slots_pp] pair-relative slots (in: survivors from cursor on; out: the wave at the front)
+    const int *surv_cnt;  // [n_pairs] survivors of the prune
+    int *cursor;          // [n_pairs] next unconsumed survivor
+    int *wave_cnt;        // [n_pairs] in: size of the previous wave, out: size of this one
+    const int *ub;
+    const float *lb;
+    int *B;               // [n_pairs] running exact bests (start: B0, S0)
+    double *S;
+    double *score;
+    int *count;
+    unsigned long long *n_exact;  // optional counter of models sent to the exact kernel
+};
+
+__global__ void wave_select_kernel(WaveArgs a) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= a.n_pairs) return;
+    const size_t pslot = (size_t)warp * a.slots_pp;
+    int B = a.B[warp];
+    double S = a.S[warp];
+    if (!a.first) {
+        // fold the previous wave's exact results into the bar
+        const int prev = a.wave_cnt[warp];
+        for (int i = lane; i < prev; i += 32) {
+            const size_t slot = pslot + a.surv_list[pslot + i];
+            B = max(B, a.count[slot]);
+            const double v = a.score[slot];
+            if (v == v) S = fmin(S, v);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            B = max(B, __shfl_xor_sync(0xffffffffu, B, o));
+            S = fmin(S, __shfl_xor_sync(0xffffffffu, S, o));
+        }
+    }
+    const int ns = a.surv_cnt[warp];
+    int pos = a.cursor[warp], nw = 0;
+    while (pos < ns && nw < a.wave_size) {
+        const int i = pos + lane;
+        const bool valid = i < ns;
+        const int rel = valid ? a.surv_list[pslot + i] : 0;
+        const bool keep = valid && (a.ub[pslot + rel] > B || (double)a.lb[pslot + rel] < S);
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        const int rank = __popc(m & ((1u << lane) - 1u));
+        const bool take = keep && nw + rank < a.wave_size;
+        // the cursor stops in front of the first kept entry that does not fit into this wave
+        const unsigned untaken = __ballot_sync(0xffffffffu, keep && !take);
+        const int stop = untaken ? __ffs(untaken) - 1 : 32;
+        if (valid && !keep && lane < stop) { a.count[pslot + rel] = 0; a.score[pslot + rel] = DBL_MAX; }
+        __syncwarp();
+        if (take) a.surv_list[pslot + nw + rank] = rel;   // nw + rank <= pos + lane: never ahead of the reads
+        nw += __popc(m & (stop >= 32 ? 0xffffffffu : ((1u << stop) - 1u)));
+        pos += stop;
+        if (stop < 32) break;
+    }
+    if (lane == 0) {
+        a.B[warp] = B;
+        a.S[warp] = S;
+        a.cursor[warp] = pos;
+        a.wave_cnt[warp] = nw;
+        if (a.n_exact && nw) atomicAdd(a.n_exact, (unsigned long long)nw);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // scan: the part of score_models() so@0x22ebc0 that does not depend on LO results.  A minimal
 // model "triggers" when it has more inliers than every earlier minimal model or a lower MSAC

@@ -282,10 +282,23 @@ def test_pruning_does_not_change_results(cfg, monkeypatch):
     scs, variant, offs, x1, x2, d1, d2, cams = _batch(cfg, range(400, 424), n=700)
     o = _options(2500, shift=c["shift"])
     monkeypatch.delenv("RP_NO_PRUNE", raising=False)
+    monkeypatch.delenv("RP_NO_WAVES", raising=False)
     pruned_ctx = nv.Context(0)
     a = pruned_ctx.estimate_batch_host(variant, offs, x1, x2, d1, d2, cams, o)
     _, cnt = pruned_ctx.last_timing()
     assert cnt["exact_models"] < 0.5 * cnt["hypotheses"]  # pruning is actually on
+    # survivors scored all at once instead of in bar-raising waves: same results, more exact work
+    monkeypatch.setenv("RP_NO_WAVES", "1")
+    flat_ctx = nv.Context(0)
+    w = flat_ctx.estimate_batch_host(variant, offs, x1, x2, d1, d2, cams, o)
+    _, cntw = flat_ctx.last_timing()
+    monkeypatch.delenv("RP_NO_WAVES")
+    assert cnt["exact_models"] <= cntw["exact_models"] < 0.5 * cntw["hypotheses"]
+    assert a[0].tobytes() == w[0].tobytes() and a[2].tobytes() == w[2].tobytes()
+    for f in ("refinements", "iterations", "num_inliers", "inlier_ratio"):
+        assert np.array_equal(a[1][f], w[1][f]), f
+    assert np.allclose(a[1]["model_score"], w[1]["model_score"], rtol=1e-12, atol=0)
+    flat_ctx.close()
     monkeypatch.setenv("RP_NO_PRUNE", "1")
     full_ctx = nv.Context(0)
     b = full_ctx.estimate_batch_host(variant, offs, x1, x2, d1, d2, cams, o)
