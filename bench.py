@@ -174,7 +174,7 @@ def reference_arm(args, c, rank, world):
             "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def _ncu_traffic(kernel, pairs_per_launch):
@@ -193,8 +193,31 @@ def _ncu_traffic(kernel, pairs_per_launch):
 
 
 # ---- the GPU arm ------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """stdout carries exactly ONE JSON line.  Libraries write banners to fd 1 (NCCL prints its version there at
+    the first communicator): park the real stdout and point fd 1 at stderr until the line is emitted."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
     args = parse_args()
+    _claim_stdout()
     from mdrp_b200 import synth
     c = synth.CONFIGS[args.config]
     rank = int(os.environ.get("RANK", "0"))
@@ -369,7 +392,7 @@ def main():
         pps, cores, kind, dt = cpu_pairs_per_s(args.config, n_sample)
         line["cpu_baseline"] = {"value": pps, "unit": "pairs/s", "cores": cores, "kind": kind,
                                 "sample": f"{n_sample} pairs of the workload, per-pair calls from a {cores}-thread pool, {dt:.1f} s"}
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
