@@ -142,6 +142,27 @@ def test_batch_vs_oracle(ctx, port, cfg):
             assert models_close(models[i], m, rtol=1e-6, atol=1e-8), (cfg, i)
 
 
+@pytest.mark.parametrize("cfg", ["cfg1_calib_scale", "cfg3_shared_focal"])
+def test_large_pair_vs_oracle(ctx, port, cfg):
+    """A pair with more correspondences than the LM kernel's shared-memory inlier list holds (8192): the final
+    refinement takes its mask-on-the-fly path and must still agree with the oracle."""
+    c = synth.CONFIGS[cfg]
+    scs, variant, offs, x1, x2, d1, d2, cams = _batch(cfg, [77, 78], n=9000)
+    iters = 200
+    models, stats, masks = ctx.estimate_batch_host(variant, offs, x1, x2, d1, d2, cams, _options(iters, c["shift"]))
+    ro = port.ransac_opt(max_iterations=iters, min_iterations=iters, max_epipolar_error=2.0, max_reproj_error=16.0,
+                         seed=0, estimate_shift=c["shift"])
+    bo = port.bundle_opt(loss_type="TRUNCATED_CAUCHY", loss_scale=1.0)
+    for i, s in enumerate(scs):
+        sl = slice(offs[i], offs[i + 1])
+        cam = ([s.f1, s.f1, 640, 480], [s.f2, s.f2, 640, 480]) if variant < 2 else (None, None)
+        m, st, mask = port.estimate(variant, x1[sl], x2[sl], d1[sl], d2[sl], cam[0], cam[1], ro, bo)
+        assert (stats[i]["refinements"], stats[i]["iterations"], stats[i]["num_inliers"]) == \
+            (st.refinements, st.iterations, st.num_inliers), i
+        assert np.array_equal(masks[sl].astype(bool), mask), i
+        assert models_close(models[i], m, rtol=1e-6, atol=1e-8), i
+
+
 def test_edge_cases_match_reference_behaviour(ctx):
     """SURVEY §8b 'Errors': N<3 -> identity, iterations 0, model_score DBL_MAX, all-False mask; empty
     batch; a pair with zero correspondences inside a batch."""
