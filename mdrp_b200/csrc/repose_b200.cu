@@ -138,15 +138,12 @@ int launch_bound(rp_ctx *ctx, bool pose, const BoundArgs &a, cudaStream_t st) {
 
 int launch_lm(rp_ctx *ctx, int variant, const LMArgs &a, long long expected_problems, cudaStream_t st) {
     ctx->launches++;
-    // enough independent problems to fill the machine with one warp each?
-    // (measured on B200: one warp per problem is no faster for LO batches and 3x slower for the
-    // per-pair final refinements, so it stays an opt-in experiment)
-    const bool warp_per_problem = expected_problems >= (long long)ctx->sms * 8 && getenv("RP_LM_WARP") != nullptr;
+    (void)expected_problems;
     // problems differ in cost (1..max_iterations LM iterations): blocks draw them from a counter
     LMArgs la = a;
     la.work_counter = &ctx->buf[B_SCALARS].as<Scalars>()->lm_work;
     CK(cudaMemsetAsync(la.work_counter, 0, sizeof(int), st));
-    CK((cudaError_t)launch_lm_kernel(ctx->sms, variant, warp_per_problem, la, st));
+    CK((cudaError_t)launch_lm_kernel(ctx->sms, variant, la, st));
     return RP_OK;
 }
 

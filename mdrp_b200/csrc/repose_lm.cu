@@ -17,20 +17,22 @@ static int occupancy_grid(int sms, K kernel, int threads) {
 }
 
 template <int VARIANT, int NP>
-static void launch_variant(int sms, bool warp_per_problem, const LMArgs &a, cudaStream_t st) {
-    if (warp_per_problem)
-        lm_kernel<VARIANT, NP, 32><<<occupancy_grid(sms, lm_kernel<VARIANT, NP, 32>, 32), 32, 0, st>>>(a);
+static void launch_variant(int sms, const LMArgs &a, cudaStream_t st) {
+    // the LO refinement (use_final = 0) always uses the TRUNCATED loss: compile-time specialisation
+    if (!a.use_final)
+        lm_kernel<VARIANT, NP, RP_LM_THREADS, RP_LOSS_TRUNCATED>
+            <<<occupancy_grid(sms, lm_kernel<VARIANT, NP, RP_LM_THREADS, RP_LOSS_TRUNCATED>, RP_LM_THREADS), RP_LM_THREADS, 0, st>>>(a);
     else
-        lm_kernel<VARIANT, NP, RP_LM_THREADS><<<occupancy_grid(sms, lm_kernel<VARIANT, NP, RP_LM_THREADS>, RP_LM_THREADS),
-                                                  RP_LM_THREADS, 0, st>>>(a);
+        lm_kernel<VARIANT, NP, RP_LM_THREADS, -1>
+            <<<occupancy_grid(sms, lm_kernel<VARIANT, NP, RP_LM_THREADS, -1>, RP_LM_THREADS), RP_LM_THREADS, 0, st>>>(a);
 }
 
-int launch_lm_kernel(int sms, int variant, bool warp_per_problem, const LMArgs &a, cudaStream_t st) {
+int launch_lm_kernel(int sms, int variant, const LMArgs &a, cudaStream_t st) {
     switch (variant) {
-    case RP_CALIB: launch_variant<RP_CALIB, 7>(sms, warp_per_problem, a, st); break;
-    case RP_CALIB_SHIFT: launch_variant<RP_CALIB_SHIFT, 9>(sms, warp_per_problem, a, st); break;
-    case RP_SHARED: launch_variant<RP_SHARED, 8>(sms, warp_per_problem, a, st); break;
-    default: launch_variant<RP_VARYING, 9>(sms, warp_per_problem, a, st); break;
+    case RP_CALIB: launch_variant<RP_CALIB, 7>(sms, a, st); break;
+    case RP_CALIB_SHIFT: launch_variant<RP_CALIB_SHIFT, 9>(sms, a, st); break;
+    case RP_SHARED: launch_variant<RP_SHARED, 8>(sms, a, st); break;
+    default: launch_variant<RP_VARYING, 9>(sms, a, st); break;
     }
     return (int)cudaGetLastError();
 }

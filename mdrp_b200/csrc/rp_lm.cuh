@@ -97,10 +97,13 @@ RP_HD double comp(V3 v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : v.z); }
 RP_HD V3 row(const M3 &M, int i) { return i == 0 ? M.r0 : (i == 1 ? M.r1 : M.r2); }
 
 // cost contribution of one correspondence
-template <int VARIANT>
+// LOSS >= 0 fixes the robust loss at compile time (the LO refinement always uses TRUNCATED: the per-residual
+// switch disappears); LOSS < 0 reads it from P.
+template <int VARIANT, int LOSS = -1>
 RP_HD double point_cost(const LMFrame &F, const LMParams &P, double x1_0, double x1_1, double x2_0, double x2_1,
                         double d1, double d2) {
     constexpr bool FOCAL_ = (VARIANT == RP_SHARED || VARIANT == RP_VARYING);
+    const int loss_type = LOSS >= 0 ? LOSS : P.loss_type;
     const V3 p1 = FOCAL_ ? v3(x1_0 * F.if1, x1_1 * F.if1, 1.0) : v3(x1_0, x1_1, 1.0);
     const V3 p2 = FOCAL_ ? v3(x2_0 * F.if2, x2_1 * F.if2, 1.0) : v3(x2_0, x2_1, 1.0);
     double cost = 0.0;
@@ -110,7 +113,7 @@ RP_HD double point_cost(const LMFrame &F, const LMParams &P, double x1_0, double
         const double A = Ep1.x * Ep1.x + Ep1.y * Ep1.y, B = Etp2.x * Etp2.x + Etp2.y * Etp2.y;
         const double inv = 1.0 / sqrt(A * F.if2sq + B * F.if1sq);
         const double rs = C * inv;
-        cost += P.weight_sampson * loss_eval(P.loss_type, P.loss_scale, rs * rs);
+        cost += P.weight_sampson * loss_eval(loss_type, P.loss_scale, rs * rs);
     }
     if (P.scale_reproj > 0.0) {
         const double a = d1 + F.shift1;
@@ -119,14 +122,14 @@ RP_HD double point_cost(const LMFrame &F, const LMParams &P, double x1_0, double
         if (Z.z > 0.0) {
             const double iz = 1.0 / Z.z;
             const double r0 = F.f2 * (Z.x * iz) - x2_0, r1 = F.f2 * (Z.y * iz) - x2_1;
-            cost += loss_eval(P.loss_type, P.loss_scale, P.scale_reproj * (r0 * r0 + r1 * r1));
+            cost += loss_eval(loss_type, P.loss_scale, P.scale_reproj * (r0 * r0 + r1 * r1));
         }
         const double b = F.scale * (d2 + F.shift2);
         const V3 Y = mulT(F.R, v3(b * p2.x - F.t.x, b * p2.y - F.t.y, b * p2.z - F.t.z));
         if (Y.z > 0.0) {
             const double iz = 1.0 / Y.z;
             const double r0 = F.f1 * (Y.x * iz) - x1_0, r1 = F.f1 * (Y.y * iz) - x1_1;
-            cost += loss_eval(P.loss_type, P.loss_scale, P.scale_reproj * (r0 * r0 + r1 * r1));
+            cost += loss_eval(loss_type, P.loss_scale, P.scale_reproj * (r0 * r0 + r1 * r1));
         }
     }
     return cost;
@@ -141,10 +144,11 @@ RP_HD double point_cost(const LMFrame &F, const LMParams &P, double x1_0, double
 // point_eval returns the cost contribution of the same correspondence as well (the value point_cost
 // computes), so one pass over the data serves both the accept test of the trial step and — when it is
 // accepted, the usual case — the normal equations of the next iteration.
-template <int VARIANT, int NP>
+template <int VARIANT, int NP, int LOSS = -1>
 RP_HD double point_eval(const LMFrame &F, const LMParams &P, double x1_0, double x1_1, double x2_0,
                         double x2_1, double d1, double d2, NormalEq<NP> &N) {
     constexpr bool FOCAL = (VARIANT == RP_SHARED || VARIANT == RP_VARYING);
+    const int loss_type = LOSS >= 0 ? LOSS : P.loss_type;
     constexpr int CF2 = (VARIANT == RP_SHARED) ? 7 : 8;  // column of f2 (== f column when shared)
     constexpr unsigned M_POSE = 0x3Fu;                    // w (0-2), t (3-5)
     constexpr unsigned M_FOC = VARIANT == RP_SHARED ? 0x80u : (VARIANT == RP_VARYING ? 0x180u : 0u);
@@ -168,8 +172,8 @@ RP_HD double point_eval(const LMFrame &F, const LMParams &P, double x1_0, double
         const double A = Ep1.x * Ep1.x + Ep1.y * Ep1.y, B = Etp2.x * Etp2.x + Etp2.y * Etp2.y;
         const double inv = 1.0 / sqrt(A * F.if2sq + B * F.if1sq);
         const double rs = C * inv;
-        cost += P.weight_sampson * loss_eval(P.loss_type, P.loss_scale, rs * rs);
-        const double w = P.weight_sampson * loss_weight(P.loss_type, P.loss_scale, rs * rs);
+        cost += P.weight_sampson * loss_eval(loss_type, P.loss_scale, rs * rs);
+        const double w = P.weight_sampson * loss_weight(loss_type, P.loss_scale, rs * rs);
         if (w != 0.0) {
 #pragma unroll
             for (int i = 0; i < NP; ++i) J[i] = 0.0;
@@ -239,9 +243,9 @@ RP_HD double point_eval(const LMFrame &F, const LMParams &P, double x1_0, double
             const double iz = 1.0 / Z.z;
             const double u0 = Z.x * iz, u1 = Z.y * iz;
             const double r0 = F.f2 * u0 - x2_0, r1 = F.f2 * u1 - x2_1;
-            cost += loss_eval(P.loss_type, P.loss_scale, P.scale_reproj * (r0 * r0 + r1 * r1));
+            cost += loss_eval(loss_type, P.loss_scale, P.scale_reproj * (r0 * r0 + r1 * r1));
             const double w = P.scale_reproj *
-                             loss_weight(P.loss_type, P.loss_scale, P.scale_reproj * (r0 * r0 + r1 * r1));
+                             loss_weight(loss_type, P.loss_scale, P.scale_reproj * (r0 * r0 + r1 * r1));
             if (w != 0.0) {
                 const double g = F.f2 * iz;
                 double J0[NP], J1[NP];
@@ -292,9 +296,9 @@ RP_HD double point_eval(const LMFrame &F, const LMParams &P, double x1_0, double
             const double iz = 1.0 / Y.z;
             const double u0 = Y.x * iz, u1 = Y.y * iz;
             const double r0 = F.f1 * u0 - x1_0, r1 = F.f1 * u1 - x1_1;
-            cost += loss_eval(P.loss_type, P.loss_scale, P.scale_reproj * (r0 * r0 + r1 * r1));
+            cost += loss_eval(loss_type, P.loss_scale, P.scale_reproj * (r0 * r0 + r1 * r1));
             const double w = P.scale_reproj *
-                             loss_weight(P.loss_type, P.loss_scale, P.scale_reproj * (r0 * r0 + r1 * r1));
+                             loss_weight(loss_type, P.loss_scale, P.scale_reproj * (r0 * r0 + r1 * r1));
             if (w != 0.0) {
                 const double g = F.f1 * iz;
                 double J0[NP], J1[NP];

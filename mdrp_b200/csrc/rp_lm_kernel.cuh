@@ -44,14 +44,17 @@ RP_D void warp_reduce_normal(NormalEq<NP> &N) {
     for (int i = 0; i < NP; ++i) N.g[i] = warp_sum(N.g[i]);
 }
 
-// THREADS = 128: one block per problem (few problems, e.g. a single pair); THREADS = 32: one warp per
-// problem (large batches: no block barriers, the serial Cholesky of one problem overlaps the others)
-template <int VARIANT, int NP, int THREADS>
+// One block of THREADS threads per problem.  (One warp per problem was measured 1.8-6x slower on B200: twelve
+// problems per SM no longer fit their correspondences in L1.)
+// LOSS: RP_LOSS_TRUNCATED for the LO refinement (use_final = 0, loss fixed at compile time), -1 for the final
+// refinement with the user's bundle options (loss read at run time).
+template <int VARIANT, int NP, int THREADS, int LOSS>
 __global__ void __launch_bounds__(THREADS, RP_LM_MIN_BLOCKS * 128 / THREADS) lm_kernel(LMArgs a) {
     constexpr int LM_THREADS = THREADS;
     constexpr int LM_WARPS = THREADS / 32;
     constexpr int NA = NP * (NP + 1) / 2;
     __shared__ Model cur, trial;
+
     __shared__ double red[LM_WARPS][NA + NP];
     __shared__ double sA[NA], sg[NP];
     __shared__ double cred[LM_WARPS];
@@ -127,7 +130,7 @@ __global__ void __launch_bounds__(THREADS, RP_LM_MIN_BLOCKS * 128 / THREADS) lm_
                 const int k = use_list ? (int)list_s[i] : i;
                 if (!use_list && mask && !mask[k]) continue;
                 const Pt64 p = pts[k];
-                c += point_cost<VARIANT>(F, P, p.x1_0, p.x1_1, p.x2_0, p.x2_1, d1[k], d2[k]);
+                c += point_cost<VARIANT, LOSS>(F, P, p.x1_0, p.x1_1, p.x2_0, p.x2_1, d1[k], d2[k]);
             }
             c = warp_sum(c);
             __syncthreads();
@@ -149,7 +152,7 @@ __global__ void __launch_bounds__(THREADS, RP_LM_MIN_BLOCKS * 128 / THREADS) lm_
                 const int k = use_list ? (int)list_s[i] : i;
                 if (!use_list && mask && !mask[k]) continue;
                 const Pt64 p = pts[k];
-                c += point_eval<VARIANT, NP>(F, P, p.x1_0, p.x1_1, p.x2_0, p.x2_1, d1[k], d2[k], N);
+                c += point_eval<VARIANT, NP, LOSS>(F, P, p.x1_0, p.x1_1, p.x2_0, p.x2_1, d1[k], d2[k], N);
             }
             c = warp_sum(c);
             __syncthreads();
@@ -246,6 +249,6 @@ __global__ void __launch_bounds__(THREADS, RP_LM_MIN_BLOCKS * 128 / THREADS) lm_
 }
 
 // defined in repose_lm.cu; returns the cudaError_t of the launch
-int launch_lm_kernel(int sms, int variant, bool warp_per_problem, const LMArgs &a, cudaStream_t st);
+int launch_lm_kernel(int sms, int variant, const LMArgs &a, cudaStream_t st);
 
 }  // namespace rp
