@@ -39,6 +39,29 @@ RP_HD double loss_weight(int type, double thr, double r2) {
     }
 }
 
+// 1/x and 1/sqrt(x) for the point loop of the LM kernel.  The IEEE division / sqrt+division sequences cost
+// ~15 / ~35 instructions with a slow-path branch each; on the device these use the hardware approximations
+// refined by Newton steps (<= 1-2 ulp, this path is not bit-pinned).  Arguments are positive and normal here
+// (projective depths behind `z > 0`, Sampson denominators); anything else falls back to the exact sequence.
+RP_HD double lm_rcp(double x) {
+#ifdef __CUDA_ARCH__
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    y = ::fma(::fma(-x, y, 1.0), y, y);
+    y = ::fma(::fma(-x, y, 1.0), y, y);
+    return (y == y && fabs(y) < 1e300 && x > 1e-300) ? y : 1.0 / x;
+#else
+    return 1.0 / x;
+#endif
+}
+RP_HD double lm_rsqrt(double x) {
+#ifdef __CUDA_ARCH__
+    return (x > 1e-300 && x < 1e300) ? rsqrt(x) : 1.0 / sqrt(x);
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
+
 struct LMParams {
     double scale_reproj, weight_sampson, loss_scale;
     int loss_type;
@@ -111,7 +134,7 @@ RP_HD double point_cost(const LMFrame &F, const LMParams &P, double x1_0, double
         const V3 Ep1 = mul(F.E, p1), Etp2 = mulT(F.E, p2);
         const double C = dot(p2, Ep1);
         const double A = Ep1.x * Ep1.x + Ep1.y * Ep1.y, B = Etp2.x * Etp2.x + Etp2.y * Etp2.y;
-        const double inv = 1.0 / sqrt(A * F.if2sq + B * F.if1sq);
+        const double inv = lm_rsqrt(A * F.if2sq + B * F.if1sq);
         const double rs = C * inv;
         cost += P.weight_sampson * loss_eval(loss_type, P.loss_scale, rs * rs);
     }
@@ -120,14 +143,14 @@ RP_HD double point_cost(const LMFrame &F, const LMParams &P, double x1_0, double
         V3 Z = mul(F.R, v3(a * p1.x, a * p1.y, a * p1.z));
         Z = Z + F.t;
         if (Z.z > 0.0) {
-            const double iz = 1.0 / Z.z;
+            const double iz = lm_rcp(Z.z);
             const double r0 = F.f2 * (Z.x * iz) - x2_0, r1 = F.f2 * (Z.y * iz) - x2_1;
             cost += loss_eval(loss_type, P.loss_scale, P.scale_reproj * (r0 * r0 + r1 * r1));
         }
         const double b = F.scale * (d2 + F.shift2);
         const V3 Y = mulT(F.R, v3(b * p2.x - F.t.x, b * p2.y - F.t.y, b * p2.z - F.t.z));
         if (Y.z > 0.0) {
-            const double iz = 1.0 / Y.z;
+            const double iz = lm_rcp(Y.z);
             const double r0 = F.f1 * (Y.x * iz) - x1_0, r1 = F.f1 * (Y.y * iz) - x1_1;
             cost += loss_eval(loss_type, P.loss_scale, P.scale_reproj * (r0 * r0 + r1 * r1));
         }
@@ -170,7 +193,7 @@ RP_HD double point_eval(const LMFrame &F, const LMParams &P, double x1_0, double
                            E.r0.z * qx + E.r1.z * qy + E.r2.z);
         const double C = qx * Ep1.x + qy * Ep1.y + Ep1.z;
         const double A = Ep1.x * Ep1.x + Ep1.y * Ep1.y, B = Etp2.x * Etp2.x + Etp2.y * Etp2.y;
-        const double inv = 1.0 / sqrt(A * F.if2sq + B * F.if1sq);
+        const double inv = lm_rsqrt(A * F.if2sq + B * F.if1sq);
         const double rs = C * inv;
         cost += P.weight_sampson * loss_eval(loss_type, P.loss_scale, rs * rs);
         const double w = P.weight_sampson * loss_weight(loss_type, P.loss_scale, rs * rs);
@@ -240,7 +263,7 @@ RP_HD double point_eval(const LMFrame &F, const LMParams &P, double x1_0, double
         const V3 Z = v3(R.r0.x * Px + R.r0.y * Py + R.r0.z * Pz + F.t.x, R.r1.x * Px + R.r1.y * Py + R.r1.z * Pz + F.t.y,
                         R.r2.x * Px + R.r2.y * Py + R.r2.z * Pz + F.t.z);
         if (Z.z > 0.0) {
-            const double iz = 1.0 / Z.z;
+            const double iz = lm_rcp(Z.z);
             const double u0 = Z.x * iz, u1 = Z.y * iz;
             const double r0 = F.f2 * u0 - x2_0, r1 = F.f2 * u1 - x2_1;
             cost += loss_eval(loss_type, P.loss_scale, P.scale_reproj * (r0 * r0 + r1 * r1));
@@ -293,7 +316,7 @@ RP_HD double point_eval(const LMFrame &F, const LMParams &P, double x1_0, double
         const V3 Y = v3(R.r0.x * Qx + R.r1.x * Qy + R.r2.x * Qz, R.r0.y * Qx + R.r1.y * Qy + R.r2.y * Qz,
                         R.r0.z * Qx + R.r1.z * Qy + R.r2.z * Qz);
         if (Y.z > 0.0) {
-            const double iz = 1.0 / Y.z;
+            const double iz = lm_rcp(Y.z);
             const double u0 = Y.x * iz, u1 = Y.y * iz;
             const double r0 = F.f1 * u0 - x1_0, r1 = F.f1 * u1 - x1_1;
             cost += loss_eval(loss_type, P.loss_scale, P.scale_reproj * (r0 * r0 + r1 * r1));

@@ -36,13 +36,40 @@ struct LMArgs {
 
 constexpr int LM_LIST_CAP = 8192;
 
-template <int NP>
-RP_D void warp_reduce_normal(NormalEq<NP> &N) {
+// Warp reduction of NV per-lane values as a reduce-scatter: at the step with lane mask O every lane keeps one
+// half of its values and sends the other half to its partner, so the number of live values halves each step
+// (NV/2 + NV/4 + ... ~ NV shuffles instead of 5 NV for NV butterfly sums).  Afterwards the warp total of
+// value `base + j`, j < lim, sits in v[j] of exactly one lane (odd counts leave a zero pad slot in the upper
+// half: `lim` keeps it from being mistaken for the neighbouring range's first value).
+template <int MAXV, int CNT, int O>
+struct ReduceScatter {
+    static RP_D void run(double (&v)[MAXV], int lane, int &base, int &lim) {
+        constexpr int H = (CNT + 1) / 2;
+        const bool up = (lane & O) != 0;
 #pragma unroll
-    for (int i = 0; i < NP * (NP + 1) / 2; ++i) N.A[i] = warp_sum(N.A[i]);
-#pragma unroll
-    for (int i = 0; i < NP; ++i) N.g[i] = warp_sum(N.g[i]);
-}
+        for (int i = 0; i < H; ++i) {
+            const double lo = v[i];
+            const double hi = (i + H < CNT) ? v[i + H] : 0.0;
+            const double send = up ? lo : hi, keep = up ? hi : lo;
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, O);
+        }
+        if (up) { base += H; lim = max(lim - H, 0); }
+        else lim = min(lim, H);
+        ReduceScatter<MAXV, H, O / 2>::run(v, lane, base, lim);
+    }
+};
+template <int MAXV, int CNT>
+struct ReduceScatter<MAXV, CNT, 0> {
+    static RP_D void run(double (&)[MAXV], int, int &, int &) {}
+};
+template <int CNT, int STEPS>
+struct ReduceScatterLeft {
+    static constexpr int value = ReduceScatterLeft<(CNT + 1) / 2, STEPS - 1>::value;
+};
+template <int CNT>
+struct ReduceScatterLeft<CNT, 0> {
+    static constexpr int value = CNT;
+};
 
 // One block of THREADS threads per problem.  (One warp per problem was measured 1.8-6x slower on B200: twelve
 // problems per SM no longer fit their correspondences in L1.)
@@ -165,14 +192,18 @@ __global__ void __launch_bounds__(THREADS, RP_LM_MIN_BLOCKS * 128 / THREADS) lm_
         };
         // per-thread partials -> sA / sg (fixed order: deterministic)
         auto reduce_normal = [&](NormalEq<NP> &N) {
-            warp_reduce_normal<NP>(N);
+            constexpr int NV = NA + NP, LEFT = ReduceScatterLeft<NV, 5>::value;
+            double v[NV];
+#pragma unroll
+            for (int i = 0; i < NA; ++i) v[i] = N.A[i];
+#pragma unroll
+            for (int i = 0; i < NP; ++i) v[NA + i] = N.g[i];
+            int base = 0, lim = NV;
+            ReduceScatter<NV, NV, 16>::run(v, lane, base, lim);
             __syncthreads();
-            if (lane == 0) {
 #pragma unroll
-                for (int i = 0; i < NA; ++i) red[wid][i] = N.A[i];
-#pragma unroll
-                for (int i = 0; i < NP; ++i) red[wid][NA + i] = N.g[i];
-            }
+            for (int j = 0; j < LEFT; ++j)
+                if (j < lim) red[wid][base + j] = v[j];
             __syncthreads();
             if (tid < NA + NP) {
                 double v = 0.0;
