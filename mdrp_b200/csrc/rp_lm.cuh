@@ -127,6 +127,9 @@ RP_HD double point_cost(const LMFrame &F, const LMParams &P, double x1_0, double
                         double d1, double d2) {
     constexpr bool FOCAL_ = (VARIANT == RP_SHARED || VARIANT == RP_VARYING);
     const int loss_type = LOSS >= 0 ? LOSS : P.loss_type;
+    // calibrated variants carry f1 = f2 = 1: literal ones let the compiler drop the multiplications
+    const double f1 = FOCAL_ ? F.f1 : 1.0, f2 = FOCAL_ ? F.f2 : 1.0;
+    const double if1sq = FOCAL_ ? F.if1sq : 1.0, if2sq = FOCAL_ ? F.if2sq : 1.0;
     const V3 p1 = FOCAL_ ? v3(x1_0 * F.if1, x1_1 * F.if1, 1.0) : v3(x1_0, x1_1, 1.0);
     const V3 p2 = FOCAL_ ? v3(x2_0 * F.if2, x2_1 * F.if2, 1.0) : v3(x2_0, x2_1, 1.0);
     double cost = 0.0;
@@ -134,7 +137,7 @@ RP_HD double point_cost(const LMFrame &F, const LMParams &P, double x1_0, double
         const V3 Ep1 = mul(F.E, p1), Etp2 = mulT(F.E, p2);
         const double C = dot(p2, Ep1);
         const double A = Ep1.x * Ep1.x + Ep1.y * Ep1.y, B = Etp2.x * Etp2.x + Etp2.y * Etp2.y;
-        const double inv = lm_rsqrt(A * F.if2sq + B * F.if1sq);
+        const double inv = lm_rsqrt(A * if2sq + B * if1sq);
         const double rs = C * inv;
         cost += P.weight_sampson * loss_eval(loss_type, P.loss_scale, rs * rs);
     }
@@ -144,14 +147,14 @@ RP_HD double point_cost(const LMFrame &F, const LMParams &P, double x1_0, double
         Z = Z + F.t;
         if (Z.z > 0.0) {
             const double iz = lm_rcp(Z.z);
-            const double r0 = F.f2 * (Z.x * iz) - x2_0, r1 = F.f2 * (Z.y * iz) - x2_1;
+            const double r0 = f2 * (Z.x * iz) - x2_0, r1 = f2 * (Z.y * iz) - x2_1;
             cost += loss_eval(loss_type, P.loss_scale, P.scale_reproj * (r0 * r0 + r1 * r1));
         }
         const double b = F.scale * (d2 + F.shift2);
         const V3 Y = mulT(F.R, v3(b * p2.x - F.t.x, b * p2.y - F.t.y, b * p2.z - F.t.z));
         if (Y.z > 0.0) {
             const double iz = lm_rcp(Y.z);
-            const double r0 = F.f1 * (Y.x * iz) - x1_0, r1 = F.f1 * (Y.y * iz) - x1_1;
+            const double r0 = f1 * (Y.x * iz) - x1_0, r1 = f1 * (Y.y * iz) - x1_1;
             cost += loss_eval(loss_type, P.loss_scale, P.scale_reproj * (r0 * r0 + r1 * r1));
         }
     }
@@ -172,6 +175,10 @@ RP_HD double point_eval(const LMFrame &F, const LMParams &P, double x1_0, double
                         double x2_1, double d1, double d2, NormalEq<NP> &N) {
     constexpr bool FOCAL = (VARIANT == RP_SHARED || VARIANT == RP_VARYING);
     const int loss_type = LOSS >= 0 ? LOSS : P.loss_type;
+    // calibrated variants carry f1 = f2 = 1: literal ones let the compiler drop the multiplications (and the
+    // six registers that would hold them)
+    const double f1 = FOCAL ? F.f1 : 1.0, f2 = FOCAL ? F.f2 : 1.0;
+    const double if1sq = FOCAL ? F.if1sq : 1.0, if2sq = FOCAL ? F.if2sq : 1.0;
     constexpr int CF2 = (VARIANT == RP_SHARED) ? 7 : 8;  // column of f2 (== f column when shared)
     constexpr unsigned M_POSE = 0x3Fu;                    // w (0-2), t (3-5)
     constexpr unsigned M_FOC = VARIANT == RP_SHARED ? 0x80u : (VARIANT == RP_VARYING ? 0x180u : 0u);
@@ -193,7 +200,7 @@ RP_HD double point_eval(const LMFrame &F, const LMParams &P, double x1_0, double
                            E.r0.z * qx + E.r1.z * qy + E.r2.z);
         const double C = qx * Ep1.x + qy * Ep1.y + Ep1.z;
         const double A = Ep1.x * Ep1.x + Ep1.y * Ep1.y, B = Etp2.x * Etp2.x + Etp2.y * Etp2.y;
-        const double inv = lm_rsqrt(A * F.if2sq + B * F.if1sq);
+        const double inv = lm_rsqrt(A * if2sq + B * if1sq);
         const double rs = C * inv;
         cost += P.weight_sampson * loss_eval(loss_type, P.loss_scale, rs * rs);
         const double w = P.weight_sampson * loss_weight(loss_type, P.loss_scale, rs * rs);
@@ -201,7 +208,7 @@ RP_HD double point_eval(const LMFrame &F, const LMParams &P, double x1_0, double
 #pragma unroll
             for (int i = 0; i < NP; ++i) J[i] = 0.0;
             const double k = C * inv * inv * inv;  // = 2 * (0.5 C inv^3): the factor 2 of d(den) folded in
-            const double a2 = F.if2sq, a1 = F.if1sq;
+            const double a2 = if2sq, a1 = if1sq;
             // rotation: dE = E [e_i]x ;  d(Ep1) = E (e_i x p1),  d(E^T p2) = -(e_i x E^T p2)
             {
                 const double dx = py * E.r0.z - E.r0.y, dy = py * E.r1.z - E.r1.y;
@@ -265,12 +272,12 @@ RP_HD double point_eval(const LMFrame &F, const LMParams &P, double x1_0, double
         if (Z.z > 0.0) {
             const double iz = lm_rcp(Z.z);
             const double u0 = Z.x * iz, u1 = Z.y * iz;
-            const double r0 = F.f2 * u0 - x2_0, r1 = F.f2 * u1 - x2_1;
+            const double r0 = f2 * u0 - x2_0, r1 = f2 * u1 - x2_1;
             cost += loss_eval(loss_type, P.loss_scale, P.scale_reproj * (r0 * r0 + r1 * r1));
             const double w = P.scale_reproj *
                              loss_weight(loss_type, P.loss_scale, P.scale_reproj * (r0 * r0 + r1 * r1));
             if (w != 0.0) {
-                const double g = F.f2 * iz;
+                const double g = f2 * iz;
                 double J0[NP], J1[NP];
 #pragma unroll
                 for (int i = 0; i < NP; ++i) { J0[i] = 0.0; J1[i] = 0.0; }
@@ -318,12 +325,12 @@ RP_HD double point_eval(const LMFrame &F, const LMParams &P, double x1_0, double
         if (Y.z > 0.0) {
             const double iz = lm_rcp(Y.z);
             const double u0 = Y.x * iz, u1 = Y.y * iz;
-            const double r0 = F.f1 * u0 - x1_0, r1 = F.f1 * u1 - x1_1;
+            const double r0 = f1 * u0 - x1_0, r1 = f1 * u1 - x1_1;
             cost += loss_eval(loss_type, P.loss_scale, P.scale_reproj * (r0 * r0 + r1 * r1));
             const double w = P.scale_reproj *
                              loss_weight(loss_type, P.loss_scale, P.scale_reproj * (r0 * r0 + r1 * r1));
             if (w != 0.0) {
-                const double g = F.f1 * iz;
+                const double g = f1 * iz;
                 double J0[NP], J1[NP];
 #pragma unroll
                 for (int i = 0; i < NP; ++i) { J0[i] = 0.0; J1[i] = 0.0; }
