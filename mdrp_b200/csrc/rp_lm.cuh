@@ -45,18 +45,20 @@ RP_HD double loss_weight(int type, double thr, double r2) {
 // (projective depths behind `z > 0`, Sampson denominators); anything else falls back to the exact sequence.
 RP_HD double lm_rcp(double x) {
 #ifdef __CUDA_ARCH__
+    if (!(x > 1e-300 && x < 1e300)) return 1.0 / x;  // (never taken on sane data: a real branch, not a select)
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     y = ::fma(::fma(-x, y, 1.0), y, y);
     y = ::fma(::fma(-x, y, 1.0), y, y);
-    return (y == y && fabs(y) < 1e300 && x > 1e-300) ? y : 1.0 / x;
+    return y;
 #else
     return 1.0 / x;
 #endif
 }
 RP_HD double lm_rsqrt(double x) {
 #ifdef __CUDA_ARCH__
-    return (x > 1e-300 && x < 1e300) ? rsqrt(x) : 1.0 / sqrt(x);
+    if (!(x > 1e-300 && x < 1e300)) return 1.0 / sqrt(x);
+    return rsqrt(x);
 #else
     return 1.0 / sqrt(x);
 #endif
