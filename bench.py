@@ -354,7 +354,8 @@ def main():
     ps = counters["point_scores"]
     hyps = counters["hypotheses"]
     n_chunk_launches = max(1, int(counters["chunks"]))
-    ps_bound = ps - min(ps, P * args.steps * 128 * c["n"])  # the first 128 models per pair go to the exact kernel
+    head = int(counters.get("head_models", 0)) or 128
+    ps_bound = ps - min(ps, P * args.steps * head * c["n"])  # the first `head` models per pair go to the exact kernel
     achieved_tf = FLOPS_PER_POINT_SCORE * ps_bound / bound_s / 1e12 if bound_s > 0 else None
     evaluated = counters["bound_evaluated"]
     executed_tf = 41.0 * evaluated / bound_s / 1e12 if bound_s > 0 else None

@@ -136,7 +136,7 @@ def _ptr(a):
 TIMING_KEYS = ["prepare", "sample", "solve", "score_minimal", "scan", "lo_refine", "lo_score_merge",
                "final_refine", "device_total", "h2d", "d2h", "bound_kernel", "r12", "r13", "r14", "r15"]
 COUNTER_KEYS = ["hypotheses", "point_scores", "lm_problems", "lm_iterations", "chunks", "exact_models",
-                "bound_evaluated", "r7"]
+                "bound_evaluated", "head_models"]
 
 
 class Context:

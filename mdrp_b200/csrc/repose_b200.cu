@@ -74,6 +74,7 @@ struct rp_ctx {
     int64_t last_cnt[8] = {0};  // [5] models through the exact kernel, [6] point-scores the bound kernel evaluated
     size_t workspace_budget = (size_t)32 << 30;  // HBM is 180 GB: big chunks amortise kernel tails
     bool prune = true;  // hypothesis-level pruning (RP_NO_PRUNE=1 scores every minimal model exactly)
+    int head = HB;      // models per pair scored exactly before the bound kernel (RP_HEAD=32|64|96|128; measured: 128 best on cfg2/cfg4, 64 marginally better on the 1000-iteration configs)
     bool waves = true;  // survivors of the prune scored in waves (RP_NO_WAVES=1: all at once)
     int occ_score[4] = {0}, occ_lm[4] = {0};
 };
@@ -328,9 +329,9 @@ int run_chunk(rp_ctx *ctx, int variant, const rp_options &opt, const ChunkIO &io
         int rc = launch_score(ctx, pose, false, sa, st);
         if (rc) return rc;
     } else {
-        // 4a. the first HB models of every pair, exactly -> (B0, S0)
+        // 4a. the first ctx->head models of every pair, exactly -> (B0, S0)
         int *first_cnt = B[B_FIRSTCNT].as<int>();
-        first_count_kernel<<<cdiv(P, 256), 256, 0, st>>>(P, nseg, seg_count, first_cnt);
+        first_count_kernel<<<cdiv(P, 256), 256, 0, st>>>(P, nseg, seg_count, first_cnt, ctx->head);
         LAUNCHED();
         build_items_kernel<<<1, 1024, 0, st>>>(P, first_cnt, B[B_FIRSTPFX].as<int>(), &sc->n_first_items, nullptr);
         LAUNCHED();
@@ -349,7 +350,7 @@ int run_chunk(rp_ctx *ctx, int variant, const rp_options &opt, const ChunkIO &io
         ba.ub = B[B_UB].as<int>(); ba.lb = B[B_LB].as<float>(); ba.point_scores = &sc->point_scores;
         ba.B0 = B[B_B0].as<int>(); ba.S0 = B[B_S0].as<double>();
         ba.evaluated = &sc->evaluated_ps;
-        ba.work_counter = &sc->bound_work;
+        ba.work_counter = &sc->bound_work; ba.head = ctx->head;
         CK(cudaEventRecord(ev[20], st));
         rc = launch_bound(ctx, pose, ba, st);
         if (rc) return rc;
@@ -357,7 +358,7 @@ int run_chunk(rp_ctx *ctx, int variant, const rp_options &opt, const ChunkIO &io
         // 4c. prune, then score the survivors exactly
         PruneArgs pa;
         pa.n_pairs = P; pa.nseg = nseg; pa.seg_count = seg_count; pa.ub = ba.ub; pa.lb = ba.lb;
-        pa.B0 = B[B_B0].as<int>(); pa.S0 = B[B_S0].as<double>(); pa.score = score; pa.count = count;
+        pa.B0 = B[B_B0].as<int>(); pa.S0 = B[B_S0].as<double>(); pa.score = score; pa.count = count; pa.head = ctx->head;
         pa.surv_list = B[B_SURVLIST].as<int>(); pa.surv_cnt = B[B_SURVCNT].as<int>();
         pa.n_survivors = ctx->waves ? nullptr : &sc->n_survivors;
         prune_kernel<<<cdiv((long long)P * 32, 256), 256, 0, st>>>(pa);
@@ -514,7 +515,8 @@ int run_chunk(rp_ctx *ctx, int variant, const rp_options &opt, const ChunkIO &io
         CK(cudaEventElapsedTime(&msb, ev[20], ev[21]));
         ctx->last_ms[11] += msb;
     }
-    ctx->last_cnt[5] += ctx->prune ? (int64_t)h_sc.n_survivors + std::min<int64_t>(h_sc.n_hyp, (int64_t)P * HB) : h_sc.n_hyp;
+    ctx->last_cnt[5] += ctx->prune ? (int64_t)h_sc.n_survivors + std::min<int64_t>(h_sc.n_hyp, (int64_t)P * ctx->head) : h_sc.n_hyp;
+    ctx->last_cnt[7] = ctx->head;
     if (h_sc.overflow) return fail(ctx, RP_ERR_OVERFLOW, "trigger event list overflowed (EV)");
     *need_more = h_sc.need_more != 0;
     return RP_OK;
@@ -701,6 +703,7 @@ int rp_create(int device, rp_ctx **out) {
     for (auto &ev : ctx->ev) cudaEventCreate(&ev);
     if (const char *np = getenv("RP_NO_PRUNE")) ctx->prune = !(np[0] == '1');
     if (const char *nw = getenv("RP_NO_WAVES")) ctx->waves = !(nw[0] == '1');
+    if (const char *hd = getenv("RP_HEAD")) { const int v = atoi(hd); if (v == 32 || v == 64 || v == 96 || v == 128) ctx->head = v; }
     if (const char *gb = getenv("RP_WORKSPACE_GB")) {
         const double v = atof(gb);
         if (v > 0.01) ctx->workspace_budget = (size_t)(v * (double)((size_t)1 << 30));

@@ -804,6 +804,7 @@ struct BoundArgs {
     unsigned long long *point_scores;
     unsigned long long *evaluated;  // optional: (model, correspondence) pairs actually evaluated
     int *work_counter;              // zeroed before the launch: blocks take work items dynamically
+    int head;                       // the first `head` models of a pair were scored exactly (multiple of SCORE_WARPS)
 };
 
 #ifndef RP_SOLVE_MIN_BLOCKS
@@ -929,14 +930,15 @@ __global__ void __launch_bounds__(SCORE_THREADS, RP_BOUND_MIN_BLOCKS) bound_kern
         }
         const int e = lo;
         const int chunk = item - a.item_prefix[e];
-        if (e % a.grp_per_pair == 0 && chunk == 0) continue;  // the first HB models of a pair are scored exactly
         const int pair = e / a.grp_per_pair;
         const int h0 = chunk * HB;
         const int nh = min(HB, a.grp_cnt[e] - h0);
         const size_t slot0 = (size_t)e * a.grp_stride + h0;
         const PairParams pp = a.pairs[pair];
         const int my_nh = (nh - w + SCORE_WARPS - 1) / SCORE_WARPS;  // models h = w + i*SCORE_WARPS
-        if (my_nh <= 0) continue;
+        // the first `head` models of a pair are scored exactly: in its first item the warp skips i < i0
+        const int i0 = (e % a.grp_per_pair == 0 && chunk == 0) ? a.head / SCORE_WARPS : 0;
+        if (my_nh <= i0) continue;
         __syncwarp();
         if (lane < my_nh) {
             const Model m = a.models[slot0 + w + lane * SCORE_WARPS];
@@ -966,7 +968,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, RP_BOUND_MIN_BLOCKS) bound_kern
         const double S0 = a.S0[pair];
         double need_d = fmax((double)(n - B0), S0 < 1e300 ? ceil(S0 / ((double)thr2_lo * (1.0 - 2e-4))) : 4.0e9);
         const int need_out = need_d > 2.0e9 ? 0x7fffffff : max((int)need_d, 1);
-        unsigned alive = my_nh >= 32 ? 0xffffffffu : ((1u << my_nh) - 1u);
+        unsigned alive = (my_nh >= 32 ? 0xffffffffu : ((1u << my_nh) - 1u)) & ~((1u << i0) - 1u);
         unsigned cheap = 0;  // models that switched to count-only evaluation (their lb is void)
         int *out_cnt = sh.outc[wid];
 #pragma unroll
@@ -1020,7 +1022,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, RP_BOUND_MIN_BLOCKS) bound_kern
         // results: abandoned models can never survive the prune (ub = 0, lb = +inf)
         __syncwarp();
 #pragma unroll 1
-        for (int i = 0; i < my_nh; ++i) {
+        for (int i = i0; i < my_nh; ++i) {
             const int h = w + i * SCORE_WARPS;
             float s = sh.sp[wid][i][lane];
 #pragma unroll
@@ -1034,7 +1036,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, RP_BOUND_MIN_BLOCKS) bound_kern
                 a.lb[slot0 + h] = dead ? INFINITY : (((cheap >> i) & 1u) ? -INFINITY : __double2float_rd(lbv));
             }
         }
-        if (a.point_scores && lane == 0) atomicAdd(a.point_scores, (unsigned long long)my_nh * (unsigned long long)n);
+        if (a.point_scores && lane == 0) atomicAdd(a.point_scores, (unsigned long long)(my_nh - i0) * (unsigned long long)n);
         if (a.evaluated && lane == 0) atomicAdd(a.evaluated, evaluated);
         __syncwarp();  // the unit's shared-memory rows are free for the next one
     }
@@ -1063,9 +1065,9 @@ __global__ void pair_bounds_kernel(int n_pairs, int nseg, const int *first_cnt, 
     if (lane == 0) { B0[warp] = b; S0[warp] = s; }
 }
 
-__global__ void first_count_kernel(int n_pairs, int nseg, const int *seg_count, int *first_cnt) {
+__global__ void first_count_kernel(int n_pairs, int nseg, const int *seg_count, int *first_cnt, int head) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_pairs) first_cnt[i] = min(seg_count[i * nseg], HB);
+    if (i < n_pairs) first_cnt[i] = min(seg_count[i * nseg], head);
 }
 
 // prune: survivors (ub > B0 or lb < S0) are compacted, in order, into a per-pair slot list; everything
@@ -1082,6 +1084,7 @@ struct PruneArgs {
     int *surv_list;   // [n_pairs * nseg*4*SEG] pair-relative slots
     int *surv_cnt;    // [n_pairs]
     unsigned long long *n_survivors;
+    int head;   // models of segment 0 that were scored exactly (multiple of 32)
 };
 
 __global__ void prune_kernel(PruneArgs a) {
@@ -1096,7 +1099,7 @@ __global__ void prune_kernel(PruneArgs a) {
     for (int seg = 0; seg < a.nseg; ++seg) {
         const int cnt = a.seg_count[warp * a.nseg + seg];
         const int rel0 = seg * (4 * SEG);
-        for (int base = (seg == 0 ? HB : 0); base < cnt; base += 32) {
+        for (int base = (seg == 0 ? a.head : 0); base < cnt; base += 32) {
             const int h = base + lane;
             bool keep = false;
             if (h < cnt) {
