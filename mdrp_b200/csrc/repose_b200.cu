@@ -150,13 +150,22 @@ int launch_lm(rp_ctx *ctx, int variant, const LMArgs &a, long long expected_prob
 
 int launch_solve(rp_ctx *ctx, int variant, const SolveArgs &a, int n_pairs, cudaStream_t st) {
     dim3 grid(a.nseg, n_pairs);
+    // RP_SOLVE_GENERIC=1: the thread-per-iteration kernel for every variant (the two-phase kernels must give
+    // bit-identical models)
+    const bool generic = getenv("RP_SOLVE_GENERIC") != nullptr;
     switch (variant) {
-    case RP_CALIB: solve_kernel<RP_CALIB><<<grid, SOLVE_THREADS, 0, st>>>(a); break;
-    case RP_CALIB_SHIFT:
-        if (getenv("RP_SOLVE_GENERIC")) solve_kernel<RP_CALIB_SHIFT><<<grid, SOLVE_THREADS, 0, st>>>(a);
-        else solve_shift_kernel<<<grid, SOLVE_THREADS, 0, st>>>(a);
+    case RP_CALIB:
+        if (generic) solve_kernel<RP_CALIB><<<grid, SOLVE_THREADS, 0, st>>>(a);
+        else solve2_kernel<P3PCand><<<grid, SOLVE_THREADS, 0, st>>>(a);
         break;
-    case RP_SHARED: solve_kernel<RP_SHARED><<<grid, SOLVE_THREADS, 0, st>>>(a); break;
+    case RP_CALIB_SHIFT:
+        if (generic) solve_kernel<RP_CALIB_SHIFT><<<grid, SOLVE_THREADS, 0, st>>>(a);
+        else solve2_kernel<ShiftCand><<<grid, SOLVE_THREADS, 0, st>>>(a);
+        break;
+    case RP_SHARED:
+        if (generic) solve_kernel<RP_SHARED><<<grid, SOLVE_THREADS, 0, st>>>(a);
+        else solve2_kernel<FocalCand><<<grid, SOLVE_THREADS, 0, st>>>(a);
+        break;
     default: solve_kernel<RP_VARYING><<<grid, SOLVE_THREADS, 0, st>>>(a); break;
     }
     LAUNCHED();

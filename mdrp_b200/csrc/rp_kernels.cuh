@@ -394,12 +394,13 @@ __global__ void __launch_bounds__(SOLVE_THREADS, RP_SOLVE_MIN_BLOCKS) solve_kern
     if (tid == 0) a.seg_count[pair * a.nseg + seg] = running_s;
 }
 
-// RP_CALIB_SHIFT specialisation of solve_kernel, two phases per block.  Phase A (thread per iteration):
-// equations, quartic and root filter -> 0..4 candidate roots, appended IN ORDER to a shared-memory queue
-// (block-wide exclusive scan).  Phase B (thread per queued root, 256 at a time, so every lane works):
-// Newton polish + triangle alignment, model written straight to its final slot (queue position = slot).
-// Same arithmetic as solve_calib_shift, hence bit-identical models; the thread-per-iteration loop over the
-// roots ran at 12.8 of 32 active lanes (ncu).
+// Two-phase form of solve_kernel for the solvers with 0..4 solutions per sample (P3P + scale, scale+shift,
+// shared focal).  Phase A (thread per iteration): the uniform part up to the filtered candidate roots
+// (solve_roots), appended IN ORDER to a shared-memory queue (block-wide exclusive scan).  Phase B (thread per
+// queued root, 256 at a time, so every lane works): the per-solution part (solve_finish: polish + pose
+// assembly), model written straight to its final slot (queue position = slot).  Same arithmetic as the
+// one-call solvers, hence bit-identical models; the thread-per-iteration loop over the roots ran at 12.8 of
+// 32 active lanes (ncu, scale+shift).  CAND = P3PCand | ShiftCand | FocalCand selects the solver.
 constexpr int SHIFT_QCAP = 4 * SOLVE_THREADS + SOLVE_THREADS;  // one round of appends on top of < 256 leftovers
 
 RP_D Triplet load_triplet(const SolveArgs &a, const PairParams &pp, int pair, int it) {
@@ -420,11 +421,12 @@ RP_D Triplet load_triplet(const SolveArgs &a, const PairParams &pp, int pair, in
 #ifndef RP_SOLVE_SHIFT_MIN_BLOCKS
 #define RP_SOLVE_SHIFT_MIN_BLOCKS 2   // 128 registers: measured 17.8 ms vs 23.1 ms per 10k pairs at 1 block/SM
 #endif
-__global__ void __launch_bounds__(SOLVE_THREADS, RP_SOLVE_SHIFT_MIN_BLOCKS) solve_shift_kernel(SolveArgs a) {
+template <class CAND>
+__global__ void __launch_bounds__(SOLVE_THREADS, RP_SOLVE_SHIFT_MIN_BLOCKS) solve2_kernel(SolveArgs a) {
     const int seg = blockIdx.x, pair = blockIdx.y;
     const PairParams pp = a.pairs[pair];
     __shared__ int warp_tot[SOLVE_THREADS / 32];
-    __shared__ ShiftCand qc[SHIFT_QCAP];
+    __shared__ CAND qc[SHIFT_QCAP];
     __shared__ int qit[SHIFT_QCAP];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const size_t slot0 = ((size_t)pair * a.nseg + seg) * (size_t)(4 * SEG);
@@ -436,23 +438,18 @@ __global__ void __launch_bounds__(SOLVE_THREADS, RP_SOLVE_SHIFT_MIN_BLOCKS) solv
     auto drain = [&](int upto) {  // finish the queued roots [head, upto)
         for (int q = head + tid; q < upto; q += SOLVE_THREADS) {
             const int it = qit[q % SHIFT_QCAP];
-            const ShiftCand c = qc[q % SHIFT_QCAP];
+            const CAND c = qc[q % SHIFT_QCAP];
             const Triplet t = load_triplet(a, pp, pair, it);
-            const ShiftSystem S = shift_system(t);
-            a.models[slot0 + q] = solve_calib_shift_finish(t, S, c);
+            a.models[slot0 + q] = solve_finish(t, c);
             a.hyp_iter[slot0 + q] = it;
         }
         head = upto;
     };
     for (int round = 0; round < SEG / SOLVE_THREADS; ++round) {
         const int it = seg * SEG + round * SOLVE_THREADS + tid;
-        ShiftCand c0, c1, c2, c3;
+        CAND c0, c1, c2, c3;
         int n = 0;
-        if (it < a.iters) {
-            const Triplet t = load_triplet(a, pp, pair, it);
-            const ShiftSystem S = shift_system(t);
-            n = solve_calib_shift_roots(t, S, c0, c1, c2, c3);
-        }
+        if (it < a.iters) n = solve_roots(load_triplet(a, pp, pair, it), c0, c1, c2, c3);
         int incl = n;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {

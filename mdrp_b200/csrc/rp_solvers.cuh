@@ -135,25 +135,19 @@ RP_HD void p3p_refine_lambda(double &l1, double &l2, double &l3, double a12, dou
     }
 }
 
-RP_HD void p3p_emit(P3PSolutions &out, double d0, double d1, double d2, V3 x0, V3 x1, V3 x2, const M3 &XX, V3 Xw0) {
-    const V3 v1 = d0 * x0 - d1 * x1;
-    const V3 v2 = d0 * x0 - d2 * x2;
-    const M3 YY = from_cols(v1, v2, cross(v1, v2));
-    const M3 R = matmul(YY, XX);
-    const int k = out.n;
-    const Quat q = rotmat_to_quat(R);
-    const V3 t = d0 * x0 - mul(R, Xw0);
-    // static indexing keeps the solution arrays in registers
-    if (k == 0) { out.q[0] = q; out.t[0] = t; }
-    else if (k == 1) { out.q[1] = q; out.t[1] = t; }
-    else if (k == 2) { out.q[2] = q; out.t[2] = t; }
-    else { out.q[3] = q; out.t[3] = t; }
-    out.n = k + 1;
-}
+// The solver is split like the scale+shift one (see ShiftCand below): p3p_setup + p3p_candidates are the
+// uniform per-sample part, p3p_finish the per-solution part (Gauss-Newton on the three depths + pose assembly).
+struct P3PSetup {
+    V3 x0, x1, x2;      // bearings after relabelling (side (1,2) is the longest)
+    V3 Xa;              // first 3-D point after relabelling
+    V3 X01, X02;
+    double a01, a02, a12, m01, m02, m12;
+};
+struct P3PCand {
+    double d0, d1, d2;  // depths along the bearings before the refinement
+};
 
-// x: unit bearings in camera 2, X: 3-D points in camera 1.  Finds R,t with d_i x_i = R X_i + t.
-RP_HD void p3p(V3 x0, V3 x1, V3 x2, V3 Xa, V3 Xb, V3 Xc, P3PSolutions &out) {
-    out.n = 0;
+RP_HD P3PSetup p3p_setup(V3 x0, V3 x1, V3 x2, V3 Xa, V3 Xb, V3 Xc) {
     V3 X01 = Xa - Xb, X02 = Xa - Xc, X12 = Xb - Xc;
     double a01 = dot(X01, X01), a02 = dot(X02, X02), a12 = dot(X12, X12);
     // relabel so that side (1,2) is the longest
@@ -172,9 +166,29 @@ RP_HD void p3p(V3 x0, V3 x1, V3 x2, V3 Xa, V3 Xb, V3 Xc, P3PSolutions &out) {
         X01 = neg(X01);
         X02 = X12;
     }
+    P3PSetup S;
+    S.x0 = x0; S.x1 = x1; S.x2 = x2; S.Xa = Xa; S.X01 = X01; S.X02 = X02;
+    S.a01 = a01; S.a02 = a02; S.a12 = a12;
+    S.m01 = dot(x0, x1); S.m02 = dot(x0, x2); S.m12 = dot(x1, x2);
+    return S;
+}
+
+RP_HD void p3p_push(int &n, P3PCand &c0, P3PCand &c1, P3PCand &c2, P3PCand &c3, double d0, double d1, double d2) {
+    P3PCand c;
+    c.d0 = d0; c.d1 = d1; c.d2 = d2;
+    // static indexing keeps the candidates in registers
+    if (n == 0) c0 = c;
+    else if (n == 1) c1 = c;
+    else if (n == 2) c2 = c;
+    else c3 = c;
+    ++n;
+}
+
+// depth triples of the (at most 4) solutions, in the order p3p.cc emits them
+RP_HD int p3p_candidates(const P3PSetup &S, P3PCand &c0, P3PCand &c1, P3PCand &c2, P3PCand &c3) {
+    const double a01 = S.a01, a02 = S.a02, a12 = S.a12, m01 = S.m01, m02 = S.m02, m12 = S.m12;
     const double a12d = 1.0 / a12;
     const double a = a01 * a12d, b = a02 * a12d;
-    const double m01 = dot(x0, x1), m02 = dot(x0, x2), m12 = dot(x1, x2);
     const double m12sq = -m12 * m12 + 1.0, m02sq = -1.0 + m02 * m02, m01sq = -1.0 + m01 * m01;
     const double ab = a * b, bsq = b * b, asq = a * a;
     const double m013 = -2.0 + 2.0 * m01 * m02 * m12;
@@ -205,8 +219,8 @@ RP_HD void p3p(V3 x0, V3 x1, V3 x2, V3 Xa, V3 Xb, V3 Xc, P3PSolutions &out) {
     }
     C01 -= v2; C02 += v1; C12 -= v0;
     C10 += v2; C20 -= v1; C21 += v0;
-    const M3 XX = inverse(from_cols(X01, X02, cross(X01, X02)));
 
+    int n = 0;
     for (int i = 0; i < 2; ++i) {
         const double p0 = C00, p1 = (i == 0) ? C10 : C01, p2 = (i == 0) ? C20 : C02;
         const bool switch_12 = fabs(p0) <= fabs(p1);
@@ -224,9 +238,8 @@ RP_HD void p3p(V3 x0, V3 x1, V3 x2, V3 Xa, V3 Xb, V3 Xc, P3PSolutions &out) {
                 double d1 = tau * d2;
                 double d0 = (w0 * d2 + w1 * d1);
                 if (d0 < 0) continue;
-                p3p_refine_lambda(d0, d1, d2, a01, a02, a12, m01, m02, m12);
-                p3p_emit(out, d0, d1, d2, x0, x1, x2, XX, Xa);
-                if (out.n == 4) return;
+                p3p_push(n, c0, c1, c2, c3, d0, d1, d2);
+                if (n == 4) return n;
             }
         } else {
             const double w0 = -p1 / p0, w1 = -p2 / p0;
@@ -241,13 +254,39 @@ RP_HD void p3p(V3 x0, V3 x1, V3 x2, V3 Xa, V3 Xb, V3 Xc, P3PSolutions &out) {
                 double d1 = tau * d0;
                 double d2 = w0 * d0 + w1 * d1;
                 if (d2 < 0) continue;
-                p3p_refine_lambda(d0, d1, d2, a01, a02, a12, m01, m02, m12);
-                p3p_emit(out, d0, d1, d2, x0, x1, x2, XX, Xa);
-                if (out.n == 4) return;
+                p3p_push(n, c0, c1, c2, c3, d0, d1, d2);
+                if (n == 4) return n;
             }
         }
-        if (out.n > 0 && G) break;
+        if (n > 0 && G) break;
     }
+    return n;
+}
+
+// refinement of the depths and pose assembly: d_i x_i = R X_i + t
+RP_HD void p3p_finish(const P3PSetup &S, const P3PCand &c, Quat &q, V3 &t) {
+    double d0 = c.d0, d1 = c.d1, d2 = c.d2;
+    p3p_refine_lambda(d0, d1, d2, S.a01, S.a02, S.a12, S.m01, S.m02, S.m12);
+    const M3 XX = inverse(from_cols(S.X01, S.X02, cross(S.X01, S.X02)));
+    const V3 v1 = d0 * S.x0 - d1 * S.x1;
+    const V3 v2 = d0 * S.x0 - d2 * S.x2;
+    const M3 YY = from_cols(v1, v2, cross(v1, v2));
+    const M3 R = matmul(YY, XX);
+    q = rotmat_to_quat(R);
+    t = d0 * S.x0 - mul(R, S.Xa);
+}
+
+// x: unit bearings in camera 2, X: 3-D points in camera 1.  Finds R,t with d_i x_i = R X_i + t.
+RP_HD void p3p(V3 x0, V3 x1, V3 x2, V3 Xa, V3 Xb, V3 Xc, P3PSolutions &out) {
+    out.n = 0;
+    const P3PSetup S = p3p_setup(x0, x1, x2, Xa, Xb, Xc);
+    P3PCand c0, c1, c2, c3;
+    const int n = p3p_candidates(S, c0, c1, c2, c3);
+    if (n > 0) { p3p_finish(S, c0, out.q[0], out.t[0]); }
+    if (n > 1) { p3p_finish(S, c1, out.q[1], out.t[1]); }
+    if (n > 2) { p3p_finish(S, c2, out.q[2], out.t[2]); }
+    if (n > 3) { p3p_finish(S, c3, out.q[3], out.t[3]); }
+    out.n = n;
 }
 
 // one minimal sample: three correspondences as homogeneous (x, y, 1) points plus depths
@@ -272,9 +311,7 @@ RP_HD void set_model(ModelSet &out, const Model &m) {
 
 // S1: X_i = d1_i (x1_i, 1), bearings b_i = (x2_i, 1)/|.|, P3P, then
 // scale = (R X_0 + t).x / (d2_0 x2_0.x) from the first sampled point; shifts stay 0.
-RP_HD void solve_calib_scale(const Triplet &s, ModelSet &out) {
-    out.n = 0;
-    V3 X[3], b[3];
+RP_HD void calib_scale_inputs(const Triplet &s, V3 (&X)[3], V3 (&b)[3]) {
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         const V3 h = s.p2[i];
@@ -282,18 +319,29 @@ RP_HD void solve_calib_scale(const Triplet &s, ModelSet &out) {
         X[i] = v3(s.d1[i] * s.p1[i].x, s.d1[i] * s.p1[i].y, s.d1[i] * s.p1[i].z);
         b[i] = v3(h.x / n, h.y / n, h.z / n);
     }
-    P3PSolutions sol;
-    p3p(b[0], b[1], b[2], X[0], X[1], X[2], sol);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        if (k >= sol.n) break;
-        Model m = identity_model();
-        m.q = sol.q[k];
-        m.t = sol.t[k];
-        const M3 R = quat_to_rotmat(m.q);
-        m.scale = (dot(R.r0, X[0]) + m.t.x) / (s.d2[0] * s.p2[0].x);
-        set_model(out, m);
-    }
+}
+RP_HD int solve_roots(const Triplet &s, P3PCand &c0, P3PCand &c1, P3PCand &c2, P3PCand &c3) {
+    V3 X[3], b[3];
+    calib_scale_inputs(s, X, b);
+    return p3p_candidates(p3p_setup(b[0], b[1], b[2], X[0], X[1], X[2]), c0, c1, c2, c3);
+}
+RP_HD Model solve_finish(const Triplet &s, const P3PCand &c) {
+    V3 X[3], b[3];
+    calib_scale_inputs(s, X, b);
+    Model m = identity_model();
+    p3p_finish(p3p_setup(b[0], b[1], b[2], X[0], X[1], X[2]), c, m.q, m.t);
+    const M3 R = quat_to_rotmat(m.q);
+    m.scale = (dot(R.r0, X[0]) + m.t.x) / (s.d2[0] * s.p2[0].x);
+    return m;
+}
+RP_HD void solve_calib_scale(const Triplet &s, ModelSet &out) {
+    out.n = 0;
+    P3PCand c0, c1, c2, c3;
+    const int n = solve_roots(s, c0, c1, c2, c3);
+    if (n > 0) set_model(out, solve_finish(s, c0));
+    if (n > 1) set_model(out, solve_finish(s, c1));
+    if (n > 2) set_model(out, solve_finish(s, c2));
+    if (n > 3) set_model(out, solve_finish(s, c3));
 }
 
 // S2: unknowns s = scale^2, u = shift1, v = shift2.  For the pairs (0,1),(0,2),(1,2):
@@ -420,6 +468,11 @@ RP_HD Model solve_calib_shift_finish(const Triplet &t, const ShiftSystem &S, con
     return m;
 }
 
+RP_HD int solve_roots(const Triplet &t, ShiftCand &c0, ShiftCand &c1, ShiftCand &c2, ShiftCand &c3) {
+    return solve_calib_shift_roots(t, shift_system(t), c0, c1, c2, c3);
+}
+RP_HD Model solve_finish(const Triplet &t, const ShiftCand &c) { return solve_calib_shift_finish(t, shift_system(t), c); }
+
 RP_HD void solve_calib_shift(const Triplet &t, ModelSet &out) {
     out.n = 0;
     const ShiftSystem S = shift_system(t);
@@ -502,8 +555,11 @@ RP_HD double peval(const Poly<D> &p, double x) {
     return v;
 }
 
-RP_HD void solve_shared_focal(const Triplet &t, ModelSet &out) {
-    out.n = 0;
+struct FocalCand {
+    double g, sc2, nu;  // 1/f^2, scale^2, depth of point 2 in camera 2 over scale
+};
+
+RP_HD int solve_roots(const Triplet &t, FocalCand &c0, FocalCand &c1, FocalCand &c2, FocalCand &c3) {
     double A1[3], B1[3];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
@@ -538,6 +594,7 @@ RP_HD void solve_shared_focal(const Triplet &t, ModelSet &out) {
         P[i] = 1.0 * (4.0 * lhs.c[i] + -1.0 * r1.c[i]) + 1.0 * (4.0 * r2.c[i] + -4.0 * r3.c[i]);
     double r0_ = 0, r1_ = 0, r2_ = 0, r3_ = 0;
     const int nr = solve_quartic_real(P[4] / P[5], P[3] / P[5], P[2] / P[5], P[1] / P[5], r0_, r1_, r2_, r3_);
+    int n = 0;
 #pragma unroll
     for (int ir = 0; ir < 4; ++ir) {
         if (ir >= nr) break;
@@ -554,21 +611,43 @@ RP_HD void solve_shared_focal(const Triplet &t, ModelSet &out) {
         if (!(sc2 > 0.0)) continue;
         const double nu = peval(N, g) / (2.0 * s1 * peval(L, g));
         if (!(nu > 0.0)) continue;
-        const double w = sqrt(g);
-        Model m = identity_model();
-        m.scale = sqrt(sc2);
-        m.f1 = 1.0 / w;
-        m.f2 = m.f1;
-        V3 X[3], Y[3];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            X[i] = v3(t.d1[i] * t.p1[i].x * w, t.d1[i] * t.p1[i].y * w, t.d1[i]);
-            const double dep = m.scale * (i < 2 ? t.d2[i] : nu);
-            Y[i] = v3(dep * t.p2[i].x * w, dep * t.p2[i].y * w, dep);
-        }
-        align_triangles(X[0], X[1], X[2], Y[0], Y[1], Y[2], m.q, m.t);
-        set_model(out, m);
+        FocalCand c;
+        c.g = g; c.sc2 = sc2; c.nu = nu;
+        // static indexing keeps the candidates in registers
+        if (n == 0) c0 = c;
+        else if (n == 1) c1 = c;
+        else if (n == 2) c2 = c;
+        else c3 = c;
+        ++n;
     }
+    return n;
+}
+
+RP_HD Model solve_finish(const Triplet &t, const FocalCand &c) {
+    const double w = sqrt(c.g);
+    Model m = identity_model();
+    m.scale = sqrt(c.sc2);
+    m.f1 = 1.0 / w;
+    m.f2 = m.f1;
+    V3 X[3], Y[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        X[i] = v3(t.d1[i] * t.p1[i].x * w, t.d1[i] * t.p1[i].y * w, t.d1[i]);
+        const double dep = m.scale * (i < 2 ? t.d2[i] : c.nu);
+        Y[i] = v3(dep * t.p2[i].x * w, dep * t.p2[i].y * w, dep);
+    }
+    align_triangles(X[0], X[1], X[2], Y[0], Y[1], Y[2], m.q, m.t);
+    return m;
+}
+
+RP_HD void solve_shared_focal(const Triplet &t, ModelSet &out) {
+    out.n = 0;
+    FocalCand c0, c1, c2, c3;
+    const int n = solve_roots(t, c0, c1, c2, c3);
+    if (n > 0) set_model(out, solve_finish(t, c0));
+    if (n > 1) set_model(out, solve_finish(t, c1));
+    if (n > 2) set_model(out, solve_finish(t, c2));
+    if (n > 3) set_model(out, solve_finish(t, c3));
 }
 
 RP_HD void solve_minimal(int variant, const Triplet &t, ModelSet &out) {

@@ -334,3 +334,22 @@ def test_pruning_does_not_change_results(cfg, monkeypatch):
     assert np.allclose(a[1]["model_score"], b[1]["model_score"], rtol=1e-12, atol=0)
     pruned_ctx.close()
     full_ctx.close()
+
+
+@pytest.mark.parametrize("cfg", ["cfg1_calib_scale", "cfg2_calib_shift", "cfg3_shared_focal"])
+def test_two_phase_solve_kernels_are_bit_identical(cfg, monkeypatch):
+    """solve2_kernel (roots per sample, then one thread per queued root) against the thread-per-iteration
+    solve_kernel (RP_SOLVE_GENERIC=1): same arithmetic, so every output byte must agree."""
+    c = synth.CONFIGS[cfg]
+    scs, variant, offs, x1, x2, d1, d2, cams = _batch(cfg, range(500, 516), n=500)
+    o = _options(3000, shift=c["shift"])
+    monkeypatch.delenv("RP_SOLVE_GENERIC", raising=False)
+    two = nv.Context(0)
+    a = two.estimate_batch_host(variant, offs, x1, x2, d1, d2, cams, o)
+    monkeypatch.setenv("RP_SOLVE_GENERIC", "1")
+    gen = nv.Context(0)
+    b = gen.estimate_batch_host(variant, offs, x1, x2, d1, d2, cams, o)
+    for u, v in zip(a, b):
+        assert u.tobytes() == v.tobytes()
+    two.close()
+    gen.close()
