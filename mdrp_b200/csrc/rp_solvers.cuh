@@ -368,7 +368,7 @@ RP_HD ShiftEq shift_equation(V3 p1i, V3 p1j, V3 p2i, V3 p2j, double ai, double a
 
 // The solver is split in two so that the RANSAC kernel can run the cheap, uniform part (equations, quartic,
 // root filter) with one thread per sample and the expensive per-root part (Newton polish + triangle
-// alignment) with one thread per surviving root (solve_shift_kernel): a sample has 0..4 roots, and a
+// alignment) with one thread per surviving root (solve2_kernel): a sample has 0..4 roots, and a
 // thread-per-sample loop over them leaves most lanes idle.
 struct ShiftSystem {
     ShiftEq e0, e1, e2;

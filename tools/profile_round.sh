@@ -19,5 +19,5 @@ cap() {  # name kernel-regex skip
 cap bound bound_kernel 0
 cap lm lm_kernel 0
 cap score_survivors score_kernel 1
-cap solve solve_shift_kernel 0
+cap solve solve2_kernel 0
 ls -la gpurun_out | head -40
