@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, RP_SOLVE_MIN_BLOCKS) solve_kern
 // assembly), model written straight to its final slot (queue position = slot).  Same arithmetic as the
 // one-call solvers, hence bit-identical models; the thread-per-iteration loop over the roots ran at 12.8 of
 // 32 active lanes (ncu, scale+shift).  CAND = P3PCand | ShiftCand | FocalCand selects the solver.
-constexpr int SHIFT_QCAP = 4 * SOLVE_THREADS + SOLVE_THREADS;  // one round of appends on top of < 256 leftovers
+constexpr int SOLVE_QCAP = 4 * SOLVE_THREADS + SOLVE_THREADS;  // one round of appends on top of < 256 leftovers
 
 RP_D Triplet load_triplet(const SolveArgs &a, const PairParams &pp, int pair, int it) {
     const int *s = a.samples + ((size_t)pair * a.iters + it) * 3;
@@ -418,16 +418,16 @@ RP_D Triplet load_triplet(const SolveArgs &a, const PairParams &pp, int pair, in
     return t;
 }
 
-#ifndef RP_SOLVE_SHIFT_MIN_BLOCKS
-#define RP_SOLVE_SHIFT_MIN_BLOCKS 2   // 128 registers: measured 17.8 ms vs 23.1 ms per 10k pairs at 1 block/SM
+#ifndef RP_SOLVE2_MIN_BLOCKS
+#define RP_SOLVE2_MIN_BLOCKS 2   // 128 registers: measured 17.8 ms vs 23.1 ms per 10k pairs at 1 block/SM
 #endif
 template <class CAND>
-__global__ void __launch_bounds__(SOLVE_THREADS, RP_SOLVE_SHIFT_MIN_BLOCKS) solve2_kernel(SolveArgs a) {
+__global__ void __launch_bounds__(SOLVE_THREADS, RP_SOLVE2_MIN_BLOCKS) solve2_kernel(SolveArgs a) {
     const int seg = blockIdx.x, pair = blockIdx.y;
     const PairParams pp = a.pairs[pair];
     __shared__ int warp_tot[SOLVE_THREADS / 32];
-    __shared__ CAND qc[SHIFT_QCAP];
-    __shared__ int qit[SHIFT_QCAP];
+    __shared__ CAND qc[SOLVE_QCAP];
+    __shared__ int qit[SOLVE_QCAP];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const size_t slot0 = ((size_t)pair * a.nseg + seg) * (size_t)(4 * SEG);
     if (!pp.valid) {
@@ -437,8 +437,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS, RP_SOLVE_SHIFT_MIN_BLOCKS) solv
     int head = 0, tail = 0;  // queue positions == slot indices of the segment (uniform across the block)
     auto drain = [&](int upto) {  // finish the queued roots [head, upto)
         for (int q = head + tid; q < upto; q += SOLVE_THREADS) {
-            const int it = qit[q % SHIFT_QCAP];
-            const CAND c = qc[q % SHIFT_QCAP];
+            const int it = qit[q % SOLVE_QCAP];
+            const CAND c = qc[q % SOLVE_QCAP];
             const Triplet t = load_triplet(a, pp, pair, it);
             a.models[slot0 + q] = solve_finish(t, c);
             a.hyp_iter[slot0 + q] = it;
@@ -467,10 +467,10 @@ __global__ void __launch_bounds__(SOLVE_THREADS, RP_SOLVE_SHIFT_MIN_BLOCKS) solv
             total += v;
         }
         const int pos = tail + wbase + (incl - n);
-        if (n > 0) { qc[pos % SHIFT_QCAP] = c0; qit[pos % SHIFT_QCAP] = it; }
-        if (n > 1) { qc[(pos + 1) % SHIFT_QCAP] = c1; qit[(pos + 1) % SHIFT_QCAP] = it; }
-        if (n > 2) { qc[(pos + 2) % SHIFT_QCAP] = c2; qit[(pos + 2) % SHIFT_QCAP] = it; }
-        if (n > 3) { qc[(pos + 3) % SHIFT_QCAP] = c3; qit[(pos + 3) % SHIFT_QCAP] = it; }
+        if (n > 0) { qc[pos % SOLVE_QCAP] = c0; qit[pos % SOLVE_QCAP] = it; }
+        if (n > 1) { qc[(pos + 1) % SOLVE_QCAP] = c1; qit[(pos + 1) % SOLVE_QCAP] = it; }
+        if (n > 2) { qc[(pos + 2) % SOLVE_QCAP] = c2; qit[(pos + 2) % SOLVE_QCAP] = it; }
+        if (n > 3) { qc[(pos + 3) % SOLVE_QCAP] = c3; qit[(pos + 3) % SOLVE_QCAP] = it; }
         tail += total;
         __syncthreads();
         // full batches only; the remainder waits for the next round (or the final drain)
