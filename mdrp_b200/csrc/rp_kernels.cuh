@@ -937,9 +937,16 @@ __global__ void __launch_bounds__(SCORE_THREADS, RP_BOUND_MIN_BLOCKS) bound_kern
         const int i0 = (e % a.grp_per_pair == 0 && chunk == 0) ? a.head / SCORE_WARPS : 0;
         if (my_nh <= i0) continue;
         __syncwarp();
+        bool nonfinite = false;
         if (lane < my_nh) {
             const Model m = a.models[slot0 + w + lane * SCORE_WARPS];
             const M3 E = POSE ? essential_from_motion(m.q, m.t) : fundamental_from_model(m);
+            // A model with a non-finite E (the minimal solvers return NaN models now and then, P3P for ~6 % of
+            // its solutions) has r2 = NaN for every correspondence: the reference counts 0 inliers and sums
+            // N thr^2, which can neither exceed B0 >= 0 nor undercut S0 <= N thr^2 (S0 exists: the pair has an
+            // exactly scored head, checked below).  Dead on arrival.
+            nonfinite = !(isfinite(E.r0.x) && isfinite(E.r0.y) && isfinite(E.r0.z) && isfinite(E.r1.x) && isfinite(E.r1.y) &&
+                          isfinite(E.r1.z) && isfinite(E.r2.x) && isfinite(E.r2.y) && isfinite(E.r2.z));
             const Filter32 f = make_filter32(E, pp.thr, pp.Mmax, pp.mmax);
             // 1012 * delta_a^2 with delta_a = 16 u Emax m (the sqrt(den) term of eps)
             const double emax = fmax(fmax(fmax(fabs(E.r0.x), fabs(E.r0.y)), fmax(fabs(E.r0.z), fabs(E.r1.x))),
@@ -966,6 +973,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, RP_BOUND_MIN_BLOCKS) bound_kern
         double need_d = fmax((double)(n - B0), S0 < 1e300 ? ceil(S0 / ((double)thr2_lo * (1.0 - 2e-4))) : 4.0e9);
         const int need_out = need_d > 2.0e9 ? 0x7fffffff : max((int)need_d, 1);
         unsigned alive = (my_nh >= 32 ? 0xffffffffu : ((1u << my_nh) - 1u)) & ~((1u << i0) - 1u);
+        if (S0 < 1e300) alive &= ~__ballot_sync(0xffffffffu, nonfinite);
         unsigned cheap = 0;  // models that switched to count-only evaluation (their lb is void)
         int *out_cnt = sh.outc[wid];
 #pragma unroll
