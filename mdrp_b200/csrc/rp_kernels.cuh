@@ -708,7 +708,13 @@ __global__ void __launch_bounds__(SCORE_THREADS) score_kernel(ScoreArgs a) {
             c.q = m.q;
             c.t = m.t;
             sh.hc[tid] = c;
-            sh.hf[tid] = make_filter32(c.E, pp.thr, pp.Mmax, pp.mmax);
+            Filter32 f32 = make_filter32(c.E, pp.thr, pp.Mmax, pp.mmax);
+            // non-finite E (NaN model from a minimal solver): r2 is NaN for every correspondence, i.e. no inliers
+            // and score N thr^2 — exactly what the loop below leaves behind when it skips the model
+            f32.pad = (isfinite(c.E.r0.x) && isfinite(c.E.r0.y) && isfinite(c.E.r0.z) && isfinite(c.E.r1.x) &&
+                       isfinite(c.E.r1.y) && isfinite(c.E.r1.z) && isfinite(c.E.r2.x) && isfinite(c.E.r2.y) &&
+                       isfinite(c.E.r2.z)) ? 0.f : 1.f;
+            sh.hf[tid] = f32;
             if (POSE) sh.hch[tid] = make_cheir32(m.q, m.t);
         }
         for (int i = tid; i < HB * SCORE_WARPS; i += SCORE_THREADS) {
@@ -732,6 +738,7 @@ __global__ void __launch_bounds__(SCORE_THREADS) score_kernel(ScoreArgs a) {
             }
             for (int h = 0; h < nh; ++h) {
                 const Filter32 f = sh.hf[h];
+                if (f.pad != 0.f) continue;  // NaN model: nothing can be an inlier
                 unsigned cand = 0;
 #pragma unroll
                 for (int j = 0; j < PT; ++j)
