@@ -34,7 +34,7 @@ struct LMArgs {
     int *work_counter;           // zeroed before the launch: blocks take problems dynamically
 };
 
-constexpr int LM_LIST_CAP = 8192;
+constexpr int LM_LIST_CAP = 16384;  // 32 KB of shared memory per block (3 blocks/SM); indices fit 16 bits
 
 // Warp reduction of NV per-lane values as a reduce-scatter: at the step with lane mask O every lane keeps one
 // half of its values and sends the other half to its partner, so the number of live values halves each step

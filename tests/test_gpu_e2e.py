@@ -144,10 +144,18 @@ def test_batch_vs_oracle(ctx, port, cfg):
 
 @pytest.mark.parametrize("cfg", ["cfg1_calib_scale", "cfg3_shared_focal"])
 def test_large_pair_vs_oracle(ctx, port, cfg):
-    """A pair with more correspondences than the LM kernel's shared-memory inlier list holds (8192): the final
-    refinement takes its mask-on-the-fly path and must still agree with the oracle."""
+    """Pairs around the capacity of the LM kernel's shared-memory inlier list (16384): 9000 correspondences use the
+    list, 17000 take the mask-on-the-fly path; both must agree with the oracle."""
     c = synth.CONFIGS[cfg]
     scs, variant, offs, x1, x2, d1, d2, cams = _batch(cfg, [77, 78], n=9000)
+    big = synth.scene_for(cfg, 79, n=17000)
+    scs.append(big)
+    bx1, bx2 = (big.x1, big.x2) if variant < 2 else big.centred()
+    x1, x2 = np.concatenate([x1, bx1]), np.concatenate([x2, bx2])
+    d1, d2 = np.concatenate([d1, big.d1]), np.concatenate([d2, big.d2])
+    offs = np.r_[offs, offs[-1] + 17000]
+    if cams is not None:
+        cams = np.concatenate([cams, [[big.f1, big.f1, 640, 480, big.f2, big.f2, 640, 480]]])
     iters = 200
     models, stats, masks = ctx.estimate_batch_host(variant, offs, x1, x2, d1, d2, cams, _options(iters, c["shift"]))
     ro = port.ransac_opt(max_iterations=iters, min_iterations=iters, max_epipolar_error=2.0, max_reproj_error=16.0,
