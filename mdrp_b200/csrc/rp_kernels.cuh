@@ -1010,9 +1010,10 @@ __global__ void __launch_bounds__(SCORE_THREADS, RP_BOUND_MIN_BLOCKS) bound_kern
             const int nvalid = min(group_pts, n - g * group_pts);
             const bool full = nvalid == group_pts;
             evaluated += (unsigned long long)__popc(alive) * nvalid;
+            // only the models still alive (late groups: a handful of the 16)
 #pragma unroll 1
-            for (int i = 0; i < my_nh; ++i) {
-                if (!((alive >> i) & 1u)) continue;
+            for (unsigned todo = alive; todo; todo &= todo - 1) {
+                const int i = __ffs(todo) - 1;
                 const BoundFilter f = sh.hf[wid][i];
                 int c = 0;
                 float s = 0.f;
