@@ -1,4 +1,7 @@
-import sys,time; sys.path.insert(0,'/root/repo')
+"""Latency of the per-pair Python call (the reference's own calling convention) on one GPU:
+    gpurun -- python tools/single_pair_latency.py"""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from mdrp_b200 import api, synth, _native as nv
 for cfg,iters in (('cfg1_calib_scale',1000),('cfg2_calib_shift',10000),('cfg5_roma_calib',1000),('cfg5_roma_calib',10000)):
