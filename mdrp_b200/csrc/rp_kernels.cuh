@@ -1341,14 +1341,17 @@ __global__ void merge_kernel(MergeArgs a) {
         const size_t pslot = (size_t)pair * a.nseg * (4 * SEG);
         const int nev = a.n_events[pair];
         // the loop of ransac<>() breaks at the first it > min_iterations with it > dynamic_max_iter;
-        // dynamic_max_iter only changes after an LO, so the break point is known between events
+        // dynamic_max_iter only changes after an LO, so the break point is known between events.  The test
+        // runs at the top of an iteration: after an LO in iteration it_prev the loop cannot stop before
+        // it_prev + 1, even when the new dynamic_max_iter is already far behind.
         double dyn_max_iter = (double)a.max_iterations;
-        long long stop_it = -1;
+        long long stop_it = -1, it_prev = -1;
         for (int i = 0; i < nev; ++i) {
             const int ev = a.events[pair * EV + i];
             const long long it_e = a.hyp_iter[pslot + ev];
-            const long long cand = max(a.min_iterations + 1, (long long)floor(dyn_max_iter) + 1);
+            const long long cand = max(max(a.min_iterations + 1, (long long)floor(dyn_max_iter) + 1), it_prev + 1);
             if (cand <= it_e) { stop_it = cand; break; }
+            it_prev = it_e;
             const double s = a.score[pslot + ev];
             if (s < st.model_score) {
                 st.model_score = s;
@@ -1374,7 +1377,7 @@ __global__ void merge_kernel(MergeArgs a) {
             }
         }
         if (stop_it < 0) {
-            const long long cand = max(a.min_iterations + 1, (long long)floor(dyn_max_iter) + 1);
+            const long long cand = max(max(a.min_iterations + 1, (long long)floor(dyn_max_iter) + 1), it_prev + 1);
             if (cand < a.iters) stop_it = cand;                             // stopped inside what we generated
             else if (a.iters >= a.max_iterations) stop_it = a.max_iterations;  // loop ran to the end
             else if (cand == a.iters) stop_it = cand;                        // would stop exactly at the next it
@@ -1405,8 +1408,9 @@ __global__ void merge2_kernel(Merge2Args a) {
     rp_stats st = a.stats[pair];
     st.refinements++;
     const double rs = a.ref_score[pair];
+    // unlike the LO inside the loop, the final refinement of ransac<>() leaves stats.model_score alone: the
+    // reported score is the one before this step (with no minimal model at all it stays DBL_MAX)
     if (rs < st.model_score) {
-        st.model_score = rs;
         st.num_inliers = a.ref_count[pair];
         a.best[pair] = a.refined[pair];
     }

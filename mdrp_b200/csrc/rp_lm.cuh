@@ -20,7 +20,7 @@ RP_HD double loss_eval(int type, double thr, double r2) {
     const double t2 = thr * thr;
     switch (type) {
     case RP_LOSS_TRIVIAL: return r2;
-    case RP_LOSS_TRUNCATED: return r2 < t2 ? r2 : t2;
+    case RP_LOSS_TRUNCATED: return t2 < r2 ? t2 : r2;  // std::min(r2, t2) of the reference: a NaN residual stays NaN
     case RP_LOSS_HUBER: { const double r = sqrt(r2); return r <= thr ? r2 : thr * (2.0 * r - thr); }
     case RP_LOSS_CAUCHY: return t2 * log1p(r2 / t2);
     case RP_LOSS_TRUNCATED_CAUCHY: return r2 > t2 ? t2 * log1p(1.0) : t2 * log1p(r2 / t2);
@@ -205,7 +205,11 @@ RP_HD double point_eval(const LMFrame &F, const LMParams &P, double x1_0, double
         const double inv = lm_rsqrt(A * if2sq + B * if1sq);
         const double rs = C * inv;
         cost += P.weight_sampson * loss_eval(loss_type, P.loss_scale, rs * rs);
-        const double w = P.weight_sampson * loss_weight(loss_type, P.loss_scale, rs * rs);
+        // the reference scales the Sampson residual and its Jacobian row by weight_sampson, so the normal equations
+        // carry weight_sampson^2 although the cost carries weight_sampson (verified on the binary; invisible at 1)
+        // ... and the focal accumulators evaluate the robust weight at weight_sampson * r^2, the calibrated one at r^2
+        const double w = P.weight_sampson * P.weight_sampson *
+                         loss_weight(loss_type, P.loss_scale, FOCAL ? P.weight_sampson * (rs * rs) : rs * rs);
         if (w != 0.0) {
 #pragma unroll
             for (int i = 0; i < NP; ++i) J[i] = 0.0;

@@ -820,7 +820,7 @@ static double loss_eval(int type, double thr, double r2) {
     const double t2 = thr * thr;
     switch (type) {
     case RO_LOSS_TRIVIAL: return r2;
-    case RO_LOSS_TRUNCATED: return r2 < t2 ? r2 : t2;
+    case RO_LOSS_TRUNCATED: return t2 < r2 ? t2 : r2; /* std::min(r2, t2): a NaN residual stays NaN */
     case RO_LOSS_HUBER: { double r = sqrt(r2); return r <= thr ? r2 : thr * (2.0 * r - thr); }
     case RO_LOSS_CAUCHY: return t2 * log1p(r2 / t2);
     case RO_LOSS_TRUNCATED_CAUCHY: return r2 > t2 ? t2 * log1p(1.0) : t2 * log1p(r2 / t2);
@@ -1057,7 +1057,16 @@ RO_API void ro_accumulate(int variant, const double *x1, const double *x2, const
     for (size_t k = 0; k < n; ++k) {
         point_terms(&c, x1 + 2 * k, x2 + 2 * k, d1[k], d2[k], 1, &o);
         if (weight_sampson > 0.0) {
-            double w = weight_sampson * loss_weight(loss_type, loss_scale, o.rs * o.rs);
+            /* the binary scales the Sampson residual AND its Jacobian row by weight_sampson before the rank-1
+             * update, i.e. the normal equations carry weight_sampson^2 while the cost (ro_cost) carries
+             * weight_sampson — verified against refine_monodepth_relpose so@0x261030 with weights 0.25/0.5/2
+             * and all losses (one damped step reproduced to 1e-16 only with the square).  Invisible at the
+             * default weight 1. */
+            /* ... and the two focal accumulators (so@0x2592e0 / so@0x260fa0) evaluate the robust weight at
+             * weight_sampson * r^2 where the calibrated one (so@0x261030) uses r^2 (same experiment, CAUCHY /
+             * HUBER / TRUNCATED_CAUCHY at weights 0.5 and 2: 1e-15 only with this argument). */
+            const double warg = (variant == RO_SHARED || variant == RO_VARYING) ? weight_sampson * (o.rs * o.rs) : o.rs * o.rs;
+            double w = weight_sampson * weight_sampson * loss_weight(loss_type, loss_scale, warg);
             if (w != 0.0)
                 for (int i = 0; i < np; ++i) {
                     Jtr[i] += w * o.Js[i] * o.rs;
@@ -1294,12 +1303,15 @@ RO_API void ro_ransac(int variant, const double *x1, const double *x2, const dou
             dyn_max_iter = ceil(log_prob_missing / log(prob_outlier) * opt->dyn_num_trials_mult);
         }
     }
+    /* final refinement: unlike the LO inside the loop it does NOT write stats.model_score (the reported score is
+     * the one before this step) — seen on the binary: with no minimal model at all model_score stays DBL_MAX
+     * while num_inliers / the model are taken from the refined identity, and one-iteration runs report the
+     * pre-refinement score. */
     ro_model refined = *best;
     est_refine(&e, &refined);
     stats->refinements++;
     double rs = est_score(&e, &refined, &cnt);
     if (rs < stats->model_score) {
-        stats->model_score = rs;
         stats->num_inliers = (int64_t)cnt;
         *best = refined;
     }

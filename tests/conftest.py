@@ -29,6 +29,11 @@ def prosac_golden():
 
 
 @pytest.fixture(scope="session")
+def extra_golden():
+    return np.load(os.path.join(ROOT, "tests", "golden", "extra.npz"))
+
+
+@pytest.fixture(scope="session")
 def port():
     from oracle import port as p
     p.build()

@@ -13,18 +13,24 @@ pytestmark = pytest.mark.gpu
 
 
 def test_randomised_parity_regular_regime(ctx, port):
-    """N >= 21 with a reprojection term.  Hard requirements on every case: iterations, num_inliers and the inlier
-    mask equal the oracle's.  The two documented degrees of freedom:
+    """N >= 21 with a reprojection term; PROSAC and early termination in a quarter of the cases each.  Hard
+    requirements: `iterations` equal the oracle's in every case; num_inliers and the inlier mask in every case with a
+    consensus.  The documented degrees of freedom:
       * `refinements` may differ only when the model is identical — the same minimal model met twice scores
         bit-identically in the reference but only up to summation order here, so a strict `<` can go either way;
-      * the model may differ only when the final refinement is under-determined (< 10 inliers for 7-9 parameters)."""
+      * the model may differ only when the final refinement is under-determined (< 10 inliers for 7-9 parameters);
+      * on inputs without any consensus (best model supported by little more than its own sample, <= 5 inliers) many
+        minimal models tie at a score of (N - 3) thr^2 + rounding noise, and which one is "best" is decided by that
+        noise in the reference as well."""
     total, bad = fuzz_parity.run(ctx, port, cases=1600, seed=11, regime="regular")
     assert total == 1600
     for b in bad:
-        assert b["same_mask"], b
-        assert b["stats_gpu"][1:] == b["stats_ref"][1:], b
-        if b["stats_gpu"][0] != b["stats_ref"][0]:
-            assert b["same_model"], b
+        assert b["stats_gpu"][1] == b["stats_ref"][1], b               # iterations: always
+        no_consensus = b["stats_ref"][2] <= 5                            # best model supported by (about) its own sample
+        if not no_consensus:
+            assert b["same_mask"] and b["stats_gpu"][2] == b["stats_ref"][2], b
+            if b["stats_gpu"][0] != b["stats_ref"][0]:
+                assert b["same_model"], b
         if not b["same_model"]:
             assert b["stats_ref"][2] < 10, b
     assert len(bad) <= 0.01 * total, bad

@@ -4,7 +4,7 @@ reference wheel is absent."""
 import numpy as np
 import pytest
 
-from util import VARIANT_ID, dedup, models_close, same_set
+from util import VARIANT_ID, dedup, extra_cases, models_close, same_set
 
 VARIANTS = ["calib", "calib_shift", "shared", "varying"]
 
@@ -140,3 +140,28 @@ def test_prosac_end_to_end_matches_reference(prosac_golden, port):
         assert abs(st.model_score - g[key + "_fstats"][1]) <= 1e-12 * abs(g[key + "_fstats"][1]), key
         assert (mask == g[key + "_mask"].astype(bool)).all(), key
         assert models_close(m, g[key + "_model"], rtol=1e-8, atol=1e-10), key
+
+
+def test_extra_goldens_match_reference(extra_golden, port):
+    """weight_sampson != 1, early termination after a late LO, one-iteration runs (final refinement leaves model_score
+    alone, DBL_MAX without any minimal model), all losses, PROSAC on/off — outputs of the reference binary."""
+    g = extra_golden
+    n = 0
+    for key, variant, o in extra_cases(g):
+        ro = port.ransac_opt(max_iterations=o["iters"], min_iterations=o["min_iters"], max_epipolar_error=o["t_epi"],
+                             max_reproj_error=o["t_rep"], seed=o["seed"], estimate_shift=variant == 1,
+                             weight_sampson=o["weight_sampson"], progressive_sampling=o["prosac"],
+                             max_prosac_iterations=o["max_prosac"])
+        bo = port.bundle_opt(max_iterations=o["bundle_iters"], loss_type=o["loss"], loss_scale=0.5 * o["t_epi"])
+        f1, f2 = g[key + "_f"]
+        cams = ([f1, f1, 640, 480], [f2, f2, 640, 480]) if variant < 2 else (None, None)
+        m, st, mask = port.estimate(variant, g[key + "_x1"], g[key + "_x2"], g[key + "_d1"], g[key + "_d2"],
+                                    cams[0], cams[1], ro, bo)
+        assert (st.refinements, st.iterations, st.num_inliers) == tuple(int(v) for v in g[key + "_stats"]), key
+        assert (mask == g[key + "_mask"].astype(bool)).all(), key
+        ref_score = g[key + "_fstats"][1]
+        assert st.model_score == ref_score or abs(st.model_score - ref_score) <= 1e-9 * abs(ref_score) + 1e-24, key  # 1e-24: zero-noise scenes score ~1e-31 (rounding noise)
+        if st.num_inliers >= 10:   # fewer inliers than ~parameters: the final refinement is under-determined
+            assert models_close(m, g[key + "_model"], rtol=1e-6, atol=1e-8), key
+        n += 1
+    assert n == 160

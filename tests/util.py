@@ -86,3 +86,15 @@ def maa(errs, max_deg=10):
     """mAA(10 deg) of /root/reference/utils/eval_utils.py:49-52; NaN counts as 180."""
     e = np.array([180.0 if not np.isfinite(x) else x for x in errs])
     return float(np.mean([np.mean(e < t) for t in range(1, max_deg + 1)]) * 100.0)
+
+
+LOSS_NAMES = ["TRIVIAL", "TRUNCATED", "HUBER", "CAUCHY", "TRUNCATED_CAUCHY"]
+
+
+def extra_cases(g):
+    """(key, variant, dict of options) for every case of tests/golden/extra.npz (make_golden_extra.py)."""
+    for key in sorted(k[:-6] for k in g.files if k.endswith("_model")):
+        io, fo = g[key + "_iopts"], g[key + "_fopts"]
+        yield key, int(key[1]), dict(iters=int(io[0]), min_iters=int(io[1]), seed=int(io[2]), prosac=bool(io[3]),
+                                     max_prosac=int(io[4]), bundle_iters=int(io[5]), loss=LOSS_NAMES[int(io[6])],
+                                     t_epi=float(fo[0]), t_rep=float(fo[1]), weight_sampson=float(fo[2]))

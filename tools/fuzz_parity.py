@@ -50,7 +50,14 @@ def random_case(rng, variant, regime="regular"):
                 t_epi=float(rng.choice([0.5, 2.0, 5.0])),
                 t_rep=float(rng.choice([8.0, 16.0] if regime == "regular" else [0.0, 8.0, 16.0])),
                 loss=str(rng.choice(LOSSES)), bundle_iters=int(rng.choice([0, 5, 100])),
-                weight_sampson=float(rng.choice([1.0, 0.5])))
+                weight_sampson=float(rng.choice([1.0, 0.5])),
+                # a quarter of the cases each: PROSAC sampling (switching back to uniform after 40 samples or never),
+                # early termination (min_iterations < max_iterations)
+                prosac=bool(rng.integers(0, 4) == 0), max_prosac=int(rng.choice([40, 100000])),
+                min_iters=None)
+    if rng.integers(0, 4) == 0:
+        opts["min_iters"] = int(rng.choice([1, 10, 30]))
+        opts["iters"] = int(rng.choice([100, 400]))
     return sc, x1, x2, d1, d2, opts
 
 
@@ -64,7 +71,9 @@ def run(ctx, port, cases=200, seed=0, verbose=False, regime="regular"):
             sc, x1, x2, d1, d2, o = random_case(rng, variant, regime)
             n = len(d1)
             opt = nv.default_options()
-            opt.max_iterations = opt.min_iterations = o["iters"]
+            opt.max_iterations = o["iters"]
+            opt.min_iterations = o["iters"] if o["min_iters"] is None else o["min_iters"]
+            opt.progressive_sampling, opt.max_prosac_iterations = int(o["prosac"]), o["max_prosac"]
             opt.max_epipolar_error, opt.max_reproj_error, opt.seed = o["t_epi"], o["t_rep"], o["seed"]
             opt.estimate_shift = int(variant == 1)
             opt.weight_sampson = o["weight_sampson"]
@@ -79,9 +88,10 @@ def run(ctx, port, cases=200, seed=0, verbose=False, regime="regular"):
                 a1, a2 = x1 - [640.0, 480.0], x2 - [640.0, 480.0]
                 cams, cam = None, (None, None)
             models, stats, masks = ctx.estimate_batch_host(variant, [0, n], a1, a2, d1, d2, cams, opt)
-            ro = port.ransac_opt(max_iterations=o["iters"], min_iterations=o["iters"], max_epipolar_error=o["t_epi"],
-                                 max_reproj_error=o["t_rep"], seed=o["seed"], estimate_shift=variant == 1,
-                                 weight_sampson=o["weight_sampson"])
+            ro = port.ransac_opt(max_iterations=o["iters"], min_iterations=int(opt.min_iterations),
+                                 max_epipolar_error=o["t_epi"], max_reproj_error=o["t_rep"], seed=o["seed"],
+                                 estimate_shift=variant == 1, weight_sampson=o["weight_sampson"],
+                                 progressive_sampling=o["prosac"], max_prosac_iterations=o["max_prosac"])
             bo = port.bundle_opt(max_iterations=o["bundle_iters"], loss_type=o["loss"], loss_scale=0.5 * o["t_epi"])
             m, st, mask = port.estimate(variant, a1, a2, d1, d2, cam[0], cam[1], ro, bo)
             total += 1
@@ -96,7 +106,7 @@ def run(ctx, port, cases=200, seed=0, verbose=False, regime="regular"):
             finite = np.isfinite(ref).all() and np.isfinite(got).all()
             same_model = bool(np.allclose(got, ref, rtol=1e-6, atol=1e-8)) if finite else bool(
                 np.array_equal(np.isnan(got), np.isnan(ref)))
-            if not (same_stats and same_mask and same_model):
+            if not (same_stats and same_mask and same_model):  # noqa: E501
                 bad.append(dict(variant=variant, n=n, opts=o, stats_gpu=(int(stats[0]["refinements"]), int(stats[0]["iterations"]),
                                                                             int(stats[0]["num_inliers"])),
                                 stats_ref=(st.refinements, st.iterations, st.num_inliers), same_mask=same_mask,
@@ -111,8 +121,26 @@ if __name__ == "__main__":
     ap.add_argument("--cases", type=int, default=400)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--regime", default="regular", choices=["regular", "all"])
+    ap.add_argument("--quiet", action="store_true")
     a = ap.parse_args()
     from oracle import port
     port.build()
-    total, bad = run(nv.Context(0), port, a.cases, a.seed, verbose=True, regime=a.regime)
+    total, bad = run(nv.Context(0), port, a.cases, a.seed, verbose=not a.quiet, regime=a.regime)
     print(f"{total} cases, {len(bad)} mismatches")
+    import collections
+    kinds = collections.Counter()
+    for b in bad:
+        if (b["stats_gpu"][2] != b["stats_ref"][2] or not b["same_mask"]) and a.quiet:
+            print(b)
+        kind = []
+        if b["stats_gpu"][1] != b["stats_ref"][1]:
+            kind.append("iterations")
+        if b["stats_gpu"][0] != b["stats_ref"][0]:
+            kind.append("refinements")
+        if b["stats_gpu"][2] != b["stats_ref"][2] or not b["same_mask"]:
+            kind.append("inliers/mask")
+        if not b["same_model"]:
+            kind.append("model")
+        kinds[(b["variant"], "+".join(kind), "early-term" if b["opts"]["min_iters"] is not None else "fixed-iters")] += 1
+    for k, v in sorted(kinds.items()):
+        print(k, v)
