@@ -396,3 +396,30 @@ def test_extra_goldens_end_to_end(ctx, extra_golden):
             assert models_close(models[0], g[key + "_model"], rtol=1e-6, atol=1e-8), key
         n += 1
     assert n == 160 and ties <= 5
+
+
+@pytest.mark.parametrize("variant", [2, 3])
+def test_no_minimal_model_found(ctx, port, variant):
+    """One iteration whose sample yields no solution: the reference refines the identity model (NaN cost under the
+    truncated loss, so the LM moves nothing), reports num_inliers of that model and leaves model_score at DBL_MAX."""
+    sc = synth.make_scene(11, 40, outlier_ratio=0.5, f1=700.0, f2=700.0 if variant == 2 else 900.0)
+    x1, x2 = sc.x1 - [640.0, 480.0], sc.x2 - [640.0, 480.0]
+    seen_empty = False
+    for seed in range(8):
+        o = _options(1, seed=seed)
+        o.bundle_max_iterations = 0
+        models, stats, masks = ctx.estimate_batch_host(variant, [0, 40], x1, x2, sc.d1, sc.d2, None, o)
+        ro = port.ransac_opt(max_iterations=1, min_iterations=1, max_epipolar_error=2.0, max_reproj_error=16.0, seed=seed)
+        m, st, mask = port.estimate(variant, x1, x2, sc.d1, sc.d2, None, None, ro,
+                                    port.bundle_opt(max_iterations=0, loss_type="TRUNCATED_CAUCHY", loss_scale=1.0))
+        assert (stats[0]["refinements"], stats[0]["iterations"], stats[0]["num_inliers"]) == \
+            (st.refinements, st.iterations, st.num_inliers), seed
+        assert np.array_equal(masks.astype(bool), mask), seed
+        if st.refinements == 1:   # nothing but the final refinement ran: no minimal model
+            seen_empty = True
+            assert stats[0]["model_score"] == DBL_MAX and st.model_score == DBL_MAX
+            assert np.array_equal(models[0]["q"], [1, 0, 0, 0]) and models[0]["scale"] == 1.0
+            assert abs(models[0]["f1"] - m.f1) <= 1e-12 * m.f1
+        else:
+            assert abs(stats[0]["model_score"] - st.model_score) <= 1e-11 * st.model_score, seed
+    assert seen_empty
