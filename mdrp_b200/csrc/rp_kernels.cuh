@@ -817,7 +817,10 @@ struct BoundArgs {
 #ifndef RP_BOUND_MIN_BLOCKS
 #define RP_BOUND_MIN_BLOCKS 2
 #endif
-constexpr int BSG = 2;                       // slices (of 32*PT points) per pass: 8 points per lane
+#ifndef RP_BOUND_BSG
+#define RP_BOUND_BSG 2
+#endif
+constexpr int BSG = RP_BOUND_BSG;            // slices (of 32*PT points) per pass: 8 points per lane (measured optimum)
 constexpr int BHW = HB / SCORE_WARPS;        // models per warp (each warp owns its models over ALL points)
 
 // Packed FP32 arithmetic of sm_100a: fma.rn.f32x2 / mul.rn.f32x2 (SASS FFMA2 / FMUL2) do two FP32
