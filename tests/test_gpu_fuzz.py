@@ -33,13 +33,13 @@ def test_randomised_parity_regular_regime(ctx, port):
                 assert b["same_model"], b
         if not b["same_model"]:
             assert b["stats_ref"][2] < 10, b
-    assert len(bad) <= 0.01 * total, bad
+    assert len(bad) <= 0.02 * total, bad   # measured 0.6 % (tools/fuzz_parity.py --cases 8000)
 
 
 def test_randomised_parity_including_undetermined_inputs(ctx, port):
     """Adds N of 3..13 and max_reproj_error = 0 (Sampson-only cost: |t|, scale and shifts are gauge directions).
     There the reference's own output is decided by exact ties / rounding noise, so only the rate is pinned."""
     total, bad = fuzz_parity.run(ctx, port, cases=1200, seed=12, regime="all")
-    assert len(bad) <= 0.04 * total, bad
+    assert len(bad) <= 0.08 * total, bad   # measured ~2-3 %
     for b in bad:
         assert b["stats_gpu"][1] == b["stats_ref"][1], b   # iterations never differ
