@@ -71,6 +71,7 @@ struct rp_ctx {
     DevBuf buf[B_NBUF];
     cudaEvent_t ev[N_EVENTS];
     double last_ms[16] = {0};
+    double prev_h2d_ms = 0.0, prev_dev_ms = 0.0;  // upload / kernel time of the previous host-path call (lead-chunk sizing)
     int64_t last_cnt[8] = {0};  // [5] models through the exact kernel, [6] point-scores the bound kernel evaluated
     size_t workspace_budget = (size_t)32 << 30;  // HBM is 180 GB: big chunks amortise kernel tails
     bool prune = true;  // hypothesis-level pruning (RP_NO_PRUNE=1 scores every minimal model exactly)
@@ -573,12 +574,19 @@ int estimate_impl(rp_ctx *ctx, int variant, int64_t n_pairs, const int64_t *offs
     std::vector<long long> rel;
     DevBuf *B = ctx->buf;
     // Chunk boundaries.  The remainder is split evenly (no tiny last chunk); on the host path a small first
-    // chunk goes ahead so that the kernels start after ~1/8 of a chunk's upload instead of a whole one — every
-    // later upload hides behind the previous chunk's kernels.
+    // chunk goes ahead so that the kernels start early and every later upload hides behind the previous
+    // chunk's kernels.  With U = upload time and C = kernel time of the whole batch, the exposed time
+    // f U + max(0, (1-f) U - f C) is smallest at f = U / (U + C); U / C is taken from the previous host call on
+    // this context (1/8 of the batch before there is one).  Only timing depends on it, never results.
     std::vector<int64_t> bounds(1, 0);
     {
         int64_t first = 0;
-        if (host_io && n_pairs >= 1024 && !getenv("RP_NO_LEAD_CHUNK")) first = std::min<int64_t>(n_pairs, std::max<int64_t>(256, chunk / 8));
+        if (host_io && n_pairs >= 1024 && !getenv("RP_NO_LEAD_CHUNK")) {
+            double f = 0.125;
+            if (ctx->prev_h2d_ms > 0.0 && ctx->prev_dev_ms > 0.0) f = ctx->prev_h2d_ms / (ctx->prev_h2d_ms + ctx->prev_dev_ms);
+            f = std::min(1.0 / 3.0, std::max(1.0 / 32.0, f));
+            first = std::min<int64_t>(std::min<int64_t>(n_pairs, chunk), std::max<int64_t>(256, (int64_t)(f * (double)n_pairs)));
+        }
         if (first > 0) bounds.push_back(first);
         const int64_t rest = n_pairs - first;
         const int64_t k = (rest + chunk - 1) / chunk;
@@ -669,6 +677,8 @@ int estimate_impl(rp_ctx *ctx, int variant, int64_t n_pairs, const int64_t *offs
     if (host_io) {
         CK(cudaEventRecord(d2h_end, cs));
         CK(cudaStreamSynchronize(cs));
+        ctx->prev_h2d_ms = ctx->last_ms[9];
+        ctx->prev_dev_ms = ctx->last_ms[8];
         for (int par = 0; par < 2 && par < n_chunks; ++par) {
             float ms = 0.f;
             if (cudaEventElapsedTime(&ms, d2h_begin[par], comp_done[par]) == cudaSuccess) ctx->last_ms[10] += ms;
