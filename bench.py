@@ -399,7 +399,7 @@ def main():
             "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roofline}
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:   # the CPU baseline is reported at N = 1 only
         cores = os.cpu_count() or 1
         n_sample = args.cpu_sample or max(64 * cores, 256)   # ~11 s of wall clock on 16 cores
         pps, cores, kind, dt = cpu_pairs_per_s(args.config, n_sample)
