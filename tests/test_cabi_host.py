@@ -45,6 +45,29 @@ def test_struct_layouts_match_header():
     assert C.sizeof(nv.BundleStats) == 56
 
 
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """sizeof / offsetof of every struct of include/repose_b200.h as gcc sees them vs the ctypes mirror."""
+    from mdrp_b200 import _native as nv
+    structs = {"rp_model": nv.Model, "rp_stats": nv.Stats, "rp_options": nv.Options,
+               "rp_bundle_options": nv.BundleOptions, "rp_bundle_stats": nv.BundleStats}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "repose_b200.h"', 'int main(void) {']
+    for cname, cls in structs.items():
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            cfield = {"lam": "lambda"}.get(fname, fname)
+            lines.append(f'printf("{cname}.{fname} %zu\\n", offsetof({cname}, {cfield}));')
+    lines += ["return 0; }"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    got = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    for cname, cls in structs.items():
+        assert int(got[cname]) == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, (cname, fname)
+
+
 def test_default_options_are_poselib_defaults(lib_path):
     from mdrp_b200 import _native as nv
     o = nv.default_options()
