@@ -49,6 +49,13 @@ def parse_args():
     return ap.parse_args()
 
 
+def bench_config(cfg_name, c, pairs, world):
+    """`config` of the JSON line: identical keys and values in both arms (ours / --impl reference)."""
+    return {"workload": workload_name(cfg_name, c, pairs), "pairs_per_gpu_per_step": pairs,
+            "l2": "inputs_larger_than_l2 (%.0f MB per step)" % (pairs * c["n"] * 48 / 1e6),
+            "parallelism": f"pairs sharded x{world}, no collective"}
+
+
 def workload_name(cfg_name, c, pairs):
     return (f"{cfg_name}: {c['variant']}{'+shift' if c['shift'] else ''}, {pairs} pairs x {c['n']} matches, "
             f"{c['iters']} RANSAC iters (min=max), {int(c['outlier_ratio'] * 100)}% outliers, "
@@ -101,56 +108,26 @@ class ClockSampler:
 
 
 # ---- CPU reference arm --------------------------------------------------------------------------------
-def cpu_pairs_per_s(cfg_name, n_sample, seed=12345):
-    """The reference's CPU path on `n_sample` pairs of the workload, all host cores (GIL released)."""
-    from concurrent.futures import ThreadPoolExecutor
-    from mdrp_b200 import synth
-    from oracle import build_ref, port, ref_wheel
-    c = synth.CONFIGS[cfg_name]
-    cores = os.cpu_count() or 1
-    batch = synth.make_batch(cfg_name, n_sample, seed=seed)
-    offs = batch["offsets"]
+def _ref_options(c):
     iters = c["iters"]
-    use_ref = build_ref.have_ref()
-    if use_ref:
-        pl = ref_wheel.poselib()
-        ro = {"max_iterations": iters, "min_iterations": iters, "max_epipolar_error": 2.0, "max_reproj_error": 16.0,
-              "seed": 0, "monodepth_estimate_shift": c["shift"]}
-        bo = {"loss_type": "TRUNCATED_CAUCHY"}
+    ro = {"max_iterations": iters, "min_iterations": iters, "max_epipolar_error": 2.0, "max_reproj_error": 16.0, "seed": 0}
+    bo = {"loss_type": "TRUNCATED_CAUCHY"}
+    if c["variant"] != "calib":
+        bo["loss_scale"] = 1.0  # the binding's default for the focal variants: 0.5 * max_epipolar_error
+    return ro, bo
 
-        def run(i):
-            sl = slice(offs[i], offs[i + 1])
-            if c["variant"] == "calib":
-                k = batch["cams"][i]
-                cam1 = {"model": "PINHOLE", "width": -1, "height": -1, "params": list(k[:4])}
-                cam2 = {"model": "PINHOLE", "width": -1, "height": -1, "params": list(k[4:])}
-                pl.estimate_monodepth_relative_pose(batch["x1"][sl], batch["x2"][sl], batch["d1"][sl], batch["d2"][sl],
-                                                    cam1, cam2, ro, bo)
-            elif c["variant"] == "shared":
-                pl.estimate_monodepth_shared_focal_relative_pose(batch["x1"][sl], batch["x2"][sl], batch["d1"][sl],
-                                                                 batch["d2"][sl], ro, bo)
-            else:
-                pl.estimate_monodepth_varying_focal_relative_pose(batch["x1"][sl], batch["x2"][sl], batch["d1"][sl],
-                                                                  batch["d2"][sl], ro, bo)
-    else:
-        port.build()
-        variant = {"calib": 1 if c["shift"] else 0, "shared": 2, "varying": 3}[c["variant"]]
-        rop = port.ransac_opt(max_iterations=iters, min_iterations=iters, max_epipolar_error=2.0, max_reproj_error=16.0,
-                              estimate_shift=c["shift"])
-        bop = port.bundle_opt(loss_type="TRUNCATED_CAUCHY")
 
-        def run(i):
-            sl = slice(offs[i], offs[i + 1])
-            k = batch["cams"][i] if batch["cams"] is not None else None
-            port.estimate(variant, batch["x1"][sl], batch["x2"][sl], batch["d1"][sl], batch["d2"][sl],
-                          None if k is None else k[:4], None if k is None else k[4:], rop, bop)
-
-    run(0)  # warm (page in the library)
-    t0 = time.perf_counter()
-    with ThreadPoolExecutor(cores) as ex:
-        list(ex.map(run, range(n_sample)))
-    dt = time.perf_counter() - t0
-    return n_sample / dt, cores, ("reference" if use_ref else "port"), dt
+def cpu_pairs_per_s(cfg_name, n_sample, seed=12345, keep=False):
+    """The reference's CPU path on `n_sample` pairs of the workload, all host cores (GIL released).
+    keep=True also returns the batch and the reference's outputs (the parity leg compares the GPU path with them)."""
+    from mdrp_b200 import synth
+    from oracle import parity
+    c = synth.CONFIGS[cfg_name]
+    batch = synth.make_batch(cfg_name, n_sample, seed=seed)
+    ro, bo = _ref_options(c)
+    ref = parity.run_reference(c["variant"], c["shift"], batch, ro, bo)
+    out = (n_sample / ref["seconds"], ref["cores"], ref["kind"], ref["seconds"])
+    return out + (batch, ref) if keep else out
 
 
 def reference_arm(args, c, rank, world):
@@ -170,7 +147,7 @@ def reference_arm(args, c, rank, world):
     line = {"impl": "reference", "metric": "image_pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * t_tot / max(args.steps, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args.config, c, args.pairs), "sample": sample},
+            "config": bench_config(args.config, c, args.pairs, args.gpus),
             "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -304,7 +281,7 @@ def main():
         for k, v in tm.items():
             stage_ms[k] = stage_ms.get(k, 0.0) + v
         for k, v in cn.items():
-            counters[k] = counters.get(k, 0) + v
+            counters[k] = v if k == "head_models" else counters.get(k, 0) + v
     e1.record(stream)
     barrier()
     elapsed = e0.elapsed_time(e1) / 1000.0
@@ -343,68 +320,88 @@ def main():
         return
 
     # ---- roofline of the dominant kernel -------------------------------------------------------------------
-    # Dominant kernel = bound_kernel (FP32 tier of the minimal-model scoring).  "achieved" follows the
-    # contract: algorithmic work = 34 FP64 flop per point-score x point-scores the launch
-    # resolves, over the kernel's own device time.  Because the kernel abandons a model as soon as it is
-    # provably irrelevant, it resolves more point-scores than it evaluates; "executed" reports what the
-    # FP32 pipe really did (41 flop per evaluated point-score: 16 FFMA + 9 FMUL/FADD/FMNMX) against the
-    # measured FP32 peak.
+    # Dominant kernel = bound_kernel (FP32 tier of the minimal-model scoring).  The headline figure is what the
+    # FP32 pipe really executed: point-scores evaluated (device counter) x 41 FP32 flop (16 FFMA + 9
+    # FMUL/FADD/FMNMX per evaluated point-score) over the kernel's own CUDA-event time, against the FP32 FMA
+    # peak measured on this device (rp_measure_pipes; MEASURED_PEAKS.json has no FP32/FP64 figure).
+    # "algorithmic" restates it in the SURVEY §8d convention (34 FP64 flop per point-score the reference would
+    # have computed, resolved or evaluated) — it can exceed 1 because the kernel abandons models early.
     bound_s = stage_ms["bound_kernel"] / 1000.0
     score_s = stage_ms["score_minimal"] / 1000.0
+    dev_s = stage_ms["device_total"] / 1000.0
     ps = counters["point_scores"]
     hyps = counters["hypotheses"]
     n_chunk_launches = max(1, int(counters["chunks"]))
     head = int(counters.get("head_models", 0)) or 128
     ps_bound = ps - min(ps, P * args.steps * head * c["n"])  # the first `head` models per pair go to the exact kernel
-    achieved_tf = FLOPS_PER_POINT_SCORE * ps_bound / bound_s / 1e12 if bound_s > 0 else None
     evaluated = counters["bound_evaluated"]
     executed_tf = 41.0 * evaluated / bound_s / 1e12 if bound_s > 0 else None
-    alg_bytes = args.steps * N * 32 + hyps * (96 + 12)  # points once per pair; model in, bounds out per hypothesis
-    roofline = {"kernel": "bound_kernel<pose> (FP32 tier over all minimal models; 34 FP64 flop/point-score algorithmic)",
-                "bound": "fp64_pipe", "achieved": achieved_tf, "peak": fp64_tf, "unit": "TFLOP/s",
-                "frac": achieved_tf / fp64_tf if (fp64_tf and achieved_tf) else None,
-                "peak_source": "rp_measure_pipes on this device (FP64 FMA chain; MEASURED_PEAKS.json has no FP64 figure)",
+    algorithmic_tf = FLOPS_PER_POINT_SCORE * ps_bound / bound_s / 1e12 if bound_s > 0 else None
+    alg_bytes = args.steps * N * 16 + hyps * (96 + 8)  # FP32 points once per pair; model in, (ub, lb) out per hypothesis
+    roofline = {"kernel": "bound_kernel (FP32 outlier-count / score-bound tier over the minimal models)",
+                "bound": "fp32_pipe", "achieved": executed_tf, "peak": fp32_tf, "unit": "TFLOP/s",
+                "frac": executed_tf / fp32_tf if (fp32_tf and executed_tf) else None,
+                "peak_source": "rp_measure_pipes on this device (FP32 FMA chains; MEASURED_PEAKS.json has no FP32 figure)",
+                "work": "evaluated point-scores (device counter) x 41 FP32 flop",
                 "traffic": _ncu_traffic("bound", P * args.steps / n_chunk_launches),
-                "executed": {"pipe": "fp32", "tflops": executed_tf, "peak_tflops": fp32_tf,
-                             "frac": executed_tf / fp32_tf if (fp32_tf and executed_tf) else None,
-                             "point_scores_evaluated_per_s": evaluated / bound_s if bound_s > 0 else None,
-                             "evaluated_fraction": evaluated / max(ps_bound, 1)},
-                "point_scores_resolved_per_s": ps_bound / bound_s if bound_s > 0 else None,
-                "flops_per_point_score": FLOPS_PER_POINT_SCORE,
+                "point_scores_evaluated_per_s": evaluated / bound_s if bound_s > 0 else None,
+                "evaluated_fraction": evaluated / max(ps_bound, 1),
                 "launches": n_chunk_launches, "ms_per_launch": 1000.0 * bound_s / n_chunk_launches,
-                "share_of_step": bound_s / (stage_ms["device_total"] / 1000.0),
-                "score_stage_share_of_step": score_s / (stage_ms["device_total"] / 1000.0),
+                "share_of_step": bound_s / dev_s,
+                "score_stage_share_of_step": score_s / dev_s,
                 "exact_models_fraction": counters["exact_models"] / max(hyps, 1),
-                "hbm_algorithmic_gbs": alg_bytes / bound_s / 1e9 if bound_s > 0 else None}
+                "algorithmic": {"note": "SURVEY 8d convention: 34 FP64 flop per point-score resolved, vs the measured FP64 FMA peak; "
+                                        "> 1 is possible because abandoned point-scores are never evaluated",
+                                "tflops": algorithmic_tf, "peak_tflops": fp64_tf,
+                                "frac": algorithmic_tf / fp64_tf if (fp64_tf and algorithmic_tf) else None,
+                                "point_scores_resolved_per_s": ps_bound / bound_s if bound_s > 0 else None}}
     # the same kernel against the HBM roof, to show which roof binds: algorithmic bytes over the kernel's time
-    # vs the measured copy bandwidth of MEASURED_PEAKS.json (fallback: the profiling guide's 6 500 GB/s)
-    hbm_peak, hbm_src = 6500.0, "fallback of B200_PROFILING.md"
+    # vs the measured copy bandwidth of MEASURED_PEAKS.json (fallback: the profiling guide's 6 650 GB/s)
+    hbm_peak, hbm_src = 6650.0, "fallback of B200_PROFILING.md"
     try:
         hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
         hbm_src = "MEASURED_PEAKS.json hbm_gbs"
     except Exception:
         pass
-    if roofline["hbm_algorithmic_gbs"]:
-        roofline["hbm"] = {"bound": "hbm", "achieved": roofline["hbm_algorithmic_gbs"], "peak": hbm_peak, "unit": "GB/s",
-                           "frac": roofline["hbm_algorithmic_gbs"] / hbm_peak, "peak_source": hbm_src,
+    if bound_s > 0:
+        roofline["hbm"] = {"bound": "hbm", "achieved": alg_bytes / bound_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                           "frac": alg_bytes / bound_s / 1e9 / hbm_peak, "peak_source": hbm_src,
                            "note": "arithmetic intensity ~5e2 flop/B: the pipe roof above binds, not this one"}
+    # second entry: the LM kernel (LO + final refinement), FP64 pipe
+    lm_s = (stage_ms["lo_refine"] + stage_ms["final_refine"]) / 1000.0
+    lm_flops = counters.get("lm_flops", 0)
+    roofline_lm = None
+    if lm_flops and lm_s > 0:
+        roofline_lm = {"kernel": "lm_kernel (LO refinement of every trigger + final LO + final refinement)",
+                       "bound": "fp64_pipe", "achieved": lm_flops / lm_s / 1e12, "peak": fp64_tf, "unit": "TFLOP/s",
+                       "frac": lm_flops / lm_s / 1e12 / fp64_tf if fp64_tf else None,
+                       "work": "device counters: residual rows evaluated / accumulated x the per-row FP64 flop counts of DESIGN.md §5",
+                       "share_of_step": lm_s / dev_s, "lm_iterations": counters["lm_iterations"],
+                       "lm_problems": counters["lm_problems"]}
 
     line = {"metric": "image_pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000.0 * elapsed_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args.config, c, P), "pairs_per_gpu_per_step": P,
-                       "l2": "inputs_larger_than_l2 (%.0f MB per step)" % (N * 48 / 1e6), "parallelism": f"pairs sharded x{world}, no collective"},
+            "config": bench_config(args.config, c, P, world),
             "secondary": {"hypothesis_scores_per_sec": world * hyps / elapsed_max, "point_scores_per_sec": world * ps / elapsed_max,
                           "models_per_iteration": hyps / (args.steps * P * c["iters"])},
             "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roofline}
+    if roofline_lm:
+        line["roofline_lm"] = roofline_lm
     if not args.no_cpu_baseline and world == 1:   # the CPU baseline is reported at N = 1 only
         cores = os.cpu_count() or 1
         n_sample = args.cpu_sample or max(64 * cores, 256)   # ~11 s of wall clock on 16 cores
-        pps, cores, kind, dt = cpu_pairs_per_s(args.config, n_sample)
+        pps, cores, kind, dt, cb, ref = cpu_pairs_per_s(args.config, n_sample, keep=True)
         line["cpu_baseline"] = {"value": pps, "unit": "pairs/s", "cores": cores, "kind": kind,
                                 "sample": f"{n_sample} pairs of the workload, per-pair calls from a {cores}-thread pool, {dt:.1f} s"}
+        # parity on the timed workload: the same sample through the GPU path (host entry point), compared with
+        # what the reference just returned for it (oracle/parity.py; untimed)
+        from oracle import parity
+        gm, gs, gk = ctx.estimate_batch_host(variant, cb["offsets"], cb["x1"], cb["x2"], cb["d1"], cb["d2"], cb["cams"], opt)
+        rec, _ = parity.compare(ref, cb["offsets"], gm, gs, gk)
+        line["parity"] = rec
     _emit(line)
     if world > 1:
         dist.destroy_process_group()

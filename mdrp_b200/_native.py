@@ -5,6 +5,7 @@ missing or no CUDA device is present, every entry point raises.
 """
 import ctypes as C
 import os
+import threading
 
 import numpy as np
 
@@ -151,6 +152,10 @@ class Context:
                               f"{self._lib.rp_last_error(None).decode()}")
         self._h = h
         self.device = device
+        # One rp_ctx owns one device workspace, its events and work counters, and ctypes releases the GIL
+        # during a native call: calls on the SAME context from several Python threads are serialised here
+        # (the reference binding is re-entrant; INTEGRATION.md: one rp_ctx per concurrently calling thread).
+        self._lock = threading.RLock()
 
     def close(self):
         if getattr(self, "_h", None):
@@ -167,6 +172,11 @@ class Context:
         if rc != 0:
             raise NativeError(f"librepose_b200 error {rc}: {self._lib.rp_last_error(self._h).decode()}")
 
+    def _call(self, fn, *args):
+        """One native call on this context: serialised per context, error code turned into NativeError."""
+        with self._lock:
+            self._check(fn(*args))
+
     @property
     def launch_count(self) -> int:
         return int(self._lib.rp_launch_count(self._h))
@@ -174,12 +184,12 @@ class Context:
     def last_timing(self):
         ms = (C.c_double * 16)()
         cn = (C.c_int64 * 8)()
-        self._check(self._lib.rp_last_timing(self._h, ms, cn))
+        self._call(self._lib.rp_last_timing, self._h, ms, cn)
         return dict(zip(TIMING_KEYS, list(ms))), dict(zip(COUNTER_KEYS, list(cn)))
 
     def measure_pipes(self):
         a, b = C.c_double(0), C.c_double(0)
-        self._check(self._lib.rp_measure_pipes(self._h, C.byref(a), C.byref(b)))
+        self._call(self._lib.rp_measure_pipes, self._h, C.byref(a), C.byref(b))
         return a.value, b.value
 
     # ---- hot path -------------------------------------------------------------------------
@@ -197,26 +207,26 @@ class Context:
         models = np.zeros(n_pairs, dtype=MODEL_DTYPE)
         stats = np.zeros(n_pairs, dtype=STATS_DTYPE)
         masks = np.zeros(max(ntot, 1), dtype=np.uint8)
-        self._check(self._lib.rp_estimate_batch_host(
+        self._call(self._lib.rp_estimate_batch_host,
             self._h, int(variant), n_pairs, _ptr(offsets), _ptr(x1), _ptr(x2), _ptr(d1), _ptr(d2),
-            _ptr(cams), C.byref(opt), _ptr(models), _ptr(stats), _ptr(masks)))
+            _ptr(cams), C.byref(opt), _ptr(models), _ptr(stats), _ptr(masks))
         return models, stats, masks[:ntot]
 
     def estimate_batch_dev(self, variant, offsets, x1_ptr, x2_ptr, d1_ptr, d2_ptr, cams_ptr, opt: Options,
                            models_ptr, stats_ptr, masks_ptr, stream=0):
         """Raw device pointers (e.g. torch tensor .data_ptr()); offsets is a host int64 array."""
         offsets = np.ascontiguousarray(offsets, dtype=np.int64)
-        self._check(self._lib.rp_estimate_batch_dev(
+        self._call(self._lib.rp_estimate_batch_dev,
             self._h, int(variant), len(offsets) - 1, _ptr(offsets), x1_ptr, x2_ptr, d1_ptr, d2_ptr,
-            cams_ptr, C.byref(opt), models_ptr, stats_ptr, masks_ptr, stream or None))
+            cams_ptr, C.byref(opt), models_ptr, stats_ptr, masks_ptr, stream or None)
 
     # ---- stage entry points -----------------------------------------------------------------
     def sample(self, n, seed, iters, progressive_sampling=False, max_prosac_iterations=100000):
         out = np.zeros((iters, 3), dtype=np.int32)
         if progressive_sampling:
-            self._check(self._lib.rp_sample_batch_prosac(self._h, n, seed, iters, 1, max_prosac_iterations, _ptr(out)))
+            self._call(self._lib.rp_sample_batch_prosac, self._h, n, seed, iters, 1, max_prosac_iterations, _ptr(out))
         else:
-            self._check(self._lib.rp_sample_batch(self._h, n, seed, iters, _ptr(out)))
+            self._call(self._lib.rp_sample_batch, self._h, n, seed, iters, _ptr(out))
         return out
 
     def solve(self, variant, x1h, x2h, d1, d2):
@@ -224,8 +234,8 @@ class Context:
         n = x1h.shape[0]
         models = np.zeros((n, 4), dtype=MODEL_DTYPE)
         counts = np.zeros(n, dtype=np.int32)
-        self._check(self._lib.rp_solve_batch(self._h, int(variant), n, _ptr(x1h), _ptr(x2h), _ptr(d1),
-                                             _ptr(d2), _ptr(models), _ptr(counts)))
+        self._call(self._lib.rp_solve_batch, self._h, int(variant), n, _ptr(x1h), _ptr(x2h), _ptr(d1),
+                                             _ptr(d2), _ptr(models), _ptr(counts))
         return models, counts
 
     def score(self, variant, models, x1, x2, sq_thr, want_masks=False):
@@ -235,8 +245,8 @@ class Context:
         scores = np.zeros(n)
         counts = np.zeros(n, dtype=np.int64)
         masks = np.zeros((n, npts), dtype=np.uint8) if want_masks else None
-        self._check(self._lib.rp_score_batch(self._h, int(variant), n, _ptr(models), npts, _ptr(x1), _ptr(x2),
-                                             float(sq_thr), _ptr(scores), _ptr(counts), _ptr(masks)))
+        self._call(self._lib.rp_score_batch, self._h, int(variant), n, _ptr(models), npts, _ptr(x1), _ptr(x2),
+                                             float(sq_thr), _ptr(scores), _ptr(counts), _ptr(masks))
         return (scores, counts, masks) if want_masks else (scores, counts)
 
     def refine(self, variant, models, x1, x2, d1, d2, scale_reproj, weight_sampson, bopt: BundleOptions,
@@ -245,9 +255,9 @@ class Context:
         x1, x2, d1, d2 = _f64(x1), _f64(x2), _f64(d1), _f64(d2)
         mk = np.ascontiguousarray(mask, dtype=np.uint8) if mask is not None else None
         stats = np.zeros(len(models), dtype=BSTATS_DTYPE)
-        self._check(self._lib.rp_refine_batch(self._h, int(variant), len(models), _ptr(models), len(x1), _ptr(x1),
+        self._call(self._lib.rp_refine_batch, self._h, int(variant), len(models), _ptr(models), len(x1), _ptr(x1),
                                               _ptr(x2), _ptr(d1), _ptr(d2), _ptr(mk), float(scale_reproj),
-                                              float(weight_sampson), C.byref(bopt), _ptr(stats)))
+                                              float(weight_sampson), C.byref(bopt), _ptr(stats))
         return models, stats
 
 

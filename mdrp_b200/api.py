@@ -150,10 +150,15 @@ def make_options(ransac_opt=None, bundle_opt=None, focal_variant=False) -> nv.Op
     o.weight_sampson = float(np.float32(ransac_opt.get("monodepth_weight_sampson", 1.0)))
     if "max_iterations" in bundle_opt:
         o.bundle_max_iterations = int(bundle_opt["max_iterations"])
+    # the binding matches the loss name case-insensitively and keeps its default (CAUCHY) for a name it
+    # does not know (verified on the wheel: 'cauchy' == 'CAUCHY', 'bogus' -> CAUCHY)
     lt = bundle_opt.get("loss_type", "CAUCHY")
-    if lt == "TRUNCATED_LE_ZACH":
-        raise NotImplementedError("TRUNCATED_LE_ZACH loss is outside this build")
-    o.loss_type = nv.LOSS.get(lt, nv.LOSS["TRIVIAL"]) if isinstance(lt, str) else int(lt)
+    if isinstance(lt, str):
+        if lt.upper() == "TRUNCATED_LE_ZACH":
+            raise NotImplementedError("TRUNCATED_LE_ZACH loss is outside this build")
+        o.loss_type = nv.LOSS.get(lt.upper(), nv.LOSS["CAUCHY"])
+    else:
+        o.loss_type = int(lt)
     # focal variants honour the user's loss_scale (default 0.5*max_epipolar_error); the calibrated
     # variant overwrites it with half the normalised threshold (SURVEY.md §8b "Errors")
     o.loss_scale = float(bundle_opt.get("loss_scale", 0.5 * o.max_epipolar_error if focal_variant else 1.0))

@@ -130,6 +130,29 @@ def pose_maa(pose_errs, max_deg=10):
     return float(np.mean([np.sum(e < t) / len(e) for t in range(1, max_deg + 1)]))
 
 
+# Experiment strings of eval.py:93-129 this build can run: the monodepth estimators with the hybrid
+# (Sampson + reprojection) LO.  Everything that would silently run as something else is refused:
+#   nLO (no local optimisation), GLO (graduated LO), reproj / sym_reproj (non-hybrid cost), reldepth,
+#   mad_poselib / madpose, 5p (no depth at all), noshift.
+_UNSUPPORTED = ("nLO", "GLO", "sym_reproj", "reldepth", "mad_poselib", "madpose", "5p", "noshift")
+
+
+def check_experiment(experiment: str) -> None:
+    """Raises ValueError for an experiment string outside SURVEY.md §8f row 1 (the fork keys that
+    api.make_options would ignore would otherwise report numbers under the wrong name)."""
+    name = experiment.split("+")[0]
+    bad = [k for k in _UNSUPPORTED if k in name]
+    if "reproj" in name and "hybrid" not in name:
+        bad.append("reproj (without hybrid)")
+    if "hybrid" not in name:
+        bad.append("no 'hybrid' LO cost")
+    if not ("p3p" in name or "ours" in name):
+        bad.append("neither p3p nor ours")
+    if bad:
+        raise ValueError(f"experiment {experiment!r} is outside this build ({', '.join(bad)}); supported: "
+                         "p3p_hybrid_*, 3p_ours_scale_hybrid_*, 3p_ours_shift_scale_hybrid-s_* [+depth]")
+
+
 def evaluate(h5, experiment, iterations=1000, threshold=2.0, reproj_threshold=16.0, first=None, device=0):
     """One experiment string of eval.py:93-160 over a whole benchmark file in ONE batched call.
 
@@ -137,6 +160,7 @@ def evaluate(h5, experiment, iterations=1000, threshold=2.0, reproj_threshold=16
     `3p_ours_scale_hybrid_ctruncated+k`, `3p_ours_shift_scale_hybrid-s_ctruncated+k`); `+k` selects the depth source.
     Returns {"median", "mAA", "errs", "inlier_ratio", "stats"}."""
     from . import api
+    check_experiment(experiment)
     depth = int(experiment.split("+")[1]) if "+" in experiment else None
     lo_iterations = 0 if "nLO" in experiment else 25
     ransac = {"max_iterations": iterations, "min_iterations": iterations, "max_epipolar_error": threshold,

@@ -36,10 +36,9 @@ def gather_depths(depth_map1, depth_map2, keypoints1, keypoints2):
     d2 = torch.empty(n, dtype=torch.float64, device=dev)
     n_out = C.c_int64(0)
     stream = torch.cuda.current_stream(dev).cuda_stream
-    ctx._check(ctx._lib.rp_gather_depths_dev(ctx._h, dm1.data_ptr(), dm1.shape[0], dm1.shape[1], dm2.data_ptr(),
-                                             dm2.shape[0], dm2.shape[1], k1.data_ptr(), k2.data_ptr(), n,
-                                             x1.data_ptr(), x2.data_ptr(), d1.data_ptr(), d2.data_ptr(),
-                                             C.byref(n_out), stream))
+    ctx._call(ctx._lib.rp_gather_depths_dev, ctx._h, dm1.data_ptr(), dm1.shape[0], dm1.shape[1], dm2.data_ptr(),
+              dm2.shape[0], dm2.shape[1], k1.data_ptr(), k2.data_ptr(), n, x1.data_ptr(), x2.data_ptr(),
+              d1.data_ptr(), d2.data_ptr(), C.byref(n_out), stream)
     m = n_out.value
     return x1[:m], x2[:m], d1[:m], d2[:m]
 

@@ -83,3 +83,14 @@ def test_evaluate_equals_per_pair_calls(ctx):
                                                              {"loss_type": "TRUNCATED_CAUCHY", "max_iterations": 100})
         e1 = max(br.rotation_error_deg(pose.R, p.R_gt), br.translation_error_deg(pose.t, p.t_gt))
         assert abs(e1 - e) < 1e-9
+
+
+def test_unsupported_experiment_strings_are_refused():
+    """eval.py:93-129 knows many more experiments than this build runs; none may run under a wrong name."""
+    from mdrp_b200 import benchmark_reader as br
+    for ok in ("p3p_hybrid_ctruncated+3", "3p_ours_scale_hybrid_ctruncated", "3p_ours_shift_scale_hybrid-s_ctruncated+11"):
+        br.check_experiment(ok)
+    for bad in ("p3p_nLO_hybrid_ctruncated", "3p_ours_scale_GLO_hybrid", "3p_ours_scale_reproj_ctruncated", "5p_ctruncated",
+                "madpose+3", "mad_poselib_shift_scale_hybrid", "3p_reldepth_hybrid", "3p_ours_scale_sym_reproj"):
+        with pytest.raises(ValueError):
+            br.check_experiment(bad)

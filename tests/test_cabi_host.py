@@ -108,6 +108,13 @@ def test_option_dict_mapping(lib_path):
     p = api.make_options({"progressive_sampling": True, "max_prosac_iterations": 5000}, {})
     assert (p.progressive_sampling, p.max_prosac_iterations) == (1, 5000)
     assert api.make_options({"progressive_sampling": False}, {}).progressive_sampling == 0
+    # loss names: case-insensitive, an unknown name keeps the binding's default CAUCHY (checked against the wheel in
+    # test_loss_name_parsing_matches_reference below)
+    assert api.make_options({}, {"loss_type": "truncated_cauchy"}).loss_type == nv.LOSS["TRUNCATED_CAUCHY"]
+    assert api.make_options({}, {"loss_type": "bogus"}).loss_type == nv.LOSS["CAUCHY"]
+    assert api.make_options({}, {}).loss_type == nv.LOSS["CAUCHY"]
+    with pytest.raises(NotImplementedError):
+        api.make_options({}, {"loss_type": "truncated_le_zach"})
     # fork flags of eval.py:105-123
     r = api._fork_ransac({"use_ours": True, "solver_shift": True, "use_p3p": False, "weight_sampson": 1.0})
     assert r["monodepth_estimate_shift"] is True
@@ -135,3 +142,44 @@ def test_argument_errors():
     off, x1, x2, d1, d2 = api._pack([np.zeros((4, 2), dtype=np.float32), np.zeros((0, 2))],
                                     [np.zeros((4, 2)), np.zeros((0, 2))], [[1, 2, 3, 4], []], [np.ones(4), np.ones(0)])
     assert off.tolist() == [0, 4, 4] and x1.dtype == np.float64 and d1.tolist() == [1, 2, 3, 4]
+
+
+def test_loss_name_parsing_matches_reference(ref, port):
+    """The wheel parses bundle_opt['loss_type'] case-insensitively and falls back to CAUCHY for unknown names:
+    its result for 'cauchy' / 'bogus' equals its result for 'CAUCHY', and differs from 'TRIVIAL'."""
+    from mdrp_b200 import synth
+    pl = ref.poselib()
+    sc = synth.scene_for("cfg1_calib_scale", 3, n=200)
+    c1, c2 = sc.camera_dicts()
+    ro = {"max_iterations": 100, "min_iterations": 100, "max_epipolar_error": 2.0, "max_reproj_error": 16.0}
+
+    def run(name):
+        g, _ = pl.estimate_monodepth_relative_pose(sc.x1, sc.x2, sc.d1, sc.d2, c1, c2, ro, {"loss_type": name})
+        return np.r_[np.array(g.pose.q), np.array(g.pose.t), g.scale]
+    base = run("CAUCHY")
+    assert np.array_equal(run("cauchy"), base) and np.array_equal(run("bogus"), base)
+    assert not np.array_equal(run("TRIVIAL"), base)
+    assert np.array_equal(run("truncated_cauchy"), run("TRUNCATED_CAUCHY"))
+
+
+def test_context_serialises_concurrent_calls():
+    """nv.Context owns one device workspace: its native calls go through one lock."""
+    import threading
+    from mdrp_b200 import _native as nv
+    c = nv.Context.__new__(nv.Context)
+    c._lock = threading.RLock()
+    c._lib = None
+    c._h = None
+    inside, seen = [0], []
+
+    def fake(*a):
+        inside[0] += 1
+        seen.append(inside[0])
+        import time
+        time.sleep(0.01)
+        inside[0] -= 1
+        return 0
+    ts = [threading.Thread(target=lambda: c._call(fake, 1)) for _ in range(6)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert seen == [1] * 6
