@@ -180,15 +180,24 @@ RP_API int rp_gather_depths_dev(rp_ctx *ctx, const float *depth1, int h1, int w1
  * this device, in TFLOP/s (2 flops per FMA). */
 RP_API int rp_measure_pipes(rp_ctx *ctx, double *fp64_tflops, double *fp32_tflops);
 
+/* Stage entry point of the tensor-core tier (mdrp_b200/csrc/rp_tc.cuh; no counterpart in the reference: it only decides
+ * which minimal models compute_sampson_msac_score so@0x4f61d0 / so@0x4f65d0 has to see at all).  For every model:
+ * the number of correspondences that are CERTAIN outliers of the Sampson test r2 < sq_threshold, a rigorous lower
+ * bound of N - inlier_count (== N for a model with a non-finite E / F).  x1 / x2 as in rp_score_batch; at most 4096
+ * models per call. */
+RP_API int rp_tc_count_batch(rp_ctx *ctx, int variant, int64_t n_models, const rp_model *models, int64_t n_points,
+                             const double *x1, const double *x2, double sq_threshold, int64_t *certain_outliers);
+
 /* per-stage device time of the last rp_estimate_batch_* call on ctx, milliseconds (summed over chunks):
  * [0] prepare, [1] sample, [2] solve, [3] score(minimal: exact head + bound + prune + exact survivors),
  * [4] scan, [5] LO refine, [6] LO score+merge+final LO, [7] final refine, [8] total device, [9] H2D,
- * [10] D2H, [11] bound kernel alone, [12..15] reserved.
- * counters: [0] minimal models generated, [1] point-scores resolved (models x correspondences),
+ * [10] D2H, [11] FP32 bound kernel alone, [12] tensor-core count tier alone, [13..15] reserved.
+ * counters: [0] minimal models generated, [1] point-scores the FP32 bound kernel resolved (models x correspondences),
  * [2] LM problems, [3] LM iterations, [4] chunks (= launches of each pipeline kernel), [5] minimal models
- * that needed the exact scorer, [6] point-scores the bound kernel actually evaluated (before abandoning),
- * [7] reserved */
-RP_API int rp_last_timing(const rp_ctx *ctx, double *ms16, int64_t *counters8);
+ * that needed the exact scorer, [6] point-scores the FP32 bound kernel actually evaluated (before abandoning),
+ * [7] exact head size, [8] point-scores the tensor-core tier evaluated, [9] minimal models that tier passed on to the
+ * FP32 bound kernel, [10] FP64 flops of the LM kernels (device counter), [11..15] reserved */
+RP_API int rp_last_timing(const rp_ctx *ctx, double *ms16, int64_t *counters16);
 
 #ifdef __cplusplus
 }

@@ -19,7 +19,7 @@ LOSS = {"TRIVIAL": 0, "TRUNCATED": 1, "HUBER": 2, "CAUCHY": 3, "TRUNCATED_CAUCHY
 EXPORTS = [
     "rp_create", "rp_destroy", "rp_last_error", "rp_default_options", "rp_launch_count",
     "rp_estimate_batch_host", "rp_estimate_batch_dev", "rp_sample_batch", "rp_sample_batch_prosac", "rp_solve_batch",
-    "rp_score_batch", "rp_refine_batch", "rp_measure_pipes", "rp_last_timing", "rp_gather_depths_dev",
+    "rp_score_batch", "rp_refine_batch", "rp_measure_pipes", "rp_last_timing", "rp_gather_depths_dev", "rp_tc_count_batch",
 ]
 
 
@@ -106,6 +106,8 @@ def load():
     L.rp_solve_batch.argtypes = [VP, C.c_int, C.c_int64, VP, VP, VP, VP, VP, VP]
     L.rp_score_batch.restype = C.c_int
     L.rp_score_batch.argtypes = [VP, C.c_int, C.c_int64, VP, C.c_int64, VP, VP, C.c_double, VP, VP, VP]
+    L.rp_tc_count_batch.restype = C.c_int
+    L.rp_tc_count_batch.argtypes = [VP, C.c_int, C.c_int64, VP, C.c_int64, VP, VP, C.c_double, VP]
     L.rp_refine_batch.restype = C.c_int
     L.rp_refine_batch.argtypes = [VP, C.c_int, C.c_int64, VP, C.c_int64, VP, VP, VP, VP, VP, C.c_double,
                                   C.c_double, C.POINTER(BundleOptions), VP]
@@ -135,9 +137,9 @@ def _ptr(a):
 
 
 TIMING_KEYS = ["prepare", "sample", "solve", "score_minimal", "scan", "lo_refine", "lo_score_merge",
-               "final_refine", "device_total", "h2d", "d2h", "bound_kernel", "r12", "r13", "r14", "r15"]
+               "final_refine", "device_total", "h2d", "d2h", "bound_kernel", "tc_kernel", "r13", "r14", "r15"]
 COUNTER_KEYS = ["hypotheses", "point_scores", "lm_problems", "lm_iterations", "chunks", "exact_models",
-                "bound_evaluated", "head_models"]
+                "bound_evaluated", "head_models", "tc_evaluated", "tc_selected", "lm_flops", "c11", "c12", "c13", "c14", "c15"]
 
 
 class Context:
@@ -183,7 +185,7 @@ class Context:
 
     def last_timing(self):
         ms = (C.c_double * 16)()
-        cn = (C.c_int64 * 8)()
+        cn = (C.c_int64 * 16)()
         self._call(self._lib.rp_last_timing, self._h, ms, cn)
         return dict(zip(TIMING_KEYS, list(ms))), dict(zip(COUNTER_KEYS, list(cn)))
 
@@ -248,6 +250,15 @@ class Context:
         self._call(self._lib.rp_score_batch, self._h, int(variant), n, _ptr(models), npts, _ptr(x1), _ptr(x2),
                                              float(sq_thr), _ptr(scores), _ptr(counts), _ptr(masks))
         return (scores, counts, masks) if want_masks else (scores, counts)
+
+    def tc_count(self, variant, models, x1, x2, sq_thr):
+        """Certain-outlier counts of the tensor-core tier (rp_tc_count_batch)."""
+        models = np.ascontiguousarray(models, dtype=MODEL_DTYPE)
+        x1, x2 = _f64(x1), _f64(x2)
+        out = np.zeros(len(models), dtype=np.int64)
+        self._call(self._lib.rp_tc_count_batch, self._h, int(variant), len(models), _ptr(models), len(x1), _ptr(x1), _ptr(x2),
+                   float(sq_thr), _ptr(out))
+        return out
 
     def refine(self, variant, models, x1, x2, d1, d2, scale_reproj, weight_sampson, bopt: BundleOptions,
                mask=None):

@@ -3,6 +3,7 @@
 // chunks, owns the HBM workspace and replays the reference's call order:
 //   estimate_* (so@0x224170 / 0x223300 / 0x223a40) -> ransac_* -> ransac<> -> final refinement.
 // There is no host fallback: without a CUDA device rp_create fails.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cstdio>
@@ -47,7 +48,9 @@ enum { B_OFFS, B_PAIRS, B_PTS64, B_PTS32, B_BEAR, B_SAMPLES, B_MODELS, B_HYPITER
        B_PTS32P, B_UB, B_LB, B_FIRSTCNT, B_FIRSTPFX, B_B0, B_S0, B_SURVLIST, B_SURVCNT, B_SURVPFX, B_WAVECUR, B_WAVECNT,
        B_MASK, B_IN_X1, B_IN_X2, B_IN_D1, B_IN_D2, B_IN_CAMS, B_TMP0, B_TMP1, B_TMP2,
        // second staging set (double buffering of the host path)
-       B_MASK_B, B_IN_X1_B, B_IN_X2_B, B_IN_D1_B, B_IN_D2_B, B_IN_CAMS_B, B_TMP0_B, B_TMP1_B, B_NBUF };
+       B_MASK_B, B_IN_X1_B, B_IN_X2_B, B_IN_D1_B, B_IN_D2_B, B_IN_CAMS_B, B_TMP0_B, B_TMP1_B,
+       // tensor-core tier: per-point feature rows, per-model outlier counts, survivor lists
+       B_FEAT, B_TCOUT, B_TCLIST, B_TCLISTCNT, B_TCLISTPFX, B_PAIRCNT, B_TCPFX, B_NBUF };
 
 // device scalars living in B_SCALARS
 struct Scalars {
@@ -55,9 +58,11 @@ struct Scalars {
     int n_surv_items, bound_work, lm_work, score_work;  // *_work: counters the persistent kernels draw work from
     unsigned long long point_scores, lm_iters, n_survivors, evaluated_ps;
     long long n_hyp;
+    int n_tc_items, n_tcsel_items;
+    unsigned long long tc_evaluated, tc_selected, lm_flops;
 };
 
-constexpr int N_EVENTS = 24;
+constexpr int N_EVENTS = 26;
 
 }  // namespace
 
@@ -72,11 +77,13 @@ struct rp_ctx {
     cudaEvent_t ev[N_EVENTS];
     double last_ms[16] = {0};
     double prev_h2d_ms = 0.0, prev_dev_ms = 0.0;  // upload / kernel time of the previous host-path call (lead-chunk sizing)
-    int64_t last_cnt[8] = {0};  // [5] models through the exact kernel, [6] point-scores the bound kernel evaluated
+    int64_t last_cnt[16] = {0};  // [5] models through the exact kernel, [6] point-scores the bound kernel evaluated
     size_t workspace_budget = (size_t)32 << 30;  // HBM is 180 GB: big chunks amortise kernel tails
     bool prune = true;  // hypothesis-level pruning (RP_NO_PRUNE=1 scores every minimal model exactly)
     int head = HB;      // models per pair scored exactly before the bound kernel (RP_HEAD=32|64|96|128; measured: 128 best on cfg2/cfg4, 64 marginally better on the 1000-iteration configs)
     bool waves = true;  // survivors of the prune scored in waves (RP_NO_WAVES=1: all at once)
+    bool tc = true;     // tensor-core count tier in front of the FP32 bound kernel (RP_NO_TC=1: off)
+    void *encode_tiled = nullptr;  // cuTensorMapEncodeTiled (driver entry point, resolved at rp_create)
     int occ_score[4] = {0}, occ_lm[4] = {0};
 };
 
@@ -105,6 +112,30 @@ inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 int fail(rp_ctx *ctx, int code, const char *msg) {
     if (ctx) ctx->err = msg;
     return code;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// tensor-core count tier over every minimal model of the chunk (rp_tc.cuh): feature rows [n_rows x 32 floats] through a
+// SWIZZLE_128B tensor map, 64 rows per TMA box
+int launch_tc(rp_ctx *ctx, const tc::TcArgs &a, float4 *feat, long long n_rows, cudaStream_t st) {
+    CUtensorMap tmap;
+    const cuuint64_t gdim[2] = {(cuuint64_t)tc::FEAT, (cuuint64_t)std::max<long long>(n_rows, 1)};
+    const cuuint64_t gstride[1] = {(cuuint64_t)tc::FEAT * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)tc::FEAT, (cuuint32_t)tc::NT};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult cr = ((EncodeTiledFn)ctx->encode_tiled)(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, feat, gdim, gstride, box, estr,
+                                                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+        ctx->err = "cuTensorMapEncodeTiled failed (" + std::to_string((int)cr) + ")";
+        return RP_ERR_CUDA;
+    }
+    tc::tc_count_kernel<0><<<ctx->sms, tc::THREADS, tc::SMEM_BYTES, st>>>(tmap, a);
+    LAUNCHED();
+    return RP_OK;
 }
 
 template <class K>
@@ -273,6 +304,16 @@ int run_chunk(rp_ctx *ctx, int variant, const rp_options &opt, const ChunkIO &io
         CK(B[B_WAVECUR].reserve(sizeof(int) * P)); CK(B[B_WAVECNT].reserve(sizeof(int) * P));
         CK(B[B_SURVPFX].reserve(sizeof(int) * (P + 1)));
     }
+    const bool use_tc = ctx->prune && ctx->tc;
+    if (use_tc) {
+        CK(B[B_FEAT].reserve(128 * (size_t)std::max<long long>(N, 1) + 128 * tc::NT));
+        CK(B[B_TCOUT].reserve(sizeof(int) * slots));
+        CK(B[B_TCLIST].reserve(sizeof(int) * slots));
+        CK(B[B_TCLISTCNT].reserve(sizeof(int) * P));
+        CK(B[B_TCLISTPFX].reserve(sizeof(int) * (P + 1)));
+        CK(B[B_PAIRCNT].reserve(sizeof(int) * P));
+        CK(B[B_TCPFX].reserve(sizeof(int) * (P + 1)));
+    }
 
     Scalars *sc = B[B_SCALARS].as<Scalars>();
     PairParams *pairs = B[B_PAIRS].as<PairParams>();
@@ -305,6 +346,10 @@ int run_chunk(rp_ctx *ctx, int variant, const rp_options &opt, const ChunkIO &io
         a.pts64 = pts64; a.pts32 = pts32; a.bear = bear; a.pairs = pairs; a.pts32p = B[B_PTS32P].as<float>();
         prepare_kernel<<<cdiv((long long)P * 32, 256), 256, 0, st>>>(a);
         LAUNCHED();
+        if (use_tc && N > 0) {
+            tc::tc_features_kernel<<<cdiv(N, 256), 256, 0, st>>>(N, pts32, B[B_FEAT].as<float4>());
+            LAUNCHED();
+        }
     }
     CK(cudaEventRecord(ev[1], st));
     // 2. sample
@@ -353,7 +398,8 @@ int run_chunk(rp_ctx *ctx, int variant, const rp_options &opt, const ChunkIO &io
         pair_bounds_kernel<<<cdiv((long long)P * 32, 256), 256, 0, st>>>(P, nseg, first_cnt, score, count,
                                                                        B[B_B0].as<int>(), B[B_S0].as<double>());
         LAUNCHED();
-        // 4b. FP32 bounds for all later models
+        // 4b. bounds for all later models.  Tensor-core tier first (certain-outlier counts of EVERY model, rp_tc.cuh),
+        // then the FP32 bound kernel only over the models that tier could not drop.
         BoundArgs ba;
         ba.n_groups = P * nseg; ba.grp_stride = 4 * SEG; ba.grp_per_pair = nseg; ba.grp_cnt = seg_count;
         ba.item_prefix = item_prefix; ba.n_items = &sc->n_items; ba.pairs = pairs; ba.models = models; ba.pts32p = B[B_PTS32P].as<ulonglong2>();
@@ -361,7 +407,33 @@ int run_chunk(rp_ctx *ctx, int variant, const rp_options &opt, const ChunkIO &io
         ba.B0 = B[B_B0].as<int>(); ba.S0 = B[B_S0].as<double>();
         ba.evaluated = &sc->evaluated_ps;
         ba.work_counter = &sc->bound_work; ba.head = ctx->head;
+        ba.slot_list = nullptr; ba.list_stride = 0;
         CK(cudaEventRecord(ev[20], st));
+        if (use_tc) {
+            pair_total_kernel<<<cdiv(P, 256), 256, 0, st>>>(P, nseg, seg_count, B[B_PAIRCNT].as<int>());
+            LAUNCHED();
+            build_items_kernel<<<1, 1024, 0, st>>>(P, B[B_PAIRCNT].as<int>(), B[B_TCPFX].as<int>(), &sc->n_tc_items, nullptr, tc::TILE_MODELS);
+            LAUNCHED();
+            tc::TcArgs ta;
+            memset(&ta, 0, sizeof ta);
+            ta.n_pairs = P; ta.nseg = nseg; ta.pairs = pairs; ta.seg_count = seg_count; ta.item_prefix = B[B_TCPFX].as<int>();
+            ta.n_items = &sc->n_tc_items; ta.models = models; ta.out = B[B_TCOUT].as<int>(); ta.pose = pose ? 1 : 0;
+            ta.evaluated = &sc->tc_evaluated;
+            rc = launch_tc(ctx, ta, B[B_FEAT].as<float4>(), N, st);
+            if (rc) return rc;
+            CK(cudaEventRecord(ev[22], st));
+            TcSelectArgs sel;
+            sel.n_pairs = P; sel.nseg = nseg; sel.head = ctx->head; sel.pairs = pairs; sel.seg_count = seg_count;
+            sel.out = B[B_TCOUT].as<int>(); sel.B0 = ba.B0; sel.S0 = ba.S0; sel.ub = ba.ub; sel.lb = ba.lb;
+            sel.list = B[B_TCLIST].as<int>(); sel.list_cnt = B[B_TCLISTCNT].as<int>(); sel.n_selected = &sc->tc_selected;
+            tc_select_kernel<<<cdiv((long long)P * 32, 256), 256, 0, st>>>(sel);
+            LAUNCHED();
+            build_items_kernel<<<1, 1024, 0, st>>>(P, B[B_TCLISTCNT].as<int>(), B[B_TCLISTPFX].as<int>(), &sc->n_tcsel_items, nullptr);
+            LAUNCHED();
+            ba.n_groups = P; ba.grp_stride = (int)slots_pp; ba.grp_per_pair = 1; ba.grp_cnt = B[B_TCLISTCNT].as<int>();
+            ba.item_prefix = B[B_TCLISTPFX].as<int>(); ba.n_items = &sc->n_tcsel_items;
+            ba.slot_list = B[B_TCLIST].as<int>(); ba.list_stride = (int)slots_pp;
+        }
         rc = launch_bound(ctx, pose, ba, st);
         if (rc) return rc;
         CK(cudaEventRecord(ev[21], st));
@@ -522,9 +594,16 @@ int run_chunk(rp_ctx *ctx, int variant, const rp_options &opt, const ChunkIO &io
     ctx->last_cnt[6] += (int64_t)h_sc.evaluated_ps;
     if (ctx->prune) {
         float msb = 0.f;
-        CK(cudaEventElapsedTime(&msb, ev[20], ev[21]));
+        CK(cudaEventElapsedTime(&msb, use_tc ? ev[22] : ev[20], ev[21]));
         ctx->last_ms[11] += msb;
+        if (use_tc) {
+            CK(cudaEventElapsedTime(&msb, ev[20], ev[22]));
+            ctx->last_ms[12] += msb;
+        }
     }
+    ctx->last_cnt[8] += (int64_t)h_sc.tc_evaluated;
+    ctx->last_cnt[9] += (int64_t)h_sc.tc_selected;
+    ctx->last_cnt[10] += (int64_t)h_sc.lm_flops;
     ctx->last_cnt[5] += ctx->prune ? (int64_t)h_sc.n_survivors + std::min<int64_t>(h_sc.n_hyp, (int64_t)P * ctx->head) : h_sc.n_hyp;
     ctx->last_cnt[7] = ctx->head;
     if (h_sc.overflow) return fail(ctx, RP_ERR_OVERFLOW, "trigger event list overflowed (EV)");
@@ -722,6 +801,19 @@ int rp_create(int device, rp_ctx **out) {
     for (auto &ev : ctx->ev) cudaEventCreate(&ev);
     if (const char *np = getenv("RP_NO_PRUNE")) ctx->prune = !(np[0] == '1');
     if (const char *nw = getenv("RP_NO_WAVES")) ctx->waves = !(nw[0] == '1');
+    if (const char *nt = getenv("RP_NO_TC")) ctx->tc = !(nt[0] == '1');
+    {
+        cudaDriverEntryPointQueryResult qres;
+        void *fn = nullptr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+            qres != cudaDriverEntryPointSuccess ||
+            cudaFuncSetAttribute(tc::tc_count_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES) != cudaSuccess) {
+            g_create_error = "tensor-map entry point / shared-memory opt-in unavailable (driver too old for sm_100a TMA?)";
+            rp_destroy(ctx);
+            return RP_ERR_CUDA;
+        }
+        ctx->encode_tiled = fn;
+    }
     if (const char *hd = getenv("RP_HEAD")) { const int v = atoi(hd); if (v == 32 || v == 64 || v == 96 || v == 128) ctx->head = v; }
     if (const char *gb = getenv("RP_WORKSPACE_GB")) {
         const double v = atof(gb);
@@ -776,10 +868,10 @@ int rp_estimate_batch_dev(rp_ctx *ctx, int variant, int64_t n_pairs, const int64
                          stream ? (cudaStream_t)stream : ctx->stream);
 }
 
-int rp_last_timing(const rp_ctx *ctx, double *ms16, int64_t *counters8) {
+int rp_last_timing(const rp_ctx *ctx, double *ms16, int64_t *counters16) {
     if (!ctx) return RP_ERR_INVALID;
     if (ms16) memcpy(ms16, ctx->last_ms, sizeof ctx->last_ms);
-    if (counters8) memcpy(counters8, ctx->last_cnt, sizeof ctx->last_cnt);
+    if (counters16) memcpy(counters16, ctx->last_cnt, sizeof ctx->last_cnt);
     return RP_OK;
 }
 
@@ -908,6 +1000,47 @@ int rp_score_batch(rp_ctx *ctx, int variant, int64_t n_models, const rp_model *m
         }
         CK(cudaStreamSynchronize(st));
     }
+    return RP_OK;
+}
+
+int rp_tc_count_batch(rp_ctx *ctx, int variant, int64_t n_models, const rp_model *models, int64_t n_points,
+                      const double *x1, const double *x2, double sq_threshold, int64_t *certain_outliers) {
+    if (!ctx || variant < 0 || variant > 3 || n_models < 0 || n_points < 0 || n_models > 4 * SEG ||
+        (n_models > 0 && (!models || !certain_outliers)) || (n_points > 0 && (!x1 || !x2)))
+        return fail(ctx, RP_ERR_INVALID, "bad argument (at most 4096 models per call)");
+    if (n_models == 0) return RP_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    DevBuf *B = ctx->buf;
+    const bool pose = variant == RP_CALIB || variant == RP_CALIB_SHIFT;
+    int rc = stage_pair(ctx, n_points, x1, x2, sq_threshold, st);
+    if (rc) return rc;
+    const size_t nn = (size_t)std::max<int64_t>(n_points, 1);
+    CK(B[B_FEAT].reserve(128 * nn + 128 * tc::NT));
+    CK(B[B_MODELS].reserve(sizeof(Model) * 4 * SEG)); CK(B[B_TCOUT].reserve(sizeof(int) * 4 * SEG));
+    CK(B[B_SEGCNT].reserve(sizeof(int) * 2)); CK(B[B_TCPFX].reserve(sizeof(int) * 4)); CK(B[B_SCALARS].reserve(sizeof(Scalars)));
+    Scalars *sc = B[B_SCALARS].as<Scalars>();
+    CK(cudaMemsetAsync(sc, 0, sizeof(Scalars), st));
+    CK(cudaMemcpyAsync(B[B_MODELS].p, models, sizeof(Model) * (size_t)n_models, cudaMemcpyHostToDevice, st));
+    const int cnt = (int)n_models;
+    CK(cudaMemcpyAsync(B[B_SEGCNT].p, &cnt, sizeof(int), cudaMemcpyHostToDevice, st));
+    if (n_points > 0) {
+        tc::tc_features_kernel<<<cdiv(n_points, 256), 256, 0, st>>>(n_points, B[B_PTS32].as<float4>(), B[B_FEAT].as<float4>());
+        LAUNCHED();
+    }
+    build_items_kernel<<<1, 1024, 0, st>>>(1, B[B_SEGCNT].as<int>(), B[B_TCPFX].as<int>(), &sc->n_tc_items, nullptr, tc::TILE_MODELS);
+    LAUNCHED();
+    tc::TcArgs ta;
+    memset(&ta, 0, sizeof ta);
+    ta.n_pairs = 1; ta.nseg = 1; ta.pairs = B[B_PAIRS].as<PairParams>(); ta.seg_count = B[B_SEGCNT].as<int>();
+    ta.item_prefix = B[B_TCPFX].as<int>(); ta.n_items = &sc->n_tc_items; ta.models = B[B_MODELS].as<Model>();
+    ta.out = B[B_TCOUT].as<int>(); ta.pose = pose ? 1 : 0;
+    rc = launch_tc(ctx, ta, B[B_FEAT].as<float4>(), n_points, st);
+    if (rc) return rc;
+    std::vector<int> h((size_t)n_models);
+    CK(cudaMemcpyAsync(h.data(), B[B_TCOUT].p, sizeof(int) * (size_t)n_models, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int64_t i = 0; i < n_models; ++i) certain_outliers[i] = h[(size_t)i];
     return RP_OK;
 }
 

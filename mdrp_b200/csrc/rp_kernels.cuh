@@ -16,6 +16,7 @@
 #include "rp_solvers.cuh"
 #include "rp_score.cuh"
 #include "rp_lm_kernel.cuh"
+#include "rp_tc.cuh"
 
 namespace rp {
 
@@ -508,7 +509,7 @@ __global__ void solve_problems_kernel(int variant, long long n, const double *x1
 // at slots [e*grp_stride, …); item = HB consecutive models of one group.  Exclusive scan of
 // ceil(cnt/HB) over the groups; single block.
 __global__ void build_items_kernel(int n_groups, const int *grp_cnt, int *item_prefix, int *n_items,
-                                   long long *n_hyp_total) {
+                                   long long *n_hyp_total, int gran = HB) {
     // tiles of 1024 groups: shuffle scan inside each warp, the 32 warp totals scanned by warp 0
     __shared__ int wtot[32];
     __shared__ long long whyp[32];
@@ -518,7 +519,7 @@ __global__ void build_items_kernel(int n_groups, const int *grp_cnt, int *item_p
     for (int base = 0; base < n_groups; base += 1024) {
         const int e = base + threadIdx.x;
         const int c = e < n_groups ? grp_cnt[e] : 0;
-        const int v = (c + HB - 1) / HB;
+        const int v = (c + gran - 1) / gran;
         hyps += c;
         int incl = v;
 #pragma unroll
@@ -809,6 +810,8 @@ struct BoundArgs {
     unsigned long long *evaluated;  // optional: (model, correspondence) pairs actually evaluated
     int *work_counter;              // zeroed before the launch: blocks take work items dynamically
     int head;                       // the first `head` models of a pair were scored exactly (multiple of SCORE_WARPS)
+    const int *slot_list;           // optional indirection (survivors of the tensor-core tier): model i of group e lives
+    int list_stride;                //   at slot e*grp_stride + slot_list[e*list_stride + i]; the head is not in the list
 };
 
 #ifndef RP_SOLVE_MIN_BLOCKS
@@ -944,12 +947,16 @@ __global__ void __launch_bounds__(SCORE_THREADS, RP_BOUND_MIN_BLOCKS) bound_kern
         const PairParams pp = a.pairs[pair];
         const int my_nh = (nh - w + SCORE_WARPS - 1) / SCORE_WARPS;  // models h = w + i*SCORE_WARPS
         // the first `head` models of a pair are scored exactly: in its first item the warp skips i < i0
-        const int i0 = (e % a.grp_per_pair == 0 && chunk == 0) ? a.head / SCORE_WARPS : 0;
+        const int i0 = (!a.slot_list && e % a.grp_per_pair == 0 && chunk == 0) ? a.head / SCORE_WARPS : 0;
         if (my_nh <= i0) continue;
         __syncwarp();
         bool nonfinite = false;
+        // slot of the warp's i-th model (lane i keeps it for the result write)
+        size_t my_slot = slot0 + w + lane * SCORE_WARPS;
+        if (a.slot_list && lane < my_nh)
+            my_slot = (size_t)e * a.grp_stride + a.slot_list[(size_t)e * a.list_stride + h0 + w + lane * SCORE_WARPS];
         if (lane < my_nh) {
-            const Model m = a.models[slot0 + w + lane * SCORE_WARPS];
+            const Model m = a.models[my_slot];
             const M3 E = POSE ? essential_from_motion(m.q, m.t) : fundamental_from_model(m);
             // A model with a non-finite E (the minimal solvers return NaN models now and then, P3P for ~6 % of
             // its solutions) has r2 = NaN for every correspondence: the reference counts 0 inliers and sums
@@ -1039,22 +1046,86 @@ __global__ void __launch_bounds__(SCORE_THREADS, RP_BOUND_MIN_BLOCKS) bound_kern
         __syncwarp();
 #pragma unroll 1
         for (int i = i0; i < my_nh; ++i) {
-            const int h = w + i * SCORE_WARPS;
+            const size_t slot_i = __shfl_sync(0xffffffffu, (unsigned long long)my_slot, i);
             float s = sh.sp[wid][i][lane];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
             if (lane == 0) {
                 const bool dead = !((alive >> i) & 1u);
-                a.ub[slot0 + h] = dead ? 0 : n - out_cnt[i];
+                a.ub[slot_i] = dead ? 0 : n - out_cnt[i];
                 // lb = thr^2 * (#certain outliers) + sum of candidate lower bounds; FP32 rounding of the
                 // terms, the rcp and the partial sums is covered by 1e-4 relative
                 const double lbv = ((double)thr2_lo * (double)out_cnt[i] + (double)s) * (1.0 - 1e-4);
-                a.lb[slot0 + h] = dead ? INFINITY : (((cheap >> i) & 1u) ? -INFINITY : __double2float_rd(lbv));
+                a.lb[slot_i] = dead ? INFINITY : (((cheap >> i) & 1u) ? -INFINITY : __double2float_rd(lbv));
             }
         }
         if (a.point_scores && lane == 0) atomicAdd(a.point_scores, (unsigned long long)(my_nh - i0) * (unsigned long long)n);
         if (a.evaluated && lane == 0) atomicAdd(a.evaluated, evaluated);
         __syncwarp();  // the unit's shared-memory rows are free for the next one
+    }
+}
+
+// models per pair (sum of its segment counts): the tensor-core tier walks a pair's models as ONE list
+__global__ void pair_total_kernel(int n_pairs, int nseg, const int *seg_count, int *pair_cnt) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pairs) return;
+    int c = 0;
+    for (int s = 0; s < nseg; ++s) c += seg_count[i * nseg + s];
+    pair_cnt[i] = c;
+}
+
+// tc_select: what the tensor-core tier (rp_tc.cuh) decided.  out[slot] = certain outliers of the model, a rigorous
+// lower bound of N - inlier_count, and thr^2 out of the score.  With (B0, S0) of the exactly scored head, a model with
+//     out >= N - B0   and   thr^2 out >= S0
+// can neither exceed the best inlier count nor undercut the best score: it gets (ub 0, lb +inf), which the prune
+// drops.  Everything else is compacted, in sequence order, into the pair's list for the FP32 bound kernel.
+// One warp per pair.
+struct TcSelectArgs {
+    int n_pairs, nseg, head;
+    const PairParams *pairs;
+    const int *seg_count;
+    const int *out;
+    const int *B0;
+    const double *S0;
+    int *ub;
+    float *lb;
+    int *list;       // [n_pairs * nseg*4*SEG] pair-relative slots of the survivors
+    int *list_cnt;   // [n_pairs]
+    unsigned long long *n_selected;
+};
+__global__ void tc_select_kernel(TcSelectArgs a) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= a.n_pairs) return;
+    const PairParams pp = a.pairs[warp];
+    const size_t slots_pp = (size_t)a.nseg * (4 * SEG);
+    const size_t pslot = (size_t)warp * slots_pp;
+    const int n = pp.n;
+    // same abandonment threshold as bound_kernel
+    const float thr2_lo = __double2float_rd(pp.sq_thr);
+    const int B0 = a.B0[warp];
+    const double S0 = a.S0[warp];
+    const double need_d = fmax((double)(n - B0), S0 < 1e300 ? ceil(S0 / ((double)thr2_lo * (1.0 - 2e-4))) : 4.0e9);
+    const int need_out = need_d > 2.0e9 ? 0x7fffffff : max((int)need_d, 1);
+    int ns = 0;
+    for (int seg = 0; seg < a.nseg; ++seg) {
+        const int cnt = a.seg_count[warp * a.nseg + seg];
+        const int rel0 = seg * (4 * SEG);
+        for (int base = (seg == 0 ? a.head : 0); base < cnt; base += 32) {
+            const int h = base + lane;
+            bool keep = false;
+            if (h < cnt) {
+                keep = a.out[pslot + rel0 + h] < need_out;
+                if (!keep) { a.ub[pslot + rel0 + h] = 0; a.lb[pslot + rel0 + h] = INFINITY; }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (keep) a.list[pslot + ns + __popc(m & ((1u << lane) - 1u))] = rel0 + h;
+            ns += __popc(m);
+        }
+    }
+    if (lane == 0) {
+        a.list_cnt[warp] = ns;
+        if (a.n_selected && ns) atomicAdd(a.n_selected, (unsigned long long)ns);
     }
 }
 

@@ -1,0 +1,493 @@
+// rp_tc.cuh — tensor-core tier of the minimal-model scoring (sm_100a: tcgen05.mma + TMEM + TMA).
+//
+// What it computes.  score_models() (so@0x22ebc0) looks at a minimal model only when it has more inliers
+// or a lower MSAC score than every earlier one, so a model with provably MANY certain outliers can be
+// dropped unseen.  For one (model, correspondence) the Sampson test of
+// compute_sampson_msac_score (so@0x4f61d0 / so@0x4f65d0) is  r2 = C^2 / den < thr^2  with
+//     C   = x2^T E x1                       = sum_j E_j  phi_j(p)      (9 monomials of the point)
+//     den = |E x1|_{01}^2 + |E^T x2|_{01}^2 = sum_k G_k(E) psi_k(p)    (11 monomials of the point)
+// i.e. two contractions [models x K] . [K x points]: a GEMM with a threshold epilogue.  This kernel runs
+// them on the 5th-generation tensor cores:
+//     Cs = 2^s C~                                    4 x tcgen05.mma kind::tf32 (hi/lo split, see below)
+//     Ts = -2^2s [(1+a) g (den~ + d_den) + (1+1/a) eps^2]   2 x tcgen05.mma kind::tf32
+//     certain outlier  <=>  Cs*Cs + Ts > 0           one FFMA.SAT per point-score out of TMEM
+// and counts the certain outliers of every model.  It is a FILTER, never the score: a point is counted
+// only if the FP64 reference test is certainly false, so  out <= N - inlier_count  and
+// thr^2 * out <= score  hold rigorously (error model below); survivors go on to the FP32 bound kernel
+// and the exact FP64 kernel (rp_kernels.cuh).
+//
+// Precision.  TF32 keeps 11 significand bits, far too few for C (the threshold sits at ~1e-3 |E|), so
+// both operands of C are split  v = hi + lo,  hi = tf32(v), lo = tf32(v - hi)  and the three products
+// hi*hi + lo*hi + hi*lo are accumulated (the products of TF32 numbers are exact in the FP32 accumulator):
+//     |2^-s Cs - C| <= eps_tc = 64 u Emax (M + thr m),   u = 2^-24
+// (input roundings 4u, dropped lo*lo and the two split residuals 3*2^-22 = 12u, four FP32 accumulation steps <= 8u even
+// with truncation: 24u, so 2.7x slack; measured on B200 by tools/tc_probe.cu: max 1.6u; M, m, Emax as in rp_score.cuh).  den only scales the threshold, so single TF32 suffices:
+//     |den~ - den| <= d_den = 2^-7 Emax^2 m^2    (two 2^-11 roundings per term on sum|G_k psi_k| <= 4 Emax^2 m^2,
+//                                                 accumulation, 2x slack)
+// and with (x+y)^2 <= (1+a) x^2 + (1+1/a) y^2, a = 1/32:
+//     Cs^2 + Ts > 0  =>  C~^2 > (1+a) g (den + 0) + (1+1/a) eps^2  =>  (|C~| - eps)^2 > g den  =>  r2 > thr^2 (1+1e-6).
+// tests/test_gpu_tc.py measures the actual errors against FP64 and checks out <= N - exact count on random
+// and adversarial models.
+//
+// Layout / schedule (one CTA per SM, persistent, 384 threads):
+//   B operand  per-point feature rows, 32 floats = 128 B, written once per pair by tc_features_kernel, fetched
+//              64 rows at a time by TMA (cp.async.bulk.tensor, SWIZZLE_128B) into a 4-stage ring  [warp 0]
+//   A operand  256 models per work item (2 M-tiles), rows built in-kernel from the 96-byte models (E, G(E),
+//              hi/lo split, constants) straight into the swizzled shared-memory layout, double buffered [warps 10-11]
+//   MMA        one elected thread issues 12 tcgen05.mma per 64-point tile (2 M-tiles x (4 + 2)) into a
+//              2-stage TMEM accumulator ring (2 x 2 x 64 columns per stage = all 512 columns)      [warp 1]
+//   epilogue   thread = model (TMEM lane), tcgen05.ld 32 columns at a time, FFMA.SAT + packed FADD  [warps 2-9]
+// Per (model, point): 48 tensor-core MACs, 8 B of TMEM read, 1.5 issue slots.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include "rp_types.cuh"
+
+namespace rp {
+namespace tc {
+
+#ifndef RP_TC_NT
+#define RP_TC_NT 64
+#endif
+#ifndef RP_TC_MT
+#define RP_TC_MT 2
+#endif
+constexpr int NT = RP_TC_NT;                 // points per accumulator tile (MMA N)
+constexpr int MT = RP_TC_MT;                 // M-tiles (128 models) per work item
+constexpr int TILE_MODELS = 128 * MT;
+constexpr int B_STAGES = 4;
+constexpr int ACC_STAGES = 512 / (MT * 2 * NT);      // accumulator ring fills the tensor memory
+constexpr int TMEM_COLS = MT * 2 * NT * ACC_STAGES;   // 512
+constexpr int FEAT = 32;                     // floats per point feature row
+constexpr int A_REGION_BYTES = 128 * 128;    // one SWIZZLE_128B region: 128 rows x 128 B
+constexpr int A_BUF_BYTES = MT * 2 * A_REGION_BYTES;
+constexpr int B_STAGE_BYTES = NT * 128;
+constexpr int EPI_WARP0 = 4, EPI_WARPS = 4 * MT, BUILD_WARP0 = EPI_WARP0 + EPI_WARPS, BUILD_WARPS = 2;
+constexpr int THREADS = 32 * (BUILD_WARP0 + BUILD_WARPS);   // warps 2, 3 idle: epilogue warp w reads TMEM lanes 32 (w % 4)
+constexpr int SMEM_BYTES = 1024 + 2 * A_BUF_BYTES + B_STAGES * B_STAGE_BYTES + 256;
+static_assert(TMEM_COLS == 512 && ACC_STAGES >= 2, "accumulator ring must fill the tensor memory exactly");
+
+constexpr double A_SPLIT = 1.0 / 32.0;                // a of (x+y)^2 <= (1+a) x^2 + (1+1/a) y^2
+constexpr double EPS_UNITS = 64.0;                    // eps_tc = EPS_UNITS u Emax (M + thr m)
+
+// ---- TF32 rounding (round to nearest, ties away: cvt.rna.tf32.f32) ---------------------------------
+RP_HD float tf32_round(float v) {
+#if defined(__CUDA_ARCH__)
+    unsigned r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+#else
+    unsigned b;
+    memcpy(&b, &v, 4);
+    if ((b & 0x7f800000u) != 0x7f800000u) b = (b + 0x1000u) & 0xffffe000u;
+    float o;
+    memcpy(&o, &b, 4);
+    return o;
+#endif
+}
+
+// ---- per-point feature row (B operand) ---------------------------------------------------------------
+// slice 0: tf32(phi_0..7)   slice 1: tf32(phi - slice 0)   slice 2: tf32(psi_0..7)   slice 3: (x2x, x2y, 1, 1, 0, 0, 0, 0)
+//   phi = (x2x x1x, x2x x1y, x2x, x2y x1x, x2y x1y, x2y, x1x, x1y)            <-> E00 E01 E02 E10 E11 E12 E20 E21 (E22: const)
+//   psi = (x1x^2, x1x x1y, x1y^2, x1x, x1y, x2x^2, x2x x2y, x2y^2 | x2x, x2y | 1)
+RP_HD void feature_row(float x1x, float x1y, float x2x, float x2y, float *row /*32*/) {
+    const float phi[8] = {x2x * x1x, x2x * x1y, x2x, x2y * x1x, x2y * x1y, x2y, x1x, x1y};
+    const float psi[8] = {x1x * x1x, x1x * x1y, x1y * x1y, x1x, x1y, x2x * x2x, x2x * x2y, x2y * x2y};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float hi = tf32_round(phi[j]);
+        row[j] = hi;
+        row[8 + j] = tf32_round(phi[j] - hi);
+        row[16 + j] = tf32_round(psi[j]);
+    }
+    row[24] = tf32_round(x2x); row[25] = tf32_round(x2y); row[26] = 1.0f; row[27] = 1.0f;
+    row[28] = row[29] = row[30] = row[31] = 0.0f;
+}
+
+// ---- per-model operand row (A operand): 5 slices of 8 floats ---------------------------------------------
+//   a0 = tf32(2^s E_j)  a1 = tf32(2^s E_j - a0)  a2 = (0, 0, E22 hi, E22 lo, 0...)            -> Cs
+//   a3 = tf32(-2^2s (1+a) g G_0..7)   a4 = (G_8', G_9', const, 0...)                           -> Ts
+// A model whose parameters leave the range the error model covers gets the zero row (no point is ever counted:
+// the model simply survives this tier); a model with a non-finite E / F — the minimal solvers return NaN models
+// now and then — has r2 = NaN for every correspondence in the reference, i.e. no inliers and score N thr^2:
+// its row is (0, ..., const = +2^100), which counts EVERY point.
+RP_HD void model_row(const M3 &E, double thr, double Mmax, double mmax, float *r0 /*32: a0 a1 a2 a3*/, float *r1 /*8: a4*/) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) r0[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r1[i] = 0.f;
+    const double e[9] = {E.r0.x, E.r0.y, E.r0.z, E.r1.x, E.r1.y, E.r1.z, E.r2.x, E.r2.y, E.r2.z};
+    double emax = 0.0;
+    bool finite = true;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { emax = fmax(emax, fabs(e[i])); finite = finite && (e[i] - e[i] == 0.0); }
+    if (!finite) { r1[2] = 1.2676506002282294e30f; return; }   // 2^100
+    const bool sane = emax > 1e-3 && emax < 1e3 && thr > 1e-6 && thr < 1.0 && Mmax < 1e3 && mmax < 1e3;
+    if (!sane) return;
+    const double u = 5.9604644775390625e-08;  // 2^-24
+    const double eps = EPS_UNITS * u * emax * (Mmax + thr * mmax) * 1.0001;
+    const double g = thr * thr * (1.0 + 1e-5);
+    const double dden = 0.0078125 * emax * emax * mmax * mmax;   // 2^-7 Emax^2 m^2
+    // Per-model power-of-two scaling: Cs = 2^s C~, Ts = 2^2s T~ with 2^2s (1+1/a) eps^2 >= 2^48.  Then |Ts| >= 2^47, and
+    // whenever Cs^2 + Ts > 0 we have |Cs| > 2^23.5: both FP32 numbers are integers, so the exact value of Cs^2 + Ts is
+    // an integer and FFMA.SAT returns exactly 0 or 1 — the per-model sums are exact counts (N < 2^24).
+    // Ranges: Cs^2 <= 2^2s Emax^2 M^2 and |Ts| <= 2^2s 1.04 g (4 Emax^2 m^2 + ...) stay below 2^48 * 2^28 (sane ranges above).
+    int ex;
+    (void)frexp((1.0 + 1.0 / A_SPLIT) * eps * eps, &ex);     // value in [2^(ex-1), 2^ex)
+    const int sc = (48 - (ex - 1) + 1) / 2;                    // 2 sc >= 48 - (ex - 1)
+    const double cs = ldexp(1.0, sc), ts = ldexp(1.0, 2 * sc);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float v = (float)(e[j] * cs);
+        const float hi = tf32_round(v);
+        r0[j] = hi;
+        r0[8 + j] = tf32_round(v - hi);
+    }
+    {
+        const float v = (float)(e[8] * cs);
+        const float hi = tf32_round(v);
+        r0[16 + 2] = hi;
+        r0[16 + 3] = tf32_round(v - hi);
+    }
+    const double G[11] = {e[0] * e[0] + e[3] * e[3], 2.0 * (e[0] * e[1] + e[3] * e[4]), e[1] * e[1] + e[4] * e[4],
+                          2.0 * (e[0] * e[2] + e[3] * e[5]), 2.0 * (e[1] * e[2] + e[4] * e[5]),
+                          e[0] * e[0] + e[1] * e[1], 2.0 * (e[0] * e[3] + e[1] * e[4]), e[3] * e[3] + e[4] * e[4],
+                          2.0 * (e[0] * e[6] + e[1] * e[7]), 2.0 * (e[3] * e[6] + e[4] * e[7]),
+                          e[2] * e[2] + e[5] * e[5] + e[6] * e[6] + e[7] * e[7]};
+    const double k = -ts * (1.0 + A_SPLIT) * g;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r0[24 + j] = tf32_round((float)(k * G[j]));
+    r1[0] = tf32_round((float)(k * G[8]));
+    r1[1] = tf32_round((float)(k * G[9]));
+    // the constant: pushed away from zero by 2^-9 before rounding (more negative = fewer certain outliers = conservative)
+    const double kc = (k * (G[10] + dden) - ts * (1.0 + 1.0 / A_SPLIT) * eps * eps) * (1.0 + 0.001953125);
+    r1[2] = tf32_round((float)kc);
+}
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------------
+#if defined(__CUDACC__)
+RP_D uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+RP_D void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+RP_D void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+RP_D void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+RP_D bool mbar_try(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a barrier that never completes (a protocol bug) traps instead of hanging the GPU.
+RP_D void mbar_wait(uint64_t *bar, uint32_t parity) {
+    for (unsigned spins = 0; !mbar_try(bar, parity); ++spins)
+        if (spins > (1u << 28)) __trap();
+}
+RP_D void tma_load_2d(void *smem_dst, const CUtensorMap *tmap, int c0, int c1, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+RP_D void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+RP_D void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+RP_D void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+RP_D void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+RP_D void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+RP_D void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+RP_D void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+RP_D void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr) : "memory");
+}
+RP_D void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// one lane of a CONVERGED warp (the tensor-core and TMA instructions take uniform-register operands: issued from a
+// `lane == 0` branch the compiler wraps each of them in a waterfall loop; under elect.sync it does not)
+RP_D bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+    return pred != 0;
+}
+RP_D float fma_sat(float a, float b, float c) {
+    float d;
+    asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (sm_100 version bit set): rows of 128 B, 8-row
+// groups 1024 B apart; a K slice of 8 TF32 (32 B) inside the 128-byte span is selected by the start address
+RP_D uint64_t desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3ffffu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::tf32, FP32 accumulate, A and B K-major, M = 128, N = NT
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
+
+// byte offset of (row, 16-byte chunk) inside a SWIZZLE_128B region (Swizzle<3,4,3> on a 1024-aligned base)
+RP_D uint32_t sw128_off(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
+
+// ---- feature kernel ------------------------------------------------------------------------------------------
+// one thread per correspondence: pts32 (float4) -> 128-byte feature row
+__global__ void tc_features_kernel(long long n, const float4 *pts32, float4 *feat) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = pts32[i];
+    float row[32];
+    feature_row(p.x, p.y, p.z, p.w, row);
+    float4 *o = feat + i * 8;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) o[c] = make_float4(row[4 * c], row[4 * c + 1], row[4 * c + 2], row[4 * c + 3]);
+}
+
+// ---- the tier ---------------------------------------------------------------------------------------------------
+struct TcArgs {
+    int n_pairs, nseg;
+    const PairParams *pairs;
+    const int *seg_count;        // [n_pairs * nseg] models per (pair, segment)
+    const int *item_prefix;      // [n_pairs + 1] work items (TILE_MODELS models of one pair) before pair p
+    const int *n_items;
+    const Model *models;         // slots: (pair * nseg + seg) * 4 * SEG + i
+    int *out;                    // slots: certain outliers (<= N - inlier count; == N for a model with a non-finite E / F)
+    int pose;                    // 1: E = [t]x R,  0: F = diag(1,1,f2) E diag(1,1,f1)
+    unsigned long long *evaluated;  // optional: point-scores evaluated
+    float *debug;                // optional: raw (Cs, Ts) of work item 0, [TILE_MODELS][2][debug_cols]
+    int debug_cols;
+};
+
+// MODE 0: the tier.  Probe modes (tools/tc_probe.cu): 1 = epilogue loads the accumulators but skips the arithmetic,
+// 2 = epilogue neither loads nor computes (TMA + MMA pipeline alone).
+template <int MODE>
+__global__ void __launch_bounds__(THREADS, 1) tc_count_kernel(const __grid_constant__ CUtensorMap tmap, TcArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = smem;                                   // [2][MT][2 regions][16 KB]
+    uint8_t *sB = smem + 2 * A_BUF_BYTES;                 // [B_STAGES][8 KB]
+    uint64_t *bars = (uint64_t *)(sB + B_STAGES * B_STAGE_BYTES);
+    uint64_t *b_full = bars, *b_empty = bars + B_STAGES, *a_full = bars + 2 * B_STAGES, *a_empty = a_full + 2,
+             *acc_full = a_empty + 2, *acc_empty = acc_full + ACC_STAGES;
+    uint32_t *tmem_base_s = (uint32_t *)(acc_empty + ACC_STAGES);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int i = 0; i < B_STAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], BUILD_WARPS * 32); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc(tmem_base_s, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_s;
+    const int n_items = *a.n_items;
+
+    auto pair_of = [&](int item) {
+        int lo = 0, hi = a.n_pairs;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (a.item_prefix[mid] <= item) lo = mid; else hi = mid;
+        }
+        return lo;
+    };
+
+    if (warp == 0) {
+        // ===== TMA producer: the pair's feature rows, 64 at a time (converged warp, one elected lane issues) =====
+        int st = 0;
+        uint32_t ph = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const PairParams pp = a.pairs[pair_of(item)];
+            const int ntiles = (pp.n + NT - 1) / NT;
+            for (int t = 0; t < ntiles; ++t) {
+                mbar_wait(&b_empty[st], ph ^ 1);
+                if (elect_one()) {
+                    mbar_expect_tx(&b_full[st], B_STAGE_BYTES);
+                    tma_load_2d(sB + st * B_STAGE_BYTES, &tmap, 0, (int)(pp.off + (long long)t * NT), &b_full[st]);
+                }
+                __syncwarp();
+                if (++st == B_STAGES) { st = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (converged warp, one elected lane issues) =====
+        int st = 0, as = 0, k = 0;
+        uint32_t ph = 0, aph = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
+            const PairParams pp = a.pairs[pair_of(item)];
+            const int ntiles = (pp.n + NT - 1) / NT;
+            const int ab = k & 1;
+            mbar_wait(&a_full[ab], (k >> 1) & 1);
+            tc_fence_after();
+            const uint32_t a_base = smem_u32(sA + ab * A_BUF_BYTES);
+            for (int t = 0; t < ntiles; ++t) {
+                mbar_wait(&acc_empty[as], aph ^ 1);
+                mbar_wait(&b_full[st], ph);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t b_base = smem_u32(sB + st * B_STAGE_BYTES);
+                    const uint64_t b0 = desc_sw128(b_base), b1 = desc_sw128(b_base + 32), b2 = desc_sw128(b_base + 64),
+                                   b3 = desc_sw128(b_base + 96);
+#pragma unroll
+                    for (int m = 0; m < MT; ++m) {
+                        const uint32_t r0 = a_base + (m * 2) * A_REGION_BYTES, r1 = r0 + A_REGION_BYTES;
+                        const uint32_t dC = tmem_base + (uint32_t)(((as * MT + m) * 2) * NT), dT = dC + NT;
+                        umma_tf32(dC, desc_sw128(r0), b0, IDESC, 0);        // E_hi . phi_hi
+                        umma_tf32(dC, desc_sw128(r0 + 32), b0, IDESC, 1);   // E_lo . phi_hi
+                        umma_tf32(dC, desc_sw128(r0), b1, IDESC, 1);        // E_hi . phi_lo
+                        umma_tf32(dC, desc_sw128(r0 + 64), b3, IDESC, 1);   // E22 (hi, lo) . (1, 1)
+                        umma_tf32(dT, desc_sw128(r0 + 96), b2, IDESC, 0);   // G_0..7 . psi_0..7
+                        umma_tf32(dT, desc_sw128(r1), b3, IDESC, 1);        // G_8, G_9, const . (x2x, x2y, 1)
+                    }
+                    umma_commit(&b_empty[st]);      // the smem stage is free once these MMAs have read it
+                    umma_commit(&acc_full[as]);     // ... and the accumulators are ready for the epilogue
+                    if (t == ntiles - 1) umma_commit(&a_empty[ab]);   // the A buffer may be rebuilt
+                }
+                __syncwarp();
+                if (++st == B_STAGES) { st = 0; ph ^= 1; }
+                if (++as == ACC_STAGES) { as = 0; aph ^= 1; }
+            }
+        }
+    } else if (warp >= EPI_WARP0 && warp < BUILD_WARP0) {
+        // ===== epilogue: thread = model =====
+        const int ew = warp - EPI_WARP0;
+        const int m = ew / 4, q = warp & 3;          // M-tile, TMEM lane quarter this warp may access
+        const int row = m * 128 + q * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        int as = 0, k = 0;
+        uint32_t aph = 0;
+        unsigned long long evaluated = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
+            const PairParams pp = a.pairs[pair_of(item)];
+            const int n = pp.n;
+            const int ntiles = (n + NT - 1) / NT;
+            float acc0 = 0.f, acc1 = 0.f;
+            for (int t = 0; t < ntiles; ++t) {
+                mbar_wait(&acc_full[as], aph);
+                tc_fence_after();
+                const uint32_t cC = lane_addr + (uint32_t)(((as * MT + m) * 2) * NT), cT = cC + NT;
+                const int nv = min(NT, n - t * NT);
+#pragma unroll
+                for (int h = 0; h < NT / 32; ++h) {
+                    if (MODE == 2) continue;
+                    uint32_t c[32], tt[32];
+                    tmem_ld32(cC + h * 32, c);
+                    tmem_ld32(cT + h * 32, tt);
+                    tmem_ld_wait();
+                    if (MODE == 1) {
+                        acc0 += __uint_as_float(c[0] ^ c[31]) + __uint_as_float(tt[0] ^ tt[31]);
+                        continue;
+                    }
+                    if (a.debug && item == 0) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int col = t * NT + h * 32 + j;
+                            if (col < a.debug_cols) {
+                                a.debug[((size_t)row * 2 + 0) * a.debug_cols + col] = __uint_as_float(c[j]);
+                                a.debug[((size_t)row * 2 + 1) * a.debug_cols + col] = __uint_as_float(tt[j]);
+                            }
+                        }
+                    }
+                    if (nv >= (h + 1) * 32) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) {
+                            acc0 += fma_sat(__uint_as_float(c[j]), __uint_as_float(c[j]), __uint_as_float(tt[j]));
+                            acc1 += fma_sat(__uint_as_float(c[j + 1]), __uint_as_float(c[j + 1]), __uint_as_float(tt[j + 1]));
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (h * 32 + j < nv)
+                                acc0 += fma_sat(__uint_as_float(c[j]), __uint_as_float(c[j]), __uint_as_float(tt[j]));
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[as]);
+                if (++as == ACC_STAGES) { as = 0; aph ^= 1; }
+            }
+            // logical model j of the pair -> (segment, index) -> slot
+            const int pair = pair_of(item);
+            int j = (item - a.item_prefix[pair]) * TILE_MODELS + row;
+            const int *segc = a.seg_count + (size_t)pair * a.nseg;
+            for (int seg = 0; seg < a.nseg; ++seg) {
+                const int c = segc[seg];
+                if (j < c) {
+                    // every addend is exactly 0 or 1 (model_row's scaling), so the FP32 sums are exact counts
+                    a.out[((size_t)pair * a.nseg + seg) * (size_t)(4 * SEG) + j] = (int)(acc0 + acc1);
+                    evaluated += (unsigned long long)n;
+                    break;
+                }
+                j -= c;
+            }
+        }
+        if (a.evaluated) {
+            for (int o = 16; o > 0; o >>= 1) evaluated += __shfl_xor_sync(0xffffffffu, evaluated, o);
+            if (lane == 0 && evaluated) atomicAdd(a.evaluated, evaluated);
+        }
+    } else if (warp >= BUILD_WARP0) {
+        // ===== A builder: 64 threads, 4 models each per work item =====
+        const int bt = tid - BUILD_WARP0 * 32;
+        int k = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
+            const int pair = pair_of(item);
+            const PairParams pp = a.pairs[pair];
+            const int ab = k & 1;
+            mbar_wait(&a_empty[ab], ((k >> 1) & 1) ^ 1);
+            const int j0 = (item - a.item_prefix[pair]) * TILE_MODELS;
+            const int *segc = a.seg_count + (size_t)pair * a.nseg;
+            for (int r = bt; r < TILE_MODELS; r += BUILD_WARPS * 32) {
+                // logical model j of the pair -> (segment, index) -> pair-relative slot
+                int j = j0 + r, seg = 0, slot = -1;
+                while (seg < a.nseg) {
+                    const int c = segc[seg];
+                    if (j < c) { slot = seg * (4 * SEG) + j; break; }
+                    j -= c;
+                    ++seg;
+                }
+                float r0[32], r1[8];
+                if (slot >= 0) {
+                    const Model mdl = a.models[((size_t)pair * a.nseg) * (size_t)(4 * SEG) + slot];
+                    const M3 E = a.pose ? essential_from_motion(mdl.q, mdl.t) : fundamental_from_model(mdl);
+                    model_row(E, pp.thr, pp.Mmax, pp.mmax, r0, r1);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) r0[i] = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) r1[i] = 0.f;
+                }
+                const int m = r >> 7, rr = r & 127;
+                uint8_t *reg0 = sA + ab * A_BUF_BYTES + (m * 2) * A_REGION_BYTES, *reg1 = reg0 + A_REGION_BYTES;
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    *(float4 *)(reg0 + sw128_off(rr, c)) = make_float4(r0[4 * c], r0[4 * c + 1], r0[4 * c + 2], r0[4 * c + 3]);
+                *(float4 *)(reg1 + sw128_off(rr, 0)) = make_float4(r1[0], r1[1], r1[2], r1[3]);
+                *(float4 *)(reg1 + sw128_off(rr, 1)) = make_float4(r1[4], r1[5], r1[6], r1[7]);
+            }
+            fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
+            mbar_arrive(&a_full[ab]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+#endif  // __CUDACC__
+
+}  // namespace tc
+}  // namespace rp

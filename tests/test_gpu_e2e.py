@@ -312,6 +312,7 @@ def test_pruning_does_not_change_results(cfg, monkeypatch):
     o = _options(2500, shift=c["shift"])
     monkeypatch.delenv("RP_NO_PRUNE", raising=False)
     monkeypatch.delenv("RP_NO_WAVES", raising=False)
+    monkeypatch.delenv("RP_NO_TC", raising=False)
     pruned_ctx = nv.Context(0)
     a = pruned_ctx.estimate_batch_host(variant, offs, x1, x2, d1, d2, cams, o)
     _, cnt = pruned_ctx.last_timing()
@@ -328,6 +329,18 @@ def test_pruning_does_not_change_results(cfg, monkeypatch):
         assert np.array_equal(a[1][f], w[1][f]), f
     assert np.allclose(a[1]["model_score"], w[1]["model_score"], rtol=1e-12, atol=0)
     flat_ctx.close()
+    # without the tensor-core tier (FP32 bound kernel over every model, the round-1 path): same bytes
+    monkeypatch.setenv("RP_NO_TC", "1")
+    notc_ctx = nv.Context(0)
+    t = notc_ctx.estimate_batch_host(variant, offs, x1, x2, d1, d2, cams, o)
+    _, cntt = notc_ctx.last_timing()
+    monkeypatch.delenv("RP_NO_TC")
+    assert cntt["tc_evaluated"] == 0 and cnt["tc_evaluated"] > 0 and 0 < cnt["tc_selected"] < 0.5 * cnt["hypotheses"]
+    assert a[0].tobytes() == t[0].tobytes() and a[2].tobytes() == t[2].tobytes()
+    for f in ("refinements", "iterations", "num_inliers", "inlier_ratio"):
+        assert np.array_equal(a[1][f], t[1][f]), f
+    assert np.allclose(a[1]["model_score"], t[1]["model_score"], rtol=1e-12, atol=0)
+    notc_ctx.close()
     monkeypatch.setenv("RP_NO_PRUNE", "1")
     full_ctx = nv.Context(0)
     b = full_ctx.estimate_batch_host(variant, offs, x1, x2, d1, d2, cams, o)
