@@ -32,7 +32,17 @@ enum rp_status {
     RP_ERR_INVALID = -1,   /* bad argument (null pointer, negative size, unknown variant) */
     RP_ERR_CUDA = -2,      /* CUDA runtime error; text in rp_last_error */
     RP_ERR_NO_DEVICE = -3, /* no CUDA device / wrong architecture */
-    RP_ERR_OVERFLOW = -4   /* an internal fixed-capacity list overflowed */
+    RP_ERR_OVERFLOW = -4,  /* an internal fixed-capacity list overflowed (no longer returned by the estimators: see rp_pair_status) */
+    RP_ERR_PARTIAL = -5    /* the call finished, but some pairs could not be (rp_pair_status < 0); all other outputs are valid */
+};
+
+/* per-pair status of the last rp_estimate_batch_* call (rp_pair_status).  Non-negative values are informational. */
+enum rp_pair_state {
+    RP_PAIR_OK = 0,
+    RP_PAIR_DEGENERATE = 1,    /* fewer than 3 correspondences: identity model, iterations 0 (as the reference) */
+    RP_PAIR_EVENTS_RERUN = 2,  /* bit: the pair had more LO triggers than the first pass keeps and was run again on its own */
+    RP_PAIR_CONTINUED = 4,     /* bit: early termination needed more than min_iterations + 1 iterations; run again on its own */
+    RP_PAIR_FAILED = -1        /* the pair's re-run could not be done (device memory); its outputs are void */
 };
 
 /* estimator variants (which minimal solver / Jacobian accumulator is used) */
@@ -187,6 +197,10 @@ RP_API int rp_measure_pipes(rp_ctx *ctx, double *fp64_tflops, double *fp32_tflop
  * models per call. */
 RP_API int rp_tc_count_batch(rp_ctx *ctx, int variant, int64_t n_models, const rp_model *models, int64_t n_points,
                              const double *x1, const double *x2, double sq_threshold, int64_t *certain_outliers);
+
+/* status[p] (enum rp_pair_state) of every pair of the last rp_estimate_batch_* call on ctx.  One hard pair never fails
+ * or slows down the rest of its batch: it is finished on its own and flagged here. */
+RP_API int rp_pair_status(const rp_ctx *ctx, int64_t n_pairs, int32_t *status);
 
 /* per-stage device time of the last rp_estimate_batch_* call on ctx, milliseconds (summed over chunks):
  * [0] prepare, [1] sample, [2] solve, [3] score(minimal: exact head + bound + prune + exact survivors),

@@ -14,12 +14,13 @@ SO_PATH = os.path.join(HERE, "librepose_b200.so")
 
 CALIB, CALIB_SHIFT, SHARED, VARYING = 0, 1, 2, 3
 VARIANTS = {"calib": CALIB, "calib_shift": CALIB_SHIFT, "shared": SHARED, "varying": VARYING}
+PAIR_OK, PAIR_DEGENERATE, PAIR_EVENTS_RERUN, PAIR_CONTINUED, PAIR_FAILED = 0, 1, 2, 4, -1   # enum rp_pair_state
 LOSS = {"TRIVIAL": 0, "TRUNCATED": 1, "HUBER": 2, "CAUCHY": 3, "TRUNCATED_CAUCHY": 4}
 
 EXPORTS = [
     "rp_create", "rp_destroy", "rp_last_error", "rp_default_options", "rp_launch_count",
     "rp_estimate_batch_host", "rp_estimate_batch_dev", "rp_sample_batch", "rp_sample_batch_prosac", "rp_solve_batch",
-    "rp_score_batch", "rp_refine_batch", "rp_measure_pipes", "rp_last_timing", "rp_gather_depths_dev", "rp_tc_count_batch",
+    "rp_score_batch", "rp_refine_batch", "rp_measure_pipes", "rp_last_timing", "rp_gather_depths_dev", "rp_tc_count_batch", "rp_pair_status",
 ]
 
 
@@ -116,6 +117,8 @@ def load():
                                        C.POINTER(C.c_int64), VP]
     L.rp_measure_pipes.restype = C.c_int
     L.rp_measure_pipes.argtypes = [VP, DP, DP]
+    L.rp_pair_status.restype = C.c_int
+    L.rp_pair_status.argtypes = [VP, C.c_int64, VP]
     L.rp_last_timing.restype = C.c_int
     L.rp_last_timing.argtypes = [VP, DP, C.POINTER(C.c_int64)]
     _lib = L
@@ -188,6 +191,12 @@ class Context:
         cn = (C.c_int64 * 16)()
         self._call(self._lib.rp_last_timing, self._h, ms, cn)
         return dict(zip(TIMING_KEYS, list(ms))), dict(zip(COUNTER_KEYS, list(cn)))
+
+    def pair_status(self, n_pairs):
+        """rp_pair_state of every pair of the last estimate call (0 ok, 1 degenerate, bits 2 / 4 re-run, -1 failed)."""
+        out = np.zeros(n_pairs, dtype=np.int32)
+        self._call(self._lib.rp_pair_status, self._h, n_pairs, _ptr(out))
+        return out
 
     def measure_pipes(self):
         a, b = C.c_double(0), C.c_double(0)

@@ -50,11 +50,14 @@ enum { B_OFFS, B_PAIRS, B_PTS64, B_PTS32, B_BEAR, B_SAMPLES, B_MODELS, B_HYPITER
        // second staging set (double buffering of the host path)
        B_MASK_B, B_IN_X1_B, B_IN_X2_B, B_IN_D1_B, B_IN_D2_B, B_IN_CAMS_B, B_TMP0_B, B_TMP1_B,
        // tensor-core tier: per-point feature rows, per-model outlier counts, survivor lists
-       B_FEAT, B_TCOUT, B_TCLIST, B_TCLISTCNT, B_TCLISTPFX, B_PAIRCNT, B_TCPFX, B_NBUF };
+       B_FEAT, B_TCOUT, B_TCLIST, B_TCLISTCNT, B_TCLISTPFX, B_PAIRCNT, B_TCPFX,
+       // per-pair flags; re-run sub-batches (event-list overflow, early termination that needs more iterations)
+       B_PAIRFLAGS, B_SUB_IDX, B_SUB_SRC, B_SUB_DST, B_SUB_X1, B_SUB_X2, B_SUB_D1, B_SUB_D2, B_SUB_CAMS, B_SUB_MODELS,
+       B_SUB_STATS, B_SUB_MASK, B_NBUF };
 
 // device scalars living in B_SCALARS
 struct Scalars {
-    int n_items, n_lo_items, n_one_items, n_prob, n_pairs_scalar, overflow, need_more, n_first_items;
+    int n_items, n_lo_items, n_one_items, n_prob, n_pairs_scalar, any_flag, reserved0, n_first_items;
     int n_surv_items, bound_work, lm_work, score_work;  // *_work: counters the persistent kernels draw work from
     unsigned long long point_scores, lm_iters, n_survivors, evaluated_ps;
     long long n_hyp;
@@ -84,6 +87,8 @@ struct rp_ctx {
     bool waves = true;  // survivors of the prune scored in waves (RP_NO_WAVES=1: all at once)
     bool tc = true;     // tensor-core count tier in front of the FP32 bound kernel (RP_NO_TC=1: off)
     void *encode_tiled = nullptr;  // cuTensorMapEncodeTiled (driver entry point, resolved at rp_create)
+    int ev_cap0 = EV;   // event-list capacity of the first pass (RP_EV_CAP: small values exercise the re-run path)
+    std::vector<int32_t> pair_status;  // per pair of the last rp_estimate_batch_* call (rp_pair_status)
     int occ_score[4] = {0}, occ_lm[4] = {0};
 };
 
@@ -251,8 +256,10 @@ struct ChunkIO {
     unsigned char *masks_out;        // device [n_points]
 };
 
-int run_chunk(rp_ctx *ctx, int variant, const rp_options &opt, const ChunkIO &io, int iters, bool *need_more,
-              cudaStream_t st) {
+// One pass over a chunk.  `flags` (host, [n_pairs]) receives PAIR_FLAG_* per pair: a flagged pair's outputs are void and
+// the caller runs it again with a larger `ev_cap` / more iterations (estimate_impl).
+int run_chunk(rp_ctx *ctx, int variant, const rp_options &opt, const ChunkIO &io, int iters, int ev_cap,
+              std::vector<int> &flags, cudaStream_t st) {
     const int P = io.n_pairs;
     const long long N = io.n_points;
     const bool pose = variant == RP_CALIB || variant == RP_CALIB_SHIFT;
@@ -275,14 +282,15 @@ int run_chunk(rp_ctx *ctx, int variant, const rp_options &opt, const ChunkIO &io
     CK(B[B_SEGCNT].reserve(sizeof(int) * (size_t)P * nseg));
     CK(B[B_ITEMPFX].reserve(sizeof(int) * ((size_t)P * nseg + 1)));
     CK(B[B_SCALARS].reserve(sizeof(Scalars)));
-    CK(B[B_EVENTS].reserve(sizeof(int) * (size_t)P * EV));
+    CK(B[B_EVENTS].reserve(sizeof(int) * (size_t)P * ev_cap));
     CK(B[B_NEVENTS].reserve(sizeof(int) * P));
-    CK(B[B_LOMODELS].reserve(sizeof(Model) * (size_t)P * EV));
-    CK(B[B_LOOFEV].reserve(sizeof(int) * (size_t)P * EV));
+    CK(B[B_LOMODELS].reserve(sizeof(Model) * (size_t)P * ev_cap));
+    CK(B[B_LOOFEV].reserve(sizeof(int) * (size_t)P * ev_cap));
     CK(B[B_LOCOUNT].reserve(sizeof(int) * P));
-    CK(B[B_PROBLIST].reserve(sizeof(int) * (size_t)P * EV));
-    CK(B[B_LOSCORE].reserve(sizeof(double) * (size_t)P * EV));
-    CK(B[B_LOCNT].reserve(sizeof(int) * (size_t)P * EV));
+    CK(B[B_PROBLIST].reserve(sizeof(int) * (size_t)P * ev_cap));
+    CK(B[B_LOSCORE].reserve(sizeof(double) * (size_t)P * ev_cap));
+    CK(B[B_PAIRFLAGS].reserve(sizeof(int) * P));
+    CK(B[B_LOCNT].reserve(sizeof(int) * (size_t)P * ev_cap));
     CK(B[B_LOITEMPFX].reserve(sizeof(int) * (P + 1)));
     CK(B[B_BEST].reserve(sizeof(Model) * P));
     CK(B[B_FINSTART].reserve(sizeof(Model) * P));
@@ -481,11 +489,12 @@ int run_chunk(rp_ctx *ctx, int variant, const rp_options &opt, const ChunkIO &io
     {
         ScanArgs a;
         a.n_pairs = P; a.nseg = nseg; a.seg_count = seg_count; a.score = score; a.count = count;
-        a.events = B[B_EVENTS].as<int>(); a.n_events = B[B_NEVENTS].as<int>(); a.overflow = &sc->overflow;
+        a.events = B[B_EVENTS].as<int>(); a.n_events = B[B_NEVENTS].as<int>(); a.ev_cap = ev_cap;
+        a.pair_flags = B[B_PAIRFLAGS].as<int>(); a.any_flag = &sc->any_flag;
         scan_kernel<<<cdiv((long long)P * 32, 256), 256, 0, st>>>(a);
         LAUNCHED();
         LoPrepArgs l;
-        l.n_pairs = P; l.nseg = nseg; l.events = a.events; l.n_events = a.n_events; l.hyp_iter = hyp_iter;
+        l.n_pairs = P; l.nseg = nseg; l.events = a.events; l.n_events = a.n_events; l.hyp_iter = hyp_iter; l.ev_cap = ev_cap;
         l.models = models; l.lo_models = B[B_LOMODELS].as<Model>(); l.lo_of_event = B[B_LOOFEV].as<int>();
         l.lo_count = B[B_LOCOUNT].as<int>(); l.prob_list = B[B_PROBLIST].as<int>(); l.n_prob = &sc->n_prob;
         lo_prepare_kernel<<<cdiv(P, 128), 128, 0, st>>>(l);
@@ -501,7 +510,7 @@ int run_chunk(rp_ctx *ctx, int variant, const rp_options &opt, const ChunkIO &io
     la.loss_scale_override = -1.0; la.scale_reproj_override = -1.0;
     la.lm_iters = &sc->lm_iters;
     {
-        la.prob_list = B[B_PROBLIST].as<int>(); la.n_prob = &sc->n_prob; la.prob_per_pair = EV;
+        la.prob_list = B[B_PROBLIST].as<int>(); la.n_prob = &sc->n_prob; la.prob_per_pair = ev_cap;
         la.models = B[B_LOMODELS].as<Model>(); la.use_final = 0;
         int rc = launch_lm(ctx, variant, la, (long long)P * 8, st);
         if (rc) return rc;
@@ -513,7 +522,7 @@ int run_chunk(rp_ctx *ctx, int variant, const rp_options &opt, const ChunkIO &io
         LAUNCHED();
         ScoreArgs s2 = sa;
         s2.slot_list = nullptr; s2.list_stride = 0;
-        s2.n_groups = P; s2.grp_stride = EV; s2.grp_per_pair = 1; s2.grp_cnt = B[B_LOCOUNT].as<int>();
+        s2.n_groups = P; s2.grp_stride = ev_cap; s2.grp_per_pair = 1; s2.grp_cnt = B[B_LOCOUNT].as<int>();
         s2.item_prefix = B[B_LOITEMPFX].as<int>(); s2.n_items = &sc->n_lo_items; s2.models = B[B_LOMODELS].as<Model>();
         s2.score = B[B_LOSCORE].as<double>(); s2.count = B[B_LOCNT].as<int>(); s2.point_scores = nullptr;
         int rc = launch_score(ctx, pose, false, s2, st);
@@ -522,7 +531,7 @@ int run_chunk(rp_ctx *ctx, int variant, const rp_options &opt, const ChunkIO &io
         m.n_pairs = P; m.nseg = nseg; m.iters = iters; m.pairs = pairs; m.events = B[B_EVENTS].as<int>();
         m.min_iterations = opt.min_iterations; m.max_iterations = opt.max_iterations;
         m.dyn_num_trials_mult = opt.dyn_num_trials_mult; m.log_prob_missing = log(1.0 - opt.success_prob);
-        m.hyp_iter = hyp_iter; m.need_more = &sc->need_more;
+        m.hyp_iter = hyp_iter; m.ev_cap = ev_cap; m.pair_flags = B[B_PAIRFLAGS].as<int>(); m.any_flag = &sc->any_flag;
         m.n_events = B[B_NEVENTS].as<int>(); m.lo_of_event = B[B_LOOFEV].as<int>(); m.score = score; m.count = count;
         m.models = models; m.lo_score = B[B_LOSCORE].as<double>(); m.lo_count_inl = B[B_LOCNT].as<int>();
         m.lo_models = B[B_LOMODELS].as<Model>(); m.lo_count = B[B_LOCOUNT].as<int>();
@@ -606,16 +615,21 @@ int run_chunk(rp_ctx *ctx, int variant, const rp_options &opt, const ChunkIO &io
     ctx->last_cnt[10] += (int64_t)h_sc.lm_flops;
     ctx->last_cnt[5] += ctx->prune ? (int64_t)h_sc.n_survivors + std::min<int64_t>(h_sc.n_hyp, (int64_t)P * ctx->head) : h_sc.n_hyp;
     ctx->last_cnt[7] = ctx->head;
-    if (h_sc.overflow) return fail(ctx, RP_ERR_OVERFLOW, "trigger event list overflowed (EV)");
-    *need_more = h_sc.need_more != 0;
+    flags.assign((size_t)P, 0);
+    if (h_sc.any_flag) {
+        CK(cudaMemcpyAsync(flags.data(), B[B_PAIRFLAGS].p, sizeof(int) * (size_t)P, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
     return RP_OK;
 }
 
-size_t bytes_per_pair(int iters, long long avg_points) {
+size_t bytes_per_pair(int iters, long long avg_points, int ev_cap = EV) {
     const int nseg = std::max(1, cdiv(iters, SEG));
     const size_t slots_pp = (size_t)nseg * 4 * SEG;
-    return slots_pp * (sizeof(Model) + 4 + 8 + 4 + 12) + (size_t)iters * 12 + (size_t)EV * (sizeof(Model) + 24) +
-           (size_t)avg_points * (sizeof(Pt64) + 32 + sizeof(Bear) + 1) + 1024;
+    // per slot: model, hyp_iter, score, count, ub, lb, survivor list, tensor-core count + list; per correspondence:
+    // FP64 / FP32 / interleaved copies, bearings, mask, 128-byte feature row
+    return slots_pp * (sizeof(Model) + 4 + 8 + 4 + 12 + 8) + (size_t)iters * 12 + (size_t)ev_cap * (sizeof(Model) + 24) +
+           (size_t)avg_points * (sizeof(Pt64) + 32 + sizeof(Bear) + 1 + 128) + 1024;
 }
 
 int check_common(rp_ctx *ctx, int variant, int64_t n_pairs, const int64_t *offsets, const rp_options *opt) {
@@ -626,6 +640,115 @@ int check_common(rp_ctx *ctx, int variant, int64_t n_pairs, const int64_t *offse
     for (int64_t p = 0; p < n_pairs; ++p)
         if (offsets[p + 1] < offsets[p] || offsets[p + 1] - offsets[p] >= (1 << 24))
             return fail(ctx, RP_ERR_INVALID, "offsets must be non-decreasing, at most 2^24-1 correspondences per pair");
+    return RP_OK;
+}
+
+// Pairs of a chunk whose first pass was flagged — more trigger events than the list holds, or (early termination) more
+// iterations needed than were generated — are gathered into compact sub-batches and run again on their own with the
+// limits raised (iterations x4 up to max_iterations, event capacity x8), until no flag is left.  Everybody else's
+// results are untouched; what a hard pair costs is bounded by ~1.33x what the reference spends on that pair.  A
+// sub-batch that cannot be run (out of device memory) marks its pairs RP_PAIR_FAILED instead of failing the call.
+int rerun_flagged(rp_ctx *ctx, int variant, const rp_options &opt, const ChunkIO &io, const std::vector<long long> &rel,
+                  const std::vector<int> &flags0, int iters0, int64_t p0, cudaStream_t st) {
+    DevBuf *B = ctx->buf;
+    const bool pose = variant == RP_CALIB || variant == RP_CALIB_SHIFT;
+    std::vector<int> todo;
+    for (int i = 0; i < io.n_pairs; ++i)
+        if (flags0[(size_t)i]) todo.push_back(i);
+    int iters = iters0, ev_cap = ctx->ev_cap0;
+    std::vector<int> flags_of((size_t)io.n_pairs, 0);
+    for (int i : todo) flags_of[(size_t)i] = flags0[(size_t)i];
+    while (!todo.empty()) {
+        bool any_more = false, any_ovf = false;
+        for (int i : todo) {
+            any_more |= (flags_of[(size_t)i] & PAIR_FLAG_NEED_MORE) != 0;
+            any_ovf |= (flags_of[(size_t)i] & PAIR_FLAG_OVERFLOW) != 0;
+            ctx->pair_status[(size_t)(p0 + i)] |= ((flags_of[(size_t)i] & PAIR_FLAG_NEED_MORE) ? RP_PAIR_CONTINUED : 0) |
+                                                  ((flags_of[(size_t)i] & PAIR_FLAG_OVERFLOW) ? RP_PAIR_EVENTS_RERUN : 0);
+        }
+        if (any_more) iters = (int)std::min<int64_t>(opt.max_iterations, (int64_t)iters * 4);
+        const int slots_pp = std::max(1, cdiv(iters, SEG)) * 4 * SEG;
+        if (any_ovf) ev_cap = (int)std::min<int64_t>((int64_t)ev_cap * 8, slots_pp);
+        std::vector<int> next;
+        size_t pos = 0;
+        while (pos < todo.size()) {
+            // sub-batch [pos, end): as many pairs as the workspace budget holds at these limits
+            size_t end = pos;
+            size_t bytes = 0;
+            long long npts = 0;
+            while (end < todo.size()) {
+                const long long n = rel[(size_t)todo[end] + 1] - rel[(size_t)todo[end]];
+                const size_t b = bytes_per_pair(iters, n, ev_cap);
+                if (end > pos && bytes + b > ctx->workspace_budget) break;
+                bytes += b;
+                npts += n;
+                ++end;
+            }
+            const int S = (int)(end - pos);
+            std::vector<int> idx((size_t)S);
+            std::vector<long long> src((size_t)S), dst((size_t)S + 1, 0);
+            for (int j = 0; j < S; ++j) {
+                idx[(size_t)j] = todo[pos + j];
+                src[(size_t)j] = rel[(size_t)idx[(size_t)j]];
+                dst[(size_t)j + 1] = dst[(size_t)j] + (rel[(size_t)idx[(size_t)j] + 1] - rel[(size_t)idx[(size_t)j]]);
+            }
+            const size_t nn = (size_t)std::max<long long>(npts, 1);
+            int rc = RP_OK;
+            std::vector<int> flags;
+            do {  // single pass; `break` = this sub-batch failed
+                cudaError_t e = cudaSuccess;
+                (void)e;
+                if ((e = B[B_SUB_IDX].reserve(sizeof(int) * S)) || (e = B[B_SUB_SRC].reserve(8 * (size_t)S)) ||
+                    (e = B[B_SUB_DST].reserve(8 * ((size_t)S + 1))) || (e = B[B_SUB_X1].reserve(16 * nn)) ||
+                    (e = B[B_SUB_X2].reserve(16 * nn)) || (e = B[B_SUB_D1].reserve(8 * nn)) || (e = B[B_SUB_D2].reserve(8 * nn)) ||
+                    (e = B[B_SUB_CAMS].reserve(64 * (size_t)S)) || (e = B[B_SUB_MODELS].reserve(sizeof(Model) * S)) ||
+                    (e = B[B_SUB_STATS].reserve(sizeof(rp_stats) * S)) || (e = B[B_SUB_MASK].reserve(nn))) {
+                    rc = RP_ERR_CUDA;
+                    break;
+                }
+                CK(cudaMemcpyAsync(B[B_SUB_IDX].p, idx.data(), sizeof(int) * S, cudaMemcpyHostToDevice, st));
+                CK(cudaMemcpyAsync(B[B_SUB_SRC].p, src.data(), 8 * (size_t)S, cudaMemcpyHostToDevice, st));
+                CK(cudaMemcpyAsync(B[B_SUB_DST].p, dst.data(), 8 * ((size_t)S + 1), cudaMemcpyHostToDevice, st));
+                SubBatchArgs g;
+                g.n_sub = S; g.pair_idx = B[B_SUB_IDX].as<int>(); g.src_off = B[B_SUB_SRC].as<long long>();
+                g.dst_off = B[B_SUB_DST].as<long long>();
+                g.x1 = io.x1; g.x2 = io.x2; g.d1 = io.d1; g.d2 = io.d2; g.cams = pose ? io.cams : nullptr;
+                g.sx1 = B[B_SUB_X1].as<double>(); g.sx2 = B[B_SUB_X2].as<double>(); g.sd1 = B[B_SUB_D1].as<double>();
+                g.sd2 = B[B_SUB_D2].as<double>(); g.scams = B[B_SUB_CAMS].as<double>();
+                g.models = io.models_out; g.stats = io.stats_out; g.masks = io.masks_out;
+                g.smodels = B[B_SUB_MODELS].as<Model>(); g.sstats = B[B_SUB_STATS].as<rp_stats>();
+                g.smasks = B[B_SUB_MASK].as<unsigned char>();
+                gather_pairs_kernel<<<S, 256, 0, st>>>(g);
+                LAUNCHED();
+                CK(cudaStreamSynchronize(st));  // idx / src / dst are stack-lifetime host buffers
+                ChunkIO sub;
+                sub.n_pairs = S; sub.n_points = npts; sub.h_offsets_rel = dst.data();
+                sub.x1 = g.sx1; sub.x2 = g.sx2; sub.d1 = g.sd1; sub.d2 = g.sd2; sub.cams = pose ? g.scams : nullptr;
+                sub.models_out = B[B_SUB_MODELS].as<Model>(); sub.stats_out = B[B_SUB_STATS].as<rp_stats>();
+                sub.masks_out = B[B_SUB_MASK].as<unsigned char>();
+                rc = run_chunk(ctx, variant, opt, sub, iters, ev_cap, flags, st);
+                if (rc) break;
+                scatter_pairs_kernel<<<S, 256, 0, st>>>(g);
+                LAUNCHED();
+                CK(cudaStreamSynchronize(st));
+            } while (false);
+            if (rc) {
+                // isolate the failure: these pairs keep their (void) first-pass outputs and are reported; a failed
+                // allocation leaves the CUDA context usable
+                (void)cudaGetLastError();
+                for (int j = 0; j < S; ++j) ctx->pair_status[(size_t)(p0 + idx[(size_t)j])] = RP_PAIR_FAILED;
+            } else {
+                for (int j = 0; j < S; ++j) {
+                    int f = flags[(size_t)j];
+                    if (iters >= opt.max_iterations) f &= ~PAIR_FLAG_NEED_MORE;  // cannot happen: the merge stops at max_iterations
+                    flags_of[(size_t)idx[(size_t)j]] = f;
+                    if (f) next.push_back(idx[(size_t)j]);
+                }
+            }
+            pos = end;
+        }
+        todo.swap(next);
+    }
     return RP_OK;
 }
 
@@ -642,12 +765,17 @@ int estimate_impl(rp_ctx *ctx, int variant, int64_t n_pairs, const int64_t *offs
     if (pose && !cams && n_pairs > 0) return fail(ctx, RP_ERR_INVALID, "calibrated variants need cams");
     memset(ctx->last_ms, 0, sizeof ctx->last_ms);
     memset(ctx->last_cnt, 0, sizeof ctx->last_cnt);
+    ctx->pair_status.assign((size_t)n_pairs, RP_PAIR_OK);
     if (n_pairs == 0) return RP_OK;
     const long long Ntot = offsets[n_pairs] - offsets[0];
-    const int plan_iters = opt.min_iterations < opt.max_iterations
-                               ? (int)std::min<int64_t>(opt.max_iterations, 16 * (opt.min_iterations + 1))
-                               : (int)opt.max_iterations;
-    const size_t bpp = bytes_per_pair(plan_iters, Ntot / n_pairs + 1);
+    // Early termination (min_iterations < max_iterations): the reference stops at the first it > min_iterations with
+    // it > dynamic_max_iter.  The first pass generates min_iterations + 1 iterations for every pair and the merge
+    // kernel replays the stop rule exactly; only the pairs that would have kept going are run again, on their own,
+    // with 4x more iterations (same seed => same prefix), see rerun_flagged below.
+    const int iters0 = opt.min_iterations < opt.max_iterations
+                           ? (int)std::min<int64_t>(opt.max_iterations, opt.min_iterations + 1)
+                           : (int)opt.max_iterations;
+    const size_t bpp = bytes_per_pair(iters0, Ntot / n_pairs + 1, ctx->ev_cap0);
     int64_t chunk = (int64_t)std::max<size_t>(1, ctx->workspace_budget / bpp);
     chunk = std::min<int64_t>(chunk, 32768);
     std::vector<long long> rel;
@@ -729,19 +857,12 @@ int estimate_impl(rp_ctx *ctx, int variant, int64_t n_pairs, const int64_t *offs
             io.cams = pose ? cams + 8 * p0 : nullptr;
             io.models_out = (Model *)models + p0; io.stats_out = stats + p0; io.masks_out = masks + o0;
         }
-        // Early termination (min_iterations < max_iterations): the reference stops at the first
-        // it > min_iterations with it > dynamic_max_iter.  Generate min_iterations+1 iterations, let
-        // the merge kernel replay the stop rule exactly, and only if some pair would have kept going
-        // regenerate the chunk with 4x more iterations (same seeds => same prefix).
-        int iters = (int)opt.max_iterations;
-        if (opt.min_iterations < opt.max_iterations) iters = (int)std::min<int64_t>(opt.max_iterations, opt.min_iterations + 1);
-        for (;;) {
-            bool need_more = false;
-            rc = run_chunk(ctx, variant, opt, io, iters, &need_more, st);
-            if (rc) return rc;
-            if (!need_more || iters >= opt.max_iterations) break;
-            iters = (int)std::min<int64_t>(opt.max_iterations, (int64_t)iters * 4);
-        }
+        std::vector<int> flags;
+        rc = run_chunk(ctx, variant, opt, io, iters0, ctx->ev_cap0, flags, st);
+        if (rc) return rc;
+        for (int i = 0; i < P; ++i) ctx->pair_status[(size_t)(p0 + i)] = rel[i + 1] - rel[i] < 3 ? RP_PAIR_DEGENERATE : RP_PAIR_OK;
+        rc = rerun_flagged(ctx, variant, opt, io, rel, flags, iters0, p0, st);
+        if (rc) return rc;
         if (host_io) {
             // run_chunk returned after synchronising the compute stream: results are complete
             float ms = 0.f;
@@ -763,6 +884,8 @@ int estimate_impl(rp_ctx *ctx, int variant, int64_t n_pairs, const int64_t *offs
             if (cudaEventElapsedTime(&ms, d2h_begin[par], comp_done[par]) == cudaSuccess) ctx->last_ms[10] += ms;
         }
     }
+    for (int32_t v : ctx->pair_status)
+        if (v < 0) return fail(ctx, RP_ERR_PARTIAL, "some pairs could not be finished (rp_pair_status); all other outputs are valid");
     return RP_OK;
 }
 
@@ -802,6 +925,7 @@ int rp_create(int device, rp_ctx **out) {
     if (const char *np = getenv("RP_NO_PRUNE")) ctx->prune = !(np[0] == '1');
     if (const char *nw = getenv("RP_NO_WAVES")) ctx->waves = !(nw[0] == '1');
     if (const char *nt = getenv("RP_NO_TC")) ctx->tc = !(nt[0] == '1');
+    if (const char *ec = getenv("RP_EV_CAP")) { const int v = atoi(ec); if (v >= 1 && v <= EV) ctx->ev_cap0 = v; }
     {
         cudaDriverEntryPointQueryResult qres;
         void *fn = nullptr;
@@ -866,6 +990,12 @@ int rp_estimate_batch_dev(rp_ctx *ctx, int variant, int64_t n_pairs, const int64
         return fail(ctx, RP_ERR_INVALID, "null data pointer");
     return estimate_impl(ctx, variant, n_pairs, offsets, x1, x2, d1, d2, cams, opt, models, stats, masks, false,
                          stream ? (cudaStream_t)stream : ctx->stream);
+}
+
+int rp_pair_status(const rp_ctx *ctx, int64_t n_pairs, int32_t *status) {
+    if (!ctx || n_pairs < 0 || (n_pairs > 0 && !status)) return RP_ERR_INVALID;
+    for (int64_t i = 0; i < n_pairs; ++i) status[i] = (size_t)i < ctx->pair_status.size() ? ctx->pair_status[(size_t)i] : RP_PAIR_FAILED;
+    return RP_OK;
 }
 
 int rp_last_timing(const rp_ctx *ctx, double *ms16, int64_t *counters16) {

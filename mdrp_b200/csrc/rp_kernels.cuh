@@ -1286,14 +1286,19 @@ __global__ void wave_select_kernel(WaveArgs a) {
 // model "triggers" when it has more inliers than every earlier minimal model or a lower MSAC
 // score than every earlier one (running max / running min, strict).  One warp per pair walks the
 // pair's slots in order and emits the triggering slots.
+constexpr int PAIR_FLAG_OVERFLOW = 1;   // more trigger events than the list holds: outputs of the pair are void
+constexpr int PAIR_FLAG_NEED_MORE = 2;  // early termination: neither stopped nor at max_iterations within the generated iterations
+
 struct ScanArgs {
     int n_pairs, nseg;
     const int *seg_count;
     const double *score;
     const int *count;
-    int *events;      // [n_pairs*EV] slot of each trigger, in order
+    int *events;      // [n_pairs*ev_cap] slot of each trigger, in order
     int *n_events;    // [n_pairs]
-    int *overflow;
+    int ev_cap;       // capacity of a pair's event list (EV; larger when an overflowing pair is re-run)
+    int *pair_flags;  // [n_pairs] PAIR_FLAG_OVERFLOW is set for a pair with more triggers than ev_cap
+    int *any_flag;    // scalar: some pair was flagged
 };
 
 __global__ void scan_kernel(ScanArgs a) {
@@ -1330,15 +1335,18 @@ __global__ void scan_kernel(ScanArgs a) {
             const unsigned m = __ballot_sync(0xffffffffu, trig);
             if (trig) {
                 const int pos = nev + __popc(m & ((1u << lane) - 1));
-                if (pos < EV) a.events[warp * EV + pos] = (int)(slot0 + h - (size_t)warp * a.nseg * (4 * SEG));
-                else *a.overflow = 1;
+                if (pos < a.ev_cap) a.events[(size_t)warp * a.ev_cap + pos] = (int)(slot0 + h - (size_t)warp * a.nseg * (4 * SEG));
             }
             nev += __popc(m);
             best_cnt = max(best_cnt, __shfl_sync(0xffffffffu, cmax, 31));
             best_score = fmin(best_score, __shfl_sync(0xffffffffu, smin, 31));
         }
     }
-    if (lane == 0) a.n_events[warp] = min(nev, EV);
+    if (lane == 0) {
+        a.n_events[warp] = min(nev, a.ev_cap);
+        a.pair_flags[warp] = nev > a.ev_cap ? PAIR_FLAG_OVERFLOW : 0;
+        if (nev > a.ev_cap) *a.any_flag = 1;
+    }
 }
 
 // LO problem list: the LO of an iteration starts from the LAST triggering model of that
@@ -1348,8 +1356,9 @@ struct LoPrepArgs {
     const int *events, *n_events;
     const int *hyp_iter;
     const Model *models;
-    Model *lo_models;   // [n_pairs*EV]
-    int *lo_of_event;   // [n_pairs*EV] index of the LO problem started by this event or -1
+    int ev_cap;
+    Model *lo_models;   // [n_pairs*ev_cap]
+    int *lo_of_event;   // [n_pairs*ev_cap] index of the LO problem started by this event or -1
     int *lo_count;      // [n_pairs]
     int *prob_list;     // compact list of lo_models indices
     int *n_prob;
@@ -1360,23 +1369,24 @@ __global__ void lo_prepare_kernel(LoPrepArgs a) {
     if (pair >= a.n_pairs) return;
     const size_t pslot = (size_t)pair * a.nseg * (4 * SEG);
     const int nev = a.n_events[pair];
+    const size_t eb = (size_t)pair * a.ev_cap;
     int nlo = 0;
     for (int i = 0; i < nev; ++i) {
-        const int ev = a.events[pair * EV + i];
+        const int ev = a.events[eb + i];
         const int it = a.hyp_iter[pslot + ev];
-        const bool last = (i + 1 == nev) || a.hyp_iter[pslot + a.events[pair * EV + i + 1]] != it;
+        const bool last = (i + 1 == nev) || a.hyp_iter[pslot + a.events[eb + i + 1]] != it;
         if (last) {
-            a.lo_models[pair * EV + nlo] = a.models[pslot + ev];
-            a.lo_of_event[pair * EV + i] = nlo;
+            a.lo_models[eb + nlo] = a.models[pslot + ev];
+            a.lo_of_event[eb + i] = nlo;
             ++nlo;
         } else {
-            a.lo_of_event[pair * EV + i] = -1;
+            a.lo_of_event[eb + i] = -1;
         }
     }
     a.lo_count[pair] = nlo;
     if (nlo) {
         const int p0 = atomicAdd(a.n_prob, nlo);
-        for (int j = 0; j < nlo; ++j) a.prob_list[p0 + j] = pair * EV + j;
+        for (int j = 0; j < nlo; ++j) a.prob_list[p0 + j] = pair * a.ev_cap + j;
     }
 }
 
@@ -1394,14 +1404,16 @@ struct MergeArgs {
     const double *score;     // minimal slots
     const int *count;
     const Model *models;
-    const double *lo_score;  // [n_pairs*EV]
+    int ev_cap;
+    const double *lo_score;  // [n_pairs*ev_cap]
     const int *lo_count_inl;
     const Model *lo_models;
     const int *lo_count;     // number of LO problems per pair
     Model *best;             // [n_pairs]
     rp_stats *stats;         // [n_pairs]
     Model *final_start;      // [n_pairs] copy of best (start of the final LO)
-    int *need_more;          // set when a pair neither stopped nor reached max_iterations
+    int *pair_flags;         // [n_pairs] |= PAIR_FLAG_NEED_MORE when a pair neither stopped nor reached max_iterations
+    int *any_flag;
 };
 
 __global__ void merge_kernel(MergeArgs a) {
@@ -1414,6 +1426,7 @@ __global__ void merge_kernel(MergeArgs a) {
     if (pp.valid) {
         const size_t pslot = (size_t)pair * a.nseg * (4 * SEG);
         const int nev = a.n_events[pair];
+        const size_t eb = (size_t)pair * a.ev_cap;
         // the loop of ransac<>() breaks at the first it > min_iterations with it > dynamic_max_iter;
         // dynamic_max_iter only changes after an LO, so the break point is known between events.  The test
         // runs at the top of an iteration: after an LO in iteration it_prev the loop cannot stop before
@@ -1421,7 +1434,7 @@ __global__ void merge_kernel(MergeArgs a) {
         double dyn_max_iter = (double)a.max_iterations;
         long long stop_it = -1, it_prev = -1;
         for (int i = 0; i < nev; ++i) {
-            const int ev = a.events[pair * EV + i];
+            const int ev = a.events[eb + i];
             const long long it_e = a.hyp_iter[pslot + ev];
             const long long cand = max(max(a.min_iterations + 1, (long long)floor(dyn_max_iter) + 1), it_prev + 1);
             if (cand <= it_e) { stop_it = cand; break; }
@@ -1432,14 +1445,14 @@ __global__ void merge_kernel(MergeArgs a) {
                 best = a.models[pslot + ev];
                 st.num_inliers = a.count[pslot + ev];
             }
-            const int lo = a.lo_of_event[pair * EV + i];
+            const int lo = a.lo_of_event[eb + i];
             if (lo >= 0) {
                 st.refinements++;
-                const double rs = a.lo_score[pair * EV + lo];
+                const double rs = a.lo_score[eb + lo];
                 if (rs < st.model_score) {
                     st.model_score = rs;
-                    st.num_inliers = a.lo_count_inl[pair * EV + lo];
-                    best = a.lo_models[pair * EV + lo];
+                    st.num_inliers = a.lo_count_inl[eb + lo];
+                    best = a.lo_models[eb + lo];
                 }
                 st.inlier_ratio = (double)st.num_inliers / (double)pp.n;
                 if (st.inlier_ratio >= 0.9999) dyn_max_iter = (double)a.min_iterations;
@@ -1455,7 +1468,7 @@ __global__ void merge_kernel(MergeArgs a) {
             if (cand < a.iters) stop_it = cand;                             // stopped inside what we generated
             else if (a.iters >= a.max_iterations) stop_it = a.max_iterations;  // loop ran to the end
             else if (cand == a.iters) stop_it = cand;                        // would stop exactly at the next it
-            else { stop_it = a.iters; *a.need_more = 1; }
+            else { stop_it = a.iters; a.pair_flags[pair] |= PAIR_FLAG_NEED_MORE; *a.any_flag = 1; }
         }
         st.iterations = stop_it;
     }
@@ -1504,6 +1517,45 @@ __global__ void finalize_kernel(int n_pairs, int variant, const PairParams *pair
     if (variant == RP_SHARED || variant == RP_VARYING) {
         best[pair].f1 *= pairs[pair].nscale;
         best[pair].f2 *= pairs[pair].nscale;
+    }
+}
+
+// Re-run sub-batches (estimate_impl): pairs that overflowed their event list or need more iterations are gathered
+// into a compact ragged batch, run again with larger limits, and their results scattered back.  Block per pair.
+struct SubBatchArgs {
+    int n_sub;
+    const int *pair_idx;          // [n_sub] pair index inside the chunk
+    const long long *src_off;     // [n_sub] first correspondence of the pair in the chunk
+    const long long *dst_off;     // [n_sub + 1] offsets of the compact batch
+    const double *x1, *x2, *d1, *d2, *cams;   // chunk inputs (cams may be null)
+    double *sx1, *sx2, *sd1, *sd2, *scams;    // compact inputs
+    Model *models; rp_stats *stats; unsigned char *masks;        // chunk outputs
+    const Model *smodels; const rp_stats *sstats; const unsigned char *smasks;   // compact outputs
+};
+__global__ void gather_pairs_kernel(SubBatchArgs a) {
+    const int j = blockIdx.x;
+    if (j >= a.n_sub) return;
+    const long long so = a.src_off[j], d0 = a.dst_off[j];
+    const int n = (int)(a.dst_off[j + 1] - d0);
+    for (int i = threadIdx.x; i < 2 * n; i += blockDim.x) {
+        a.sx1[2 * d0 + i] = a.x1[2 * so + i];
+        a.sx2[2 * d0 + i] = a.x2[2 * so + i];
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        a.sd1[d0 + i] = a.d1[so + i];
+        a.sd2[d0 + i] = a.d2[so + i];
+    }
+    if (a.cams && threadIdx.x < 8) a.scams[8 * (size_t)j + threadIdx.x] = a.cams[8 * (size_t)a.pair_idx[j] + threadIdx.x];
+}
+__global__ void scatter_pairs_kernel(SubBatchArgs a) {
+    const int j = blockIdx.x;
+    if (j >= a.n_sub) return;
+    const long long so = a.src_off[j], d0 = a.dst_off[j];
+    const int n = (int)(a.dst_off[j + 1] - d0);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) a.masks[so + i] = a.smasks[d0 + i];
+    if (threadIdx.x == 0) {
+        a.models[a.pair_idx[j]] = a.smodels[j];
+        a.stats[a.pair_idx[j]] = a.sstats[j];
     }
 }
 
