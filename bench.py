@@ -298,14 +298,30 @@ def main():
     assert ninl > 0.5 * c["n"] * (1 - c["outlier_ratio"]), f"implausible result (mean inliers {ninl})"
 
     # ---- e2e: host buffers through the C ABI, copies inside the timed region --------------------------
-    for _ in range(max(1, min(args.warmup, 3))):
+    # At N > 1 the job is not done until rank 0 holds everybody's results: the gather of the sharded product path
+    # (mdrp_b200.sharding.gather_results: preallocated byte tensors over NCCL / NVLink, one read-back on rank 0) is
+    # inside the timed region.
+    from mdrp_b200 import sharding
+    np_models = h_models.numpy().view(nv.MODEL_DTYPE).reshape(-1)
+    np_stats = h_stats.numpy().view(nv.STATS_DTYPE).reshape(-1)
+    np_masks = h_masks.numpy()[:N]
+    gathered = [None]
+
+    def step_e2e():
         step_host()
+        if world > 1:
+            gathered[0] = sharding.gather_results(h_models, h_stats, h_masks[:N], rank, world, device=dev)
+
+    for _ in range(max(1, min(args.warmup, 3))):
+        step_e2e()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        step_host()
+        step_e2e()
     torch.cuda.synchronize()
     e2e_elapsed = time.perf_counter() - t0
+    if world > 1 and rank == 0:
+        assert len(gathered[0][0]) == world * P and gathered[0][0][:P].tobytes() == np_models.tobytes()
     t = torch.tensor([e2e_elapsed], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -313,71 +329,73 @@ def main():
     assert torch.equal(h_stats.to(dev), d_stats), "host-buffer and device-buffer paths disagree"
     h2d = N * 48 + (P * 64 if host_cams is not None else 0) + (P + 1) * 8
     d2h = P * (96 + 40) + N
+    gather_bytes = (world - 1) * d2h if world > 1 else 0   # what rank 0 receives over NVLink and reads back per step
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel -------------------------------------------------------------------
-    # Dominant kernel = bound_kernel (FP32 tier of the minimal-model scoring).  The headline figure is what the
-    # FP32 pipe really executed: point-scores evaluated (device counter) x 41 FP32 flop (16 FFMA + 9
-    # FMUL/FADD/FMNMX per evaluated point-score) over the kernel's own CUDA-event time, against the FP32 FMA
-    # peak measured on this device (rp_measure_pipes; MEASURED_PEAKS.json has no FP32/FP64 figure).
-    # "algorithmic" restates it in the SURVEY §8d convention (34 FP64 flop per point-score the reference would
-    # have computed, resolved or evaluated) — it can exceed 1 because the kernel abandons models early.
-    bound_s = stage_ms["bound_kernel"] / 1000.0
-    score_s = stage_ms["score_minimal"] / 1000.0
+    # ---- rooflines ---------------------------------------------------------------------------------------------
+    # Every kernel that holds > 10 % of the step gets an entry: its algorithmic work (stated in DESIGN.md §5, counted by
+    # device counters) over its own CUDA-event time, against the measured peak of the pipe that bounds it.  `roofline`
+    # (the contract's key) is the entry of the kernel with the largest share of the step.
     dev_s = stage_ms["device_total"] / 1000.0
-    ps = counters["point_scores"]
     hyps = counters["hypotheses"]
     n_chunk_launches = max(1, int(counters["chunks"]))
-    head = int(counters.get("head_models", 0)) or 128
-    ps_bound = ps - min(ps, P * args.steps * head * c["n"])  # the first `head` models per pair go to the exact kernel
-    evaluated = counters["bound_evaluated"]
-    executed_tf = 41.0 * evaluated / bound_s / 1e12 if bound_s > 0 else None
-    algorithmic_tf = FLOPS_PER_POINT_SCORE * ps_bound / bound_s / 1e12 if bound_s > 0 else None
-    alg_bytes = args.steps * N * 16 + hyps * (96 + 8)  # FP32 points once per pair; model in, (ub, lb) out per hypothesis
-    roofline = {"kernel": "bound_kernel (FP32 outlier-count / score-bound tier over the minimal models)",
-                "bound": "fp32_pipe", "achieved": executed_tf, "peak": fp32_tf, "unit": "TFLOP/s",
-                "frac": executed_tf / fp32_tf if (fp32_tf and executed_tf) else None,
-                "peak_source": "rp_measure_pipes on this device (FP32 FMA chains; MEASURED_PEAKS.json has no FP32 figure)",
-                "work": "evaluated point-scores (device counter) x 41 FP32 flop",
-                "traffic": _ncu_traffic("bound", P * args.steps / n_chunk_launches),
-                "point_scores_evaluated_per_s": evaluated / bound_s if bound_s > 0 else None,
-                "evaluated_fraction": evaluated / max(ps_bound, 1),
-                "launches": n_chunk_launches, "ms_per_launch": 1000.0 * bound_s / n_chunk_launches,
-                "share_of_step": bound_s / dev_s,
-                "score_stage_share_of_step": score_s / dev_s,
-                "exact_models_fraction": counters["exact_models"] / max(hyps, 1),
-                "algorithmic": {"note": "SURVEY 8d convention: 34 FP64 flop per point-score resolved, vs the measured FP64 FMA peak; "
-                                        "> 1 is possible because abandoned point-scores are never evaluated",
-                                "tflops": algorithmic_tf, "peak_tflops": fp64_tf,
-                                "frac": algorithmic_tf / fp64_tf if (fp64_tf and algorithmic_tf) else None,
-                                "point_scores_resolved_per_s": ps_bound / bound_s if bound_s > 0 else None}}
-    # the same kernel against the HBM roof, to show which roof binds: algorithmic bytes over the kernel's time
-    # vs the measured copy bandwidth of MEASURED_PEAKS.json (fallback: the profiling guide's 6 650 GB/s)
-    hbm_peak, hbm_src = 6650.0, "fallback of B200_PROFILING.md"
     try:
-        hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
-        hbm_src = "MEASURED_PEAKS.json hbm_gbs"
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        hbm_peak, hbm_src = float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+        bf16_tf, bf16_src = float(peaks["bf16_tflops_sustained"]), "MEASURED_PEAKS.json bf16_tflops_sustained"
     except Exception:
-        pass
+        hbm_peak, hbm_src, bf16_tf, bf16_src = 6650.0, "fallback of B200_PROFILING.md", 1400.0, "fallback of B200_PROFILING.md (sustained)"
+    pipes_src = "rp_measure_pipes on this device (FMA chains; MEASURED_PEAKS.json has no FP32 / FP64 figure)"
+    entries = []
+    # (1) tensor-core count tier: 96 tensor flop per point-score (48 TF32 MACs: hi/lo-split C 32, den 16)
+    tc_s = stage_ms.get("tc_kernel", 0.0) / 1000.0
+    if tc_s > 0:
+        tc_ps = counters["tc_evaluated"]
+        tf32_peak = bf16_tf / 2.0
+        entries.append({"kernel": "tc_count_kernel (tcgen05.mma kind::tf32 + TMEM epilogue: certain-outlier count of every minimal model)",
+                        "bound": "tensor", "achieved": 96.0 * tc_ps / tc_s / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
+                        "frac": 96.0 * tc_ps / tc_s / 1e12 / tf32_peak,
+                        "peak_source": bf16_src + " / 2 (dense TF32 runs at half the bf16 rate; no TF32 figure is measured)",
+                        "work": "point-scores evaluated (device counter) x 96 tensor flop",
+                        "traffic": _ncu_traffic("tc", P * args.steps / n_chunk_launches),
+                        "point_scores_per_s": tc_ps / tc_s, "launches": n_chunk_launches,
+                        "ms_per_launch": 1000.0 * tc_s / n_chunk_launches, "share_of_step": tc_s / dev_s,
+                        "passed_on_fraction": counters["tc_selected"] / max(hyps, 1),
+                        "hbm": {"bound": "hbm", "achieved": (args.steps * N * 128 + hyps * 100) / tc_s / 1e9, "peak": hbm_peak,
+                                "unit": "GB/s", "frac": (args.steps * N * 128 + hyps * 100) / tc_s / 1e9 / hbm_peak,
+                                "peak_source": hbm_src, "note": "feature rows once per pair + model in / count out: this roof does not bind"}})
+    # (2) FP32 bound kernel over the survivors of (1): 41 FP32 flop per evaluated point-score
+    bound_s = stage_ms["bound_kernel"] / 1000.0
     if bound_s > 0:
-        roofline["hbm"] = {"bound": "hbm", "achieved": alg_bytes / bound_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                           "frac": alg_bytes / bound_s / 1e9 / hbm_peak, "peak_source": hbm_src,
-                           "note": "arithmetic intensity ~5e2 flop/B: the pipe roof above binds, not this one"}
-    # second entry: the LM kernel (LO + final refinement), FP64 pipe
+        evaluated = counters["bound_evaluated"]
+        entries.append({"kernel": "bound_kernel (FP32 outlier-count / score-bound tier, packed f32x2)", "bound": "fp32_pipe",
+                        "achieved": 41.0 * evaluated / bound_s / 1e12, "peak": fp32_tf, "unit": "TFLOP/s",
+                        "frac": 41.0 * evaluated / bound_s / 1e12 / fp32_tf if fp32_tf else None, "peak_source": pipes_src,
+                        "work": "evaluated point-scores (device counter) x 41 FP32 flop",
+                        "traffic": _ncu_traffic("bound", P * args.steps / n_chunk_launches),
+                        "evaluated_fraction": evaluated / max(counters["point_scores"], 1), "launches": n_chunk_launches,
+                        "ms_per_launch": 1000.0 * bound_s / n_chunk_launches, "share_of_step": bound_s / dev_s})
+    # (3) LM kernel (LO refinement of every trigger, final LO, final refinement): FP64 flops from device counters x the
+    # per-row counts of rp_lm.cuh (LM_FLOPS)
     lm_s = (stage_ms["lo_refine"] + stage_ms["final_refine"]) / 1000.0
-    lm_flops = counters.get("lm_flops", 0)
-    roofline_lm = None
-    if lm_flops and lm_s > 0:
-        roofline_lm = {"kernel": "lm_kernel (LO refinement of every trigger + final LO + final refinement)",
-                       "bound": "fp64_pipe", "achieved": lm_flops / lm_s / 1e12, "peak": fp64_tf, "unit": "TFLOP/s",
-                       "frac": lm_flops / lm_s / 1e12 / fp64_tf if fp64_tf else None,
-                       "work": "device counters: residual rows evaluated / accumulated x the per-row FP64 flop counts of DESIGN.md §5",
-                       "share_of_step": lm_s / dev_s, "lm_iterations": counters["lm_iterations"],
-                       "lm_problems": counters["lm_problems"]}
+    if lm_s > 0 and counters.get("lm_flops", 0):
+        entries.append({"kernel": "lm_kernel (Levenberg-Marquardt: LO of every trigger + final refinement)", "bound": "fp64_pipe",
+                        "achieved": counters["lm_flops"] / lm_s / 1e12, "peak": fp64_tf, "unit": "TFLOP/s",
+                        "frac": counters["lm_flops"] / lm_s / 1e12 / fp64_tf if fp64_tf else None, "peak_source": pipes_src,
+                        "work": "device counters: correspondences evaluated, rows accumulated x the FP64 flop table LM_FLOPS (DESIGN.md §5)",
+                        "traffic": _ncu_traffic("lm", P * args.steps / n_chunk_launches),
+                        "share_of_step": lm_s / dev_s, "lm_iterations": counters["lm_iterations"],
+                        "lm_problems": counters["lm_problems"], "note": "includes the LO / final score+merge kernels between the two LM launches: "
+                        "stage timers, not per-kernel"})
+    entries.sort(key=lambda e: -e["share_of_step"])
+    roofline = dict(entries[0]) if entries else {}
+    roofline["exact_models_fraction"] = counters["exact_models"] / max(hyps, 1)
+    roofline["score_stage_share_of_step"] = stage_ms["score_minimal"] / 1000.0 / dev_s
+    ps = hyps * c["n"]   # point-scores the reference would compute for these minimal models
 
     line = {"metric": "image_pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000.0 * elapsed_max / args.steps, "higher_is_better": True,
@@ -386,10 +404,9 @@ def main():
             "secondary": {"hypothesis_scores_per_sec": world * hyps / elapsed_max, "point_scores_per_sec": world * ps / elapsed_max,
                           "models_per_iteration": hyps / (args.steps * P * c["iters"])},
             "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
-            "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": int(launches), "clocks": clk, "roofline": roofline}
-    if roofline_lm:
-        line["roofline_lm"] = roofline_lm
+            "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "gathered_to_rank0_bytes_per_step": gather_bytes},
+            "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "rooflines": entries}
     if not args.no_cpu_baseline and world == 1:   # the CPU baseline is reported at N = 1 only
         cores = os.cpu_count() or 1
         n_sample = args.cpu_sample or max(64 * cores, 256)   # ~11 s of wall clock on 16 cores

@@ -509,6 +509,7 @@ int run_chunk(rp_ctx *ctx, int variant, const rp_options &opt, const ChunkIO &io
     la.initial_lambda = 1e-3; la.min_lambda = 1e-10; la.max_lambda = 1e10;
     la.loss_scale_override = -1.0; la.scale_reproj_override = -1.0;
     la.lm_iters = &sc->lm_iters;
+    la.lm_flops = &sc->lm_flops;
     {
         la.prob_list = B[B_PROBLIST].as<int>(); la.n_prob = &sc->n_prob; la.prob_per_pair = ev_cap;
         la.models = B[B_LOMODELS].as<Model>(); la.use_final = 0;

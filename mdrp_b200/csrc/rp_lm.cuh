@@ -172,9 +172,19 @@ RP_HD double point_cost(const LMFrame &F, const LMParams &P, double x1_0, double
 // point_eval returns the cost contribution of the same correspondence as well (the value point_cost
 // computes), so one pass over the data serves both the accept test of the trial step and — when it is
 // accepted, the usual case — the normal equations of the next iteration.
+// FP64 flops of one correspondence in one LM pass, counted from the formulas below (FMA = 2, mul / add / compare = 1,
+// rcp = 1, rsqrt = 2; structural zeros and the calibrated variants' literal unit focals not counted):
+//   residuals + cost (always)          : LM_FLOPS[v][0]
+//   Sampson row, Jacobian + J^T J      : LM_FLOPS[v][1]   (6 | 6 | 7 | 8 columns)
+//   reprojection 1->2, both rows       : LM_FLOPS[v][2]   (6 | 7 | 7 | 8 columns)
+//   reprojection 2->1, both rows       : LM_FLOPS[v][3]   (7 | 8 | 8 | 9 columns)
+// (v = RP_CALIB, RP_CALIB_SHIFT, RP_SHARED, RP_VARYING; derivation in DESIGN.md §5).  `rows` counts the accumulated
+// rows of the three kinds in three 21-bit fields; the LM kernel turns the counts into the bench's lm_flops.
+constexpr int LM_FLOPS[4][4] = {{110, 167, 170, 207}, {110, 167, 222, 247}, {120, 224, 223, 268}, {120, 243, 261, 310}};
+
 template <int VARIANT, int NP, int LOSS = -1>
 RP_HD double point_eval(const LMFrame &F, const LMParams &P, double x1_0, double x1_1, double x2_0,
-                        double x2_1, double d1, double d2, NormalEq<NP> &N) {
+                        double x2_1, double d1, double d2, NormalEq<NP> &N, unsigned long long &rows) {
     constexpr bool FOCAL = (VARIANT == RP_SHARED || VARIANT == RP_VARYING);
     const int loss_type = LOSS >= 0 ? LOSS : P.loss_type;
     // calibrated variants carry f1 = f2 = 1: literal ones let the compiler drop the multiplications (and the
@@ -265,6 +275,7 @@ RP_HD double point_eval(const LMFrame &F, const LMParams &P, double x1_0, double
                 else { J[7] = j1; J[CF2] = j2; }
             }
             N.template add_row<M_S>(w, J, rs);
+            rows += 1ull;
         }
     }
     if (!(P.scale_reproj > 0.0)) return cost;
@@ -318,6 +329,7 @@ RP_HD double point_eval(const LMFrame &F, const LMParams &P, double x1_0, double
                 }
                 N.template add_row<M_12>(w, J0, r0);
                 N.template add_row<M_12>(w, J1, r1);
+                rows += 1ull << 21;
             }
         }
     }
@@ -363,6 +375,7 @@ RP_HD double point_eval(const LMFrame &F, const LMParams &P, double x1_0, double
                 }
                 N.template add_row<M_21>(w, J0, r0);
                 N.template add_row<M_21>(w, J1, r1);
+                rows += 1ull << 42;
             }
         }
     }
@@ -372,7 +385,8 @@ RP_HD double point_eval(const LMFrame &F, const LMParams &P, double x1_0, double
 template <int VARIANT, int NP>
 RP_HD void point_accumulate(const LMFrame &F, const LMParams &P, double x1_0, double x1_1, double x2_0,
                             double x2_1, double d1, double d2, NormalEq<NP> &N) {
-    (void)point_eval<VARIANT, NP>(F, P, x1_0, x1_1, x2_0, x2_1, d1, d2, N);
+    unsigned long long rows = 0;
+    (void)point_eval<VARIANT, NP>(F, P, x1_0, x1_1, x2_0, x2_1, d1, d2, N, rows);
 }
 
 // parameter update of lm_impl's problem.step(): R <- R exp([dw]x), everything else additive

@@ -31,6 +31,7 @@ struct LMArgs {
     double scale_reproj_override;
     rp_bundle_stats *stats;      // optional, per problem index
     unsigned long long *lm_iters;
+    unsigned long long *lm_flops;   // optional: FP64 flops executed (LM_FLOPS table x device counts)
     int *work_counter;           // zeroed before the launch: blocks take problems dynamically
 };
 
@@ -150,6 +151,7 @@ __global__ void __launch_bounds__(THREADS, RP_LM_MIN_BLOCKS * 128 / THREADS) lm_
             __syncthreads();
         }
 
+        unsigned long long rows = 0;   // accumulated rows of this thread (three 21-bit fields, see LM_FLOPS)
         auto block_cost = [&](const Model &m) -> double {
             const LMFrame F = make_frame(m);
             double c = 0.0;
@@ -179,7 +181,7 @@ __global__ void __launch_bounds__(THREADS, RP_LM_MIN_BLOCKS * 128 / THREADS) lm_
                 const int k = use_list ? (int)list_s[i] : i;
                 if (!use_list && mask && !mask[k]) continue;
                 const Pt64 p = pts[k];
-                c += point_eval<VARIANT, NP, LOSS>(F, P, p.x1_0, p.x1_1, p.x2_0, p.x2_1, d1[k], d2[k], N);
+                c += point_eval<VARIANT, NP, LOSS>(F, P, p.x1_0, p.x1_1, p.x2_0, p.x2_1, d1[k], d2[k], N, rows);
             }
             c = warp_sum(c);
             __syncthreads();
@@ -219,9 +221,11 @@ __global__ void __launch_bounds__(THREADS, RP_LM_MIN_BLOCKS * 128 / THREADS) lm_
         // speculatively and they are reduced only when the step is accepted (the last iteration, whose
         // Jacobians nobody would read, is a cost-only pass).
         NormalEq<NP> N;
+        int passes = 0;                // passes over the correspondences (uniform)
         double cost;
         if (max_it > 0) { cost = block_eval(cur, N); reduce_normal(N); }
         else cost = block_cost(cur);
+        ++passes;
         const double initial_cost = cost;
         double lambda = a.initial_lambda;
         double grad_norm = -1.0, step_norm = -1.0;
@@ -251,6 +255,7 @@ __global__ void __launch_bounds__(THREADS, RP_LM_MIN_BLOCKS * 128 / THREADS) lm_
             if (stop_s) break;
             const bool last = it == max_it - 1;
             const double cost_new = last ? block_cost(trial) : block_eval(trial, N);
+            ++passes;
             if (cost_new < cost) {
                 __syncthreads();
                 if (tid == 0) cur = trial;
@@ -275,6 +280,16 @@ __global__ void __launch_bounds__(THREADS, RP_LM_MIN_BLOCKS * 128 / THREADS) lm_
                 a.stats[prob] = s;
             }
             if (a.lm_iters) atomicAdd(a.lm_iters, (unsigned long long)it);
+        }
+        if (a.lm_flops) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) rows += __shfl_xor_sync(0xffffffffu, rows, o);   // fields stay < 2^21 per block
+            if (lane == 0) {
+                const unsigned long long fl = (rows & 0x1fffffull) * LM_FLOPS[VARIANT][1] + ((rows >> 21) & 0x1fffffull) * LM_FLOPS[VARIANT][2] +
+                                              ((rows >> 42) & 0x1fffffull) * LM_FLOPS[VARIANT][3] +
+                                              (wid == 0 ? (unsigned long long)passes * m_work * LM_FLOPS[VARIANT][0] : 0ull);
+                atomicAdd(a.lm_flops, fl);
+            }
         }
     }
 }
