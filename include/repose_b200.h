@@ -184,6 +184,17 @@ RP_API int rp_gather_depths_dev(rp_ctx *ctx, const float *depth1, int h1, int w1
                                 const float *kp1, const float *kp2, int64_t n, double *x1, double *x2, double *d1,
                                 double *d2, int64_t *n_out, void *stream);
 
+/* The same recipe for a whole batch of pairs in one call (the reference's video demo runs it per frame pair,
+ * /root/reference/make_video.py:270-290): depth maps of one size stacked [n_frames, h, w] (DEVICE), pair p reads frames
+ * frame1[p] / frame2[p] (HOST index arrays) and owns the keypoint rows [in_offsets[p], in_offsets[p+1]) of kp1 / kp2
+ * (DEVICE [N,2] float32; in_offsets HOST).  One CTA per pair compacts its rows; the call synchronises ONCE to return
+ * out_offsets (HOST, [n_pairs+1]) — the packed offsets rp_estimate_batch_dev needs — and leaves x1, x2, d1, d2 (DEVICE,
+ * capacity N rows) packed accordingly. */
+RP_API int rp_gather_depths_batch_dev(rp_ctx *ctx, int64_t n_pairs, const int64_t *in_offsets, const float *depth_maps,
+                                      int n_frames, int h, int w, const int32_t *frame1, const int32_t *frame2,
+                                      const float *kp1, const float *kp2, double *x1, double *x2, double *d1, double *d2,
+                                      int64_t *out_offsets, void *stream);
+
 /* ---- measurement helpers ---------------------------------------------------------
  * Pipe micro-benchmarks for the roofline denominators SURVEY.md §8d asks for (the driver's
  * MEASURED_PEAKS.json has only HBM and bf16): sustained FP64 and FP32 FMA throughput of

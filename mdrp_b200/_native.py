@@ -20,7 +20,7 @@ LOSS = {"TRIVIAL": 0, "TRUNCATED": 1, "HUBER": 2, "CAUCHY": 3, "TRUNCATED_CAUCHY
 EXPORTS = [
     "rp_create", "rp_destroy", "rp_last_error", "rp_default_options", "rp_launch_count",
     "rp_estimate_batch_host", "rp_estimate_batch_dev", "rp_sample_batch", "rp_sample_batch_prosac", "rp_solve_batch",
-    "rp_score_batch", "rp_refine_batch", "rp_measure_pipes", "rp_last_timing", "rp_gather_depths_dev", "rp_tc_count_batch", "rp_pair_status",
+    "rp_score_batch", "rp_refine_batch", "rp_measure_pipes", "rp_last_timing", "rp_gather_depths_dev", "rp_tc_count_batch", "rp_pair_status", "rp_gather_depths_batch_dev",
 ]
 
 
@@ -115,6 +115,8 @@ def load():
     L.rp_gather_depths_dev.restype = C.c_int
     L.rp_gather_depths_dev.argtypes = [VP, VP, C.c_int, C.c_int, VP, C.c_int, C.c_int, VP, VP, C.c_int64, VP, VP, VP, VP,
                                        C.POINTER(C.c_int64), VP]
+    L.rp_gather_depths_batch_dev.restype = C.c_int
+    L.rp_gather_depths_batch_dev.argtypes = [VP, C.c_int64, VP, VP, C.c_int, C.c_int, C.c_int, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP]
     L.rp_measure_pipes.restype = C.c_int
     L.rp_measure_pipes.argtypes = [VP, DP, DP]
     L.rp_pair_status.restype = C.c_int

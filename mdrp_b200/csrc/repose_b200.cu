@@ -1241,6 +1241,54 @@ int rp_gather_depths_dev(rp_ctx *ctx, const float *depth1, int h1, int w1, const
     return RP_OK;
 }
 
+int rp_gather_depths_batch_dev(rp_ctx *ctx, int64_t n_pairs, const int64_t *in_offsets, const float *depth_maps, int n_frames,
+                               int h, int w, const int32_t *frame1, const int32_t *frame2, const float *kp1, const float *kp2,
+                               double *x1, double *x2, double *d1, double *d2, int64_t *out_offsets, void *stream) {
+    if (!ctx || n_pairs < 0 || !in_offsets || !out_offsets || h <= 0 || w <= 0 || n_frames <= 0 ||
+        (n_pairs > 0 && (!depth_maps || !frame1 || !frame2)))
+        return fail(ctx, RP_ERR_INVALID, "bad argument");
+    out_offsets[0] = 0;
+    if (n_pairs == 0) return RP_OK;
+    const long long N = in_offsets[n_pairs] - in_offsets[0];
+    for (int64_t p = 0; p < n_pairs; ++p) {
+        if (in_offsets[p + 1] < in_offsets[p] || frame1[p] < 0 || frame1[p] >= n_frames || frame2[p] < 0 || frame2[p] >= n_frames)
+            return fail(ctx, RP_ERR_INVALID, "offsets must be non-decreasing and frame indices inside [0, n_frames)");
+    }
+    if (N > 0 && (!kp1 || !kp2 || !x1 || !x2 || !d1 || !d2)) return fail(ctx, RP_ERR_INVALID, "null data pointer");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    DevBuf *B = ctx->buf;
+    const size_t nn = (size_t)std::max<long long>(N, 1);
+    CK(B[B_SUB_X1].reserve(16 * nn)); CK(B[B_SUB_X2].reserve(16 * nn)); CK(B[B_SUB_D1].reserve(8 * nn)); CK(B[B_SUB_D2].reserve(8 * nn));
+    CK(B[B_SUB_SRC].reserve(8 * ((size_t)n_pairs + 1))); CK(B[B_SUB_DST].reserve(8 * ((size_t)n_pairs + 1)));
+    CK(B[B_SUB_IDX].reserve(sizeof(int) * 3 * (size_t)n_pairs));
+    std::vector<long long> rel((size_t)n_pairs + 1);
+    for (int64_t p = 0; p <= n_pairs; ++p) rel[(size_t)p] = in_offsets[p] - in_offsets[0];
+    int *d_f1 = B[B_SUB_IDX].as<int>(), *d_f2 = d_f1 + n_pairs, *d_cnt = d_f2 + n_pairs;
+    CK(cudaMemcpyAsync(B[B_SUB_SRC].p, rel.data(), 8 * ((size_t)n_pairs + 1), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_f1, frame1, sizeof(int) * (size_t)n_pairs, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_f2, frame2, sizeof(int) * (size_t)n_pairs, cudaMemcpyHostToDevice, st));
+    GatherBatchArgs g;
+    g.n_pairs = (int)n_pairs; g.h = h; g.w = w; g.depth = depth_maps; g.frame1 = d_f1; g.frame2 = d_f2;
+    g.in_off = B[B_SUB_SRC].as<long long>(); g.out_off = B[B_SUB_DST].as<long long>();
+    g.kp1 = kp1; g.kp2 = kp2;
+    g.tx1 = B[B_SUB_X1].as<double>(); g.tx2 = B[B_SUB_X2].as<double>(); g.td1 = B[B_SUB_D1].as<double>(); g.td2 = B[B_SUB_D2].as<double>();
+    g.x1 = x1; g.x2 = x2; g.d1 = d1; g.d2 = d2; g.count = d_cnt;
+    gather_depths_batch_kernel<<<(unsigned)n_pairs, 256, 0, st>>>(g);
+    LAUNCHED();
+    std::vector<int> cnt((size_t)n_pairs);
+    CK(cudaMemcpyAsync(cnt.data(), d_cnt, sizeof(int) * (size_t)n_pairs, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));   // the one synchronisation of the batch: the caller needs the packed offsets
+    std::vector<long long> out((size_t)n_pairs + 1, 0);
+    for (int64_t p = 0; p < n_pairs; ++p) out[(size_t)p + 1] = out[(size_t)p] + cnt[(size_t)p];
+    for (int64_t p = 0; p <= n_pairs; ++p) out_offsets[p] = out[(size_t)p];
+    CK(cudaMemcpyAsync(B[B_SUB_DST].p, out.data(), 8 * ((size_t)n_pairs + 1), cudaMemcpyHostToDevice, st));
+    gather_depths_pack_kernel<<<(unsigned)n_pairs, 256, 0, st>>>(g);
+    LAUNCHED();
+    CK(cudaStreamSynchronize(st));   // `out` is a stack-lifetime host buffer
+    return RP_OK;
+}
+
 int rp_measure_pipes(rp_ctx *ctx, double *fp64_tflops, double *fp32_tflops) {
     if (!ctx) return RP_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));

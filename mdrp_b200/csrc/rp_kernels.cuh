@@ -1610,6 +1610,76 @@ __global__ void gather_depths_kernel(const float *depth1, int h1, int w1, const 
     if (tid == 0) *n_out = running;
 }
 
+// Batched form for video / many pairs (make_video.py:270-290 runs the same recipe per frame pair): depth maps of one
+// size stacked [F, h, w], pair p = (frame1[p], frame2[p]) with keypoints [in_off[p], in_off[p+1]).  Pass 1: one CTA per
+// pair, stable compaction of the pair's rows INTO ITS OWN INPUT RANGE of the temporary arrays + the kept count; the host
+// reads the n_pairs counts once (it needs the packed offsets anyway: rp_estimate_batch_dev takes them), pass 2 moves
+// every pair's block to its packed position.
+struct GatherBatchArgs {
+    int n_pairs, h, w;
+    const float *depth;            // [F, h, w]
+    const int *frame1, *frame2;    // [n_pairs]
+    const long long *in_off;       // [n_pairs + 1]
+    const long long *out_off;      // [n_pairs + 1] (pass 2)
+    const float *kp1, *kp2;        // [N, 2]
+    double *tx1, *tx2, *td1, *td2; // temporaries, capacity N
+    double *x1, *x2, *d1, *d2;     // packed outputs
+    int *count;                    // [n_pairs]
+};
+__global__ void gather_depths_batch_kernel(GatherBatchArgs a) {
+    __shared__ int warp_tot[32];
+    __shared__ int running;
+    const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const long long i0 = a.in_off[pair];
+    const int n = (int)(a.in_off[pair + 1] - i0);
+    const float *dm1 = a.depth + (size_t)a.frame1[pair] * a.h * a.w, *dm2 = a.depth + (size_t)a.frame2[pair] * a.h * a.w;
+    if (tid == 0) running = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += blockDim.x) {
+        const int i = base + tid;
+        bool keep = false;
+        float ax = 0, ay = 0, bx = 0, by = 0, da = 0, db = 0;
+        if (i < n) {
+            ax = a.kp1[2 * (i0 + i)]; ay = a.kp1[2 * (i0 + i) + 1]; bx = a.kp2[2 * (i0 + i)]; by = a.kp2[2 * (i0 + i) + 1];
+            const int r1 = min(max((int)ay, 0), a.h - 1), c1 = min(max((int)ax, 0), a.w - 1);
+            const int r2 = min(max((int)by, 0), a.h - 1), c2 = min(max((int)bx, 0), a.w - 1);
+            da = dm1[(size_t)r1 * a.w + c1];
+            db = dm2[(size_t)r2 * a.w + c2];
+            keep = !(isinf(da) && isinf(db));
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) warp_tot[wid] = __popc(m);
+        __syncthreads();
+        int wbase = 0, total = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+            if (w < wid) wbase += warp_tot[w];
+            total += warp_tot[w];
+        }
+        if (keep) {
+            const long long o = i0 + running + wbase + __popc(m & ((1u << lane) - 1u));
+            a.tx1[2 * o] = ax; a.tx1[2 * o + 1] = ay; a.tx2[2 * o] = bx; a.tx2[2 * o + 1] = by;
+            a.td1[o] = da; a.td2[o] = db;
+        }
+        __syncthreads();
+        if (tid == 0) running += total;
+        __syncthreads();
+    }
+    if (tid == 0) a.count[pair] = running;
+}
+__global__ void gather_depths_pack_kernel(GatherBatchArgs a) {
+    const int pair = blockIdx.x;
+    const long long i0 = a.in_off[pair], o0 = a.out_off[pair];
+    const int n = (int)(a.out_off[pair + 1] - o0);
+    for (int i = threadIdx.x; i < 2 * n; i += blockDim.x) {
+        a.x1[2 * o0 + i] = a.tx1[2 * i0 + i];
+        a.x2[2 * o0 + i] = a.tx2[2 * i0 + i];
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        a.d1[o0 + i] = a.td1[i0 + i];
+        a.d2[o0 + i] = a.td2[i0 + i];
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // pipe micro-benchmarks (the FP64 / FP32 FMA peaks are not in MEASURED_PEAKS.json)
 // 16 independent FMA chains per thread, 8 blocks of 256 threads per SM: enough ILP x TLP to saturate either pipe

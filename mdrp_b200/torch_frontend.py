@@ -43,6 +43,31 @@ def gather_depths(depth_map1, depth_map2, keypoints1, keypoints2):
     return x1[:m], x2[:m], d1[:m], d2[:m]
 
 
+def gather_depths_batch(depth_maps, frame1, frame2, offsets, keypoints1, keypoints2):
+    """`gather_depths` for a batch of pairs in one call (a video: make_video.py:270-290).  depth_maps: [F,H,W] float32
+    CUDA; frame1 / frame2: per-pair frame indices; offsets: [P+1] rows of the packed keypoints [N,2] float32 CUDA.
+    Returns (out_offsets int64 numpy, x1, x2, d1, d2) — the packed float64 CUDA tensors `estimate_batch` takes."""
+    ctx = _ctx_for(depth_maps)
+    dm = depth_maps.contiguous().float()
+    k1, k2 = keypoints1.contiguous().float(), keypoints2.contiguous().float()
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    f1 = np.ascontiguousarray(frame1, dtype=np.int32)
+    f2 = np.ascontiguousarray(frame2, dtype=np.int32)
+    P, n, dev = len(offsets) - 1, k1.shape[0], dm.device
+    if len(f1) != P or len(f2) != P or int(offsets[-1]) - int(offsets[0]) != n:
+        raise ValueError("frame1 / frame2 need one entry per pair and offsets must cover the keypoints")
+    x1 = torch.empty(n, 2, dtype=torch.float64, device=dev)
+    x2 = torch.empty(n, 2, dtype=torch.float64, device=dev)
+    d1 = torch.empty(n, dtype=torch.float64, device=dev)
+    d2 = torch.empty(n, dtype=torch.float64, device=dev)
+    out = np.zeros(P + 1, dtype=np.int64)
+    ctx._call(ctx._lib.rp_gather_depths_batch_dev, ctx._h, P, offsets.ctypes.data, dm.data_ptr(), dm.shape[0], dm.shape[1],
+              dm.shape[2], f1.ctypes.data, f2.ctypes.data, k1.data_ptr(), k2.data_ptr(), x1.data_ptr(), x2.data_ptr(),
+              d1.data_ptr(), d2.data_ptr(), out.ctypes.data, torch.cuda.current_stream(dev).cuda_stream)
+    m = int(out[-1])
+    return out, x1[:m], x2[:m], d1[:m], d2[:m]
+
+
 def estimate_batch(variant, offsets, x1, x2, d1, d2, cams, opt: nv.Options):
     """Packed CUDA float64 tensors in (offsets: host int64 array), CUDA tensors out:
     models [P,12] float64, stats [P,5] (int64 view; columns 3,4 are float64 bit patterns — use

@@ -51,10 +51,30 @@ def test_read_and_pack():
     assert b.offsets.tolist() == [0, 200, 400, 600] and b.x1.shape == (600, 2) and b.cams.shape == (3, 8)
     assert b.cams[1].tolist() == [scenes[1].f1, scenes[1].f1, 640.0, 480.0, scenes[1].f2, scenes[1].f2, 640.0, 480.0]
     assert np.array_equal(b.d2[200:400], pairs[1].d[:, 1])
-    c = br.pack(pairs, centre=True)
+    # focal drivers: centred keypoints, depths as they are, their own minimum match counts
+    sh = list(br.read_pairs(h5, depth=2, driver="shared"))
+    c = br.pack(sh, centre=True)
     assert c.cams is None and np.allclose(c.x1[:200], scenes[0].x1 - [640.0, 480.0])
+    assert np.isinf(sh[0].d[0, 0]) and np.isnan(sh[0].d[1, 1])          # eval_shared_f.py:353-356: no sanitising
+    assert np.allclose(next(br.read_pairs(h5, depth=1, driver="varying", ppbug=True)).kp1, scenes[0].x1 - [320.0, 240.0])
     halved = next(br.read_pairs(h5, depth=1, ppbug=True))
     assert halved.K1[0, 2] == 320.0 and h5["K_img000a_o"][0, 2] == 640.0   # the file's matrix is not modified
+
+
+def test_focal_driver_rules():
+    """eval_shared_f.py:340-351 / eval_varying_f.py:340: minimum match counts and the focal rescale of image 2."""
+    h5, scenes = fake_benchmark(n_pairs=2, n=50, cfg="cfg4_varying_focal")   # f1 = 700, f2 = 900
+    h5["corr_short_o_short2_o"] = np.zeros((6, 32))
+    h5["pose_short_o_short2_o"] = np.eye(3, 4)
+    h5["K_short_o"] = h5["K_short2_o"] = np.array([[800.0, 0, 640], [0, 800.0, 480], [0, 0, 1]])
+    assert len(list(br.read_pairs(h5, driver="calib"))) == 3 and len(list(br.read_pairs(h5, driver="shared"))) == 3
+    assert len(list(br.read_pairs(h5, driver="varying"))) == 2            # 6 matches < 7
+    sh = next(br.read_pairs(h5, depth=1, driver="shared"))
+    assert np.allclose(sh.kp2, (scenes[0].x2 - [640.0, 480.0]) * 700.0 / 900.0) and abs(sh.K2[0, 0] - 700.0) < 1e-9
+    va = next(br.read_pairs(h5, depth=1, driver="varying"))
+    assert np.allclose(va.kp2, scenes[0].x2 - [640.0, 480.0]) and va.K2[0, 0] == 900.0
+    with pytest.raises(ValueError):
+        list(br.read_pairs(h5, driver="nope"))
 
 
 def test_metrics_match_reference_definitions():
@@ -94,3 +114,23 @@ def test_unsupported_experiment_strings_are_refused():
                 "madpose+3", "mad_poselib_shift_scale_hybrid", "3p_reldepth_hybrid", "3p_ours_scale_sym_reproj"):
         with pytest.raises(ValueError):
             br.check_experiment(bad)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("driver,cfg", [("shared", "cfg3_shared_focal"), ("varying", "cfg4_varying_focal")])
+def test_evaluate_focal_drivers_equal_per_pair_calls(ctx, driver, cfg):
+    """eval_shared_f.py:177 / eval_varying_f.py:168 through the fork names, pair by pair, against the batched evaluation."""
+    from mdrp_b200 import api
+    h5, scenes = fake_benchmark(n_pairs=5, n=400, cfg=cfg)
+    exp = "3p_ours_scale_hybrid_ctruncated+1"
+    res = br.evaluate(h5, exp, iterations=500, driver=driver)
+    assert len(res["errs"]) == 4 and res["mAA"] > 0.7 and res["f_err"] < 0.05 and 0.0 <= res["mAA_f"] <= 1.0
+    fn = api.estimate_shared_focal_monodepth_relative_pose if driver == "shared" else api.estimate_varying_focal_monodepth_relative_pose
+    ransac = {"max_iterations": 500, "min_iterations": 500, "max_epipolar_error": 2.0, "max_reproj_error": 16.0,
+              "use_ours": True, "solver_scale": True, "solver_shift": False, "use_p3p": False, "optimize_hybrid": True}
+    for p, e in zip(br.read_pairs(h5, depth=1, driver=driver), res["errs"]):
+        pair, info = fn(p.kp1, p.kp2, p.d, ransac, {"loss_type": "TRUNCATED_CAUCHY", "max_iterations": 100})
+        e1 = max(br.rotation_error_deg(pair.pose.R, p.R_gt), br.translation_error_deg(pair.pose.t, p.t_gt))
+        assert abs(e1 - e) < 1e-9
+    with pytest.raises(ValueError):
+        br.evaluate(h5, "3p_ours_shift_scale_hybrid-s_ctruncated+1", driver=driver)

@@ -86,3 +86,32 @@ def test_inf_depths_do_not_poison_the_batch(ctx, port):
         assert (st.refinements, st.num_inliers) == (stats[i]["refinements"], stats[i]["num_inliers"]), i
         assert np.array_equal(mk, masks[offs[i]:offs[i + 1]].astype(bool)), i
         assert models_close(models[i], m, rtol=1e-6, atol=1e-8), i
+
+
+def test_batched_gather_equals_per_pair(ctx):
+    """rp_gather_depths_batch_dev over a ragged batch of frame pairs == rp_gather_depths_dev pair by pair, and the packed
+    result feeds the batched estimator."""
+    import torch
+    from mdrp_b200 import torch_frontend as tf
+    rng = np.random.default_rng(5)
+    F, H, W = 4, 120, 160
+    maps = rng.uniform(1, 9, size=(F, H, W)).astype(np.float32)
+    maps[rng.uniform(size=maps.shape) < 0.3] = np.inf
+    sizes = [700, 0, 33, 1025, 256]
+    f1, f2 = [0, 1, 2, 3, 0], [1, 2, 3, 0, 2]
+    offs = np.r_[0, np.cumsum(sizes)]
+    kp1 = rng.uniform(-3, [W + 3, H + 3], size=(offs[-1], 2)).astype(np.float32)   # a few outside: clamped to the border
+    kp2 = rng.uniform(-3, [W + 3, H + 3], size=(offs[-1], 2)).astype(np.float32)
+    g = torch.from_numpy(maps).cuda()
+    k1, k2 = torch.from_numpy(kp1).cuda(), torch.from_numpy(kp2).cuda()
+    out, x1, x2, d1, d2 = tf.gather_depths_batch(g, f1, f2, offs, k1, k2)
+    assert out[0] == 0 and len(out) == len(sizes) + 1 and x1.shape[0] == out[-1]
+    for p in range(len(sizes)):
+        sl = slice(offs[p], offs[p + 1])
+        if sizes[p] == 0:
+            assert out[p + 1] == out[p]
+            continue
+        a1, a2, e1, e2 = tf.gather_depths(g[f1[p]], g[f2[p]], k1[sl], k2[sl])
+        o = slice(out[p], out[p + 1])
+        assert a1.shape[0] == out[p + 1] - out[p] and 0 < a1.shape[0] < sizes[p]
+        assert torch.equal(x1[o], a1) and torch.equal(x2[o], a2) and torch.equal(d1[o], e1) and torch.equal(d2[o], e2)
