@@ -29,15 +29,20 @@
 // tests/test_gpu_tc.py measures the actual errors against FP64 and checks out <= N - exact count on random
 // and adversarial models.
 //
-// Layout / schedule (one CTA per SM, persistent, 384 threads):
-//   B operand  per-point feature rows, 32 floats = 128 B, written once per pair by tc_features_kernel, fetched
-//              64 rows at a time by TMA (cp.async.bulk.tensor, SWIZZLE_128B) into a 4-stage ring  [warp 0]
-//   A operand  256 models per work item (2 M-tiles), rows built in-kernel from the 96-byte models (E, G(E),
-//              hi/lo split, constants) straight into the swizzled shared-memory layout, double buffered [warps 10-11]
-//   MMA        one elected thread issues 12 tcgen05.mma per 64-point tile (2 M-tiles x (4 + 2)) into a
-//              2-stage TMEM accumulator ring (2 x 2 x 64 columns per stage = all 512 columns)      [warp 1]
-//   epilogue   thread = model (TMEM lane), tcgen05.ld 32 columns at a time, FFMA.SAT + packed FADD  [warps 2-9]
-// Per (model, point): 48 tensor-core MACs, 8 B of TMEM read, 1.5 issue slots.
+// Layout / schedule (one CTA per SM, persistent, 512 threads):
+//   B operand  per-point feature rows, 32 floats = 128 B, written once per pair by tc_features_kernel, fetched 64 rows
+//              at a time by TMA (cp.async.bulk.tensor, SWIZZLE_128B) into a 6-stage ring; one more, constant, slice
+//              (0,0,0,0,1,1,0,0) per row sits in shared memory for the whole kernel                       [warp 0]
+//   A operand  256 models per work item (2 M-tiles).  A does not change over the ~32 point tiles of an item, so the
+//              builder warps compute the rows from the 96-byte models (E, G(E), hi/lo split, constants) and write them
+//              ONCE per item straight into TENSOR MEMORY (tcgen05.st, thread = row = TMEM lane, double buffered); the
+//              MMAs take A from there.  (With A in shared memory every MMA re-read 4 KB of A next to 2 KB of B for
+//              128 x 64 x 8 MACs: measured 86 cycles per MMA, tensor pipe at 17 %.)                       [warps 12-15]
+//   MMA        one elected thread issues 6 tcgen05.mma per (64-point tile, M-tile) into one of three accumulator
+//              slots (Cs | Ts, 128 columns); TMEM map: 3 x 128 accumulator + 2 x 2 x 32 A columns = 512   [warp 1]
+//   epilogue   group m = the four warps of M-tile m, thread = model (TMEM lane), tcgen05.ld 16 columns at a time,
+//              FFMA.SAT + FADD; two MMA groups of slack to drain a slot                                    [warps 4-11]
+// Per (model, point): 48 tensor-core MACs, 8 B of TMEM read, ~2 issue slots.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -46,27 +51,9 @@
 namespace rp {
 namespace tc {
 
-#ifndef RP_TC_NT
-#define RP_TC_NT 64
-#endif
-#ifndef RP_TC_MT
-#define RP_TC_MT 2
-#endif
-constexpr int NT = RP_TC_NT;                 // points per accumulator tile (MMA N)
-constexpr int MT = RP_TC_MT;                 // M-tiles (128 models) per work item
+constexpr int MT = 2;                        // M-tiles (128 models) per work item
 constexpr int TILE_MODELS = 128 * MT;
-constexpr int B_STAGES = 4;
-constexpr int ACC_STAGES = 512 / (MT * 2 * NT);      // accumulator ring fills the tensor memory
-constexpr int TMEM_COLS = MT * 2 * NT * ACC_STAGES;   // 512
-constexpr int FEAT = 32;                     // floats per point feature row
-constexpr int A_REGION_BYTES = 128 * 128;    // one SWIZZLE_128B region: 128 rows x 128 B
-constexpr int A_BUF_BYTES = MT * 2 * A_REGION_BYTES;
-constexpr int B_STAGE_BYTES = NT * 128;
-constexpr int EPI_WARP0 = 4, EPI_WARPS = 4 * MT, BUILD_WARP0 = EPI_WARP0 + EPI_WARPS, BUILD_WARPS = 2;
-constexpr int THREADS = 32 * (BUILD_WARP0 + BUILD_WARPS);   // warps 2, 3 idle: epilogue warp w reads TMEM lanes 32 (w % 4)
-constexpr int SMEM_BYTES = 1024 + 2 * A_BUF_BYTES + B_STAGES * B_STAGE_BYTES + 256;
-static_assert(TMEM_COLS == 512 && ACC_STAGES >= 2, "accumulator ring must fill the tensor memory exactly");
-
+constexpr int FEAT = 32;                     // floats per point feature row (128 B)
 constexpr double A_SPLIT = 1.0 / 32.0;                // a of (x+y)^2 <= (1+a) x^2 + (1+1/a) y^2
 constexpr double EPS_UNITS = 64.0;                    // eps_tc = EPS_UNITS u Emax (M + thr m)
 
@@ -87,7 +74,8 @@ RP_HD float tf32_round(float v) {
 }
 
 // ---- per-point feature row (B operand) ---------------------------------------------------------------
-// slice 0: tf32(phi_0..7)   slice 1: tf32(phi - slice 0)   slice 2: tf32(psi_0..7)   slice 3: (x2x, x2y, 1, 1, 0, 0, 0, 0)
+// slice 0: tf32(phi_0..7)   slice 1: tf32(phi - slice 0)   slice 2: tf32(psi_0..7)   slice 3: (x2x, x2y, 1, 0, 0, 0, 0, 0)
+// (+ the constant slice K = (0, 0, 0, 0, 1, 1, 0, 0), the same for every point: kept once in shared memory)
 //   phi = (x2x x1x, x2x x1y, x2x, x2y x1x, x2y x1y, x2y, x1x, x1y)            <-> E00 E01 E02 E10 E11 E12 E20 E21 (E22: const)
 //   psi = (x1x^2, x1x x1y, x1y^2, x1x, x1y, x2x^2, x2x x2y, x2y^2 | x2x, x2y | 1)
 RP_HD void feature_row(float x1x, float x1y, float x2x, float x2y, float *row /*32*/) {
@@ -100,28 +88,27 @@ RP_HD void feature_row(float x1x, float x1y, float x2x, float x2y, float *row /*
         row[8 + j] = tf32_round(phi[j] - hi);
         row[16 + j] = tf32_round(psi[j]);
     }
-    row[24] = tf32_round(x2x); row[25] = tf32_round(x2y); row[26] = 1.0f; row[27] = 1.0f;
-    row[28] = row[29] = row[30] = row[31] = 0.0f;
+    row[24] = tf32_round(x2x); row[25] = tf32_round(x2y); row[26] = 1.0f;
+    row[27] = row[28] = row[29] = row[30] = row[31] = 0.0f;
 }
 
-// ---- per-model operand row (A operand): 5 slices of 8 floats ---------------------------------------------
-//   a0 = tf32(2^s E_j)  a1 = tf32(2^s E_j - a0)  a2 = (0, 0, E22 hi, E22 lo, 0...)            -> Cs
-//   a3 = tf32(-2^2s (1+a) g G_0..7)   a4 = (G_8', G_9', const, 0...)                           -> Ts
+// ---- per-model operand row (A operand): 4 slices of 8 floats ---------------------------------------------
+//   a0 = tf32(2^s E_j)   a1 = tf32(2^s E_j - a0)                                      . slice 0 / 1 / 0 of B  -> Cs
+//   a2 = tf32(-2^2s (1+a) g G_0..7)                                                    . slice 2               -> Ts
+//   a3 = (G_8', G_9', const, 0 | E22 hi, E22 lo, 0, 0)   . slice 3 (x2x, x2y, 1, 0 | 0...) -> Ts,  . slice K -> Cs
 // A model whose parameters leave the range the error model covers gets the zero row (no point is ever counted:
 // the model simply survives this tier); a model with a non-finite E / F — the minimal solvers return NaN models
 // now and then — has r2 = NaN for every correspondence in the reference, i.e. no inliers and score N thr^2:
 // its row is (0, ..., const = +2^100), which counts EVERY point.
-RP_HD void model_row(const M3 &E, double thr, double Mmax, double mmax, float *r0 /*32: a0 a1 a2 a3*/, float *r1 /*8: a4*/) {
+RP_HD void model_row(const M3 &E, double thr, double Mmax, double mmax, float *r0 /*32: a0 a1 a2 a3*/) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) r0[i] = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) r1[i] = 0.f;
     const double e[9] = {E.r0.x, E.r0.y, E.r0.z, E.r1.x, E.r1.y, E.r1.z, E.r2.x, E.r2.y, E.r2.z};
     double emax = 0.0;
     bool finite = true;
 #pragma unroll
     for (int i = 0; i < 9; ++i) { emax = fmax(emax, fabs(e[i])); finite = finite && (e[i] - e[i] == 0.0); }
-    if (!finite) { r1[2] = 1.2676506002282294e30f; return; }   // 2^100
+    if (!finite) { r0[24 + 2] = 1.2676506002282294e30f; return; }   // 2^100
     const bool sane = emax > 1e-3 && emax < 1e3 && thr > 1e-6 && thr < 1.0 && Mmax < 1e3 && mmax < 1e3;
     if (!sane) return;
     const double u = 5.9604644775390625e-08;  // 2^-24
@@ -146,8 +133,8 @@ RP_HD void model_row(const M3 &E, double thr, double Mmax, double mmax, float *r
     {
         const float v = (float)(e[8] * cs);
         const float hi = tf32_round(v);
-        r0[16 + 2] = hi;
-        r0[16 + 3] = tf32_round(v - hi);
+        r0[24 + 4] = hi;
+        r0[24 + 5] = tf32_round(v - hi);
     }
     const double G[11] = {e[0] * e[0] + e[3] * e[3], 2.0 * (e[0] * e[1] + e[3] * e[4]), e[1] * e[1] + e[4] * e[4],
                           2.0 * (e[0] * e[2] + e[3] * e[5]), 2.0 * (e[1] * e[2] + e[4] * e[5]),
@@ -156,12 +143,12 @@ RP_HD void model_row(const M3 &E, double thr, double Mmax, double mmax, float *r
                           e[2] * e[2] + e[5] * e[5] + e[6] * e[6] + e[7] * e[7]};
     const double k = -ts * (1.0 + A_SPLIT) * g;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) r0[24 + j] = tf32_round((float)(k * G[j]));
-    r1[0] = tf32_round((float)(k * G[8]));
-    r1[1] = tf32_round((float)(k * G[9]));
+    for (int j = 0; j < 8; ++j) r0[16 + j] = tf32_round((float)(k * G[j]));
+    r0[24] = tf32_round((float)(k * G[8]));
+    r0[25] = tf32_round((float)(k * G[9]));
     // the constant: pushed away from zero by 2^-9 before rounding (more negative = fewer certain outliers = conservative)
     const double kc = (k * (G[10] + dden) - ts * (1.0 + 1.0 / A_SPLIT) * eps * eps) * (1.0 + 0.001953125);
-    r1[2] = tf32_round((float)kc);
+    r0[26] = tf32_round((float)kc);
 }
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------
@@ -226,6 +213,9 @@ RP_D bool elect_one() {
     asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
     return pred != 0;
 }
+RP_D unsigned long long pack2f(float lo, float hi) { unsigned long long r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+RP_D void unpack2f(unsigned long long v, float &lo, float &hi) { asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+RP_D unsigned long long add2(unsigned long long a, unsigned long long b) { unsigned long long d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 RP_D float fma_sat(float a, float b, float c) {
     float d;
     asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
@@ -237,12 +227,6 @@ RP_D float fma_sat(float a, float b, float c) {
 RP_D uint64_t desc_sw128(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3ffffu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
-// kind::tf32, FP32 accumulate, A and B K-major, M = 128, N = NT
-constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
-
-// byte offset of (row, 16-byte chunk) inside a SWIZZLE_128B region (Swizzle<3,4,3> on a 1024-aligned base)
-RP_D uint32_t sw128_off(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
-
 // ---- feature kernel ------------------------------------------------------------------------------------------
 // one thread per correspondence: pts32 (float4) -> 128-byte feature row
 __global__ void tc_features_kernel(long long n, const float4 *pts32, float4 *feat) {
@@ -271,31 +255,75 @@ struct TcArgs {
     int debug_cols;
 };
 
+// ---- the kernel -------------------------------------------------------------------------------------------------
+constexpr int NT = 64;                                       // points per accumulator tile (MMA N)
+constexpr int A_COLS = 32;                                   // a0 a1 a2 a3, 8 TMEM columns each
+constexpr int SLOTS = 3;                                     // accumulator slots (one M-tile x one point tile: Cs | Ts)
+constexpr int TMEM_A = SLOTS * 2 * NT;                       // first A column: 384
+constexpr int B_STAGE_BYTES = NT * 128;
+constexpr int B_STAGES = 6;
+constexpr int KSLICE_BYTES = NT * 32;                        // constant slice, SWIZZLE_NONE K-major: 8-row groups of 256 B
+constexpr int EPI_WARP0 = 4, BUILD_WARP0 = EPI_WARP0 + 4 * MT, THREADS = 32 * (BUILD_WARP0 + 4);
+constexpr int SMEM_BYTES = 1024 + B_STAGES * B_STAGE_BYTES + KSLICE_BYTES + 256;
+// kind::tf32, FP32 accumulate, A and B K-major, M = 128, N = NT
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
+static_assert(TMEM_A + 2 * MT * A_COLS == 512, "accumulator slots + A buffers fill the tensor memory exactly");
+
+// K-major SWIZZLE_NONE descriptor of the constant slice: core matrices (8 rows x 16 B) 128 B apart along K, 8-row groups
+// 256 B apart
+RP_D uint64_t desc_kslice(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3ffffu) >> 4) | (8ull << 16) | (16ull << 32) | (1ull << 46);
+}
+RP_D void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}"
+                 ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+RP_D void tmem_st8(uint32_t taddr, const float *v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+                   "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])),
+                   "r"(__float_as_uint(v[7])) : "memory");
+}
+RP_D void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+RP_D void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr) : "memory");
+}
+
 // MODE 0: the tier.  Probe modes (tools/tc_probe.cu): 1 = epilogue loads the accumulators but skips the arithmetic,
 // 2 = epilogue neither loads nor computes (TMA + MMA pipeline alone).
 template <int MODE>
 __global__ void __launch_bounds__(THREADS, 1) tc_count_kernel(const __grid_constant__ CUtensorMap tmap, TcArgs a) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t *sA = smem;                                   // [2][MT][2 regions][16 KB]
-    uint8_t *sB = smem + 2 * A_BUF_BYTES;                 // [B_STAGES][8 KB]
-    uint64_t *bars = (uint64_t *)(sB + B_STAGES * B_STAGE_BYTES);
+    uint8_t *sB = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // [B_STAGES][NT x 128 B]
+    uint8_t *sK = sB + B_STAGES * B_STAGE_BYTES;                                   // constant slice
+    uint64_t *bars = (uint64_t *)(sK + KSLICE_BYTES);
     uint64_t *b_full = bars, *b_empty = bars + B_STAGES, *a_full = bars + 2 * B_STAGES, *a_empty = a_full + 2,
-             *acc_full = a_empty + 2, *acc_empty = acc_full + ACC_STAGES;
-    uint32_t *tmem_base_s = (uint32_t *)(acc_empty + ACC_STAGES);
+             *slot_full = a_empty + 2, *slot_empty = slot_full + SLOTS;
+    uint32_t *tmem_base_s = (uint32_t *)(slot_empty + SLOTS);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         for (int i = 0; i < B_STAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], BUILD_WARPS * 32); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], EPI_WARPS); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 4); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < SLOTS; ++i) { mbar_init(&slot_full[i], 1); mbar_init(&slot_empty[i], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) tmem_alloc(tmem_base_s, TMEM_COLS);
+    if (warp == 0) tmem_alloc(tmem_base_s, 512);
+    // the constant slice (0,0,0,0 | 1,1,0,0) per row: row r, 16-byte chunk c at (r / 8) * 256 + c * 128 + (r % 8) * 16
+    for (int i = tid; i < NT * 2; i += THREADS) {
+        const int r = i >> 1, c = i & 1;
+        *(float4 *)(sK + (r >> 3) * 256 + c * 128 + (r & 7) * 16) = c ? make_float4(1.f, 1.f, 0.f, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_s;
+    const uint32_t tmem_a = tmem_base + (uint32_t)TMEM_A;
     const int n_items = *a.n_items;
 
     auto pair_of = [&](int item) {
@@ -308,7 +336,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_count_kernel(const __grid_const
     };
 
     if (warp == 0) {
-        // ===== TMA producer: the pair's feature rows, 64 at a time (converged warp, one elected lane issues) =====
+        // ===== TMA producer =====
         int st = 0;
         uint32_t ph = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -325,111 +353,118 @@ __global__ void __launch_bounds__(THREADS, 1) tc_count_kernel(const __grid_const
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer (converged warp, one elected lane issues) =====
-        int st = 0, as = 0, k = 0;
-        uint32_t ph = 0, aph = 0;
+        // ===== MMA issuer: per point tile one group of 6 MMAs per M-tile, each group into its own accumulator slot =====
+        int st = 0, k = 0;
+        uint32_t ph = 0;
+        unsigned seq = 0;   // running (point tile, M-tile) index: slot = seq % SLOTS
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
             const PairParams pp = a.pairs[pair_of(item)];
             const int ntiles = (pp.n + NT - 1) / NT;
             const int ab = k & 1;
             mbar_wait(&a_full[ab], (k >> 1) & 1);
             tc_fence_after();
-            const uint32_t a_base = smem_u32(sA + ab * A_BUF_BYTES);
             for (int t = 0; t < ntiles; ++t) {
-                mbar_wait(&acc_empty[as], aph ^ 1);
                 mbar_wait(&b_full[st], ph);
-                tc_fence_after();
-                if (elect_one()) {
-                    const uint32_t b_base = smem_u32(sB + st * B_STAGE_BYTES);
-                    const uint64_t b0 = desc_sw128(b_base), b1 = desc_sw128(b_base + 32), b2 = desc_sw128(b_base + 64),
-                                   b3 = desc_sw128(b_base + 96);
 #pragma unroll
-                    for (int m = 0; m < MT; ++m) {
-                        const uint32_t r0 = a_base + (m * 2) * A_REGION_BYTES, r1 = r0 + A_REGION_BYTES;
-                        const uint32_t dC = tmem_base + (uint32_t)(((as * MT + m) * 2) * NT), dT = dC + NT;
-                        umma_tf32(dC, desc_sw128(r0), b0, IDESC, 0);        // E_hi . phi_hi
-                        umma_tf32(dC, desc_sw128(r0 + 32), b0, IDESC, 1);   // E_lo . phi_hi
-                        umma_tf32(dC, desc_sw128(r0), b1, IDESC, 1);        // E_hi . phi_lo
-                        umma_tf32(dC, desc_sw128(r0 + 64), b3, IDESC, 1);   // E22 (hi, lo) . (1, 1)
-                        umma_tf32(dT, desc_sw128(r0 + 96), b2, IDESC, 0);   // G_0..7 . psi_0..7
-                        umma_tf32(dT, desc_sw128(r1), b3, IDESC, 1);        // G_8, G_9, const . (x2x, x2y, 1)
+                for (int m = 0; m < MT; ++m) {
+                    const unsigned slot = (seq + m) % SLOTS;
+                    mbar_wait(&slot_empty[slot], (((seq + m) / SLOTS) & 1) ^ 1);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t b_base = smem_u32(sB + st * B_STAGE_BYTES);
+                        const uint64_t b0 = desc_sw128(b_base), b1 = desc_sw128(b_base + 32), b2 = desc_sw128(b_base + 64),
+                                       b3 = desc_sw128(b_base + 96), bK = desc_kslice(smem_u32(sK));
+                        const uint32_t ar = tmem_a + (uint32_t)((ab * MT + m) * A_COLS);
+                        const uint32_t dC = tmem_base + slot * (2 * NT), dT = dC + NT;
+                        umma_tf32_ts(dC, ar, b0, IDESC, 0);        // E_hi . phi_hi
+                        umma_tf32_ts(dC, ar + 8, b0, IDESC, 1);    // E_lo . phi_hi
+                        umma_tf32_ts(dC, ar, b1, IDESC, 1);        // E_hi . phi_lo
+                        umma_tf32_ts(dC, ar + 24, bK, IDESC, 1);   // E22 (hi, lo) . (1, 1)            [constant slice]
+                        umma_tf32_ts(dT, ar + 16, b2, IDESC, 0);   // G_0..7 . psi_0..7
+                        umma_tf32_ts(dT, ar + 24, b3, IDESC, 1);   // G_8, G_9, const . (x2x, x2y, 1)
+                        umma_commit(&slot_full[slot]);
+                        if (m == MT - 1) {
+                            umma_commit(&b_empty[st]);
+                            if (t == ntiles - 1) umma_commit(&a_empty[ab]);
+                        }
                     }
-                    umma_commit(&b_empty[st]);      // the smem stage is free once these MMAs have read it
-                    umma_commit(&acc_full[as]);     // ... and the accumulators are ready for the epilogue
-                    if (t == ntiles - 1) umma_commit(&a_empty[ab]);   // the A buffer may be rebuilt
+                    __syncwarp();
                 }
-                __syncwarp();
+                seq += MT;
                 if (++st == B_STAGES) { st = 0; ph ^= 1; }
-                if (++as == ACC_STAGES) { as = 0; aph ^= 1; }
             }
         }
     } else if (warp >= EPI_WARP0 && warp < BUILD_WARP0) {
-        // ===== epilogue: thread = model =====
-        const int ew = warp - EPI_WARP0;
-        const int m = ew / 4, q = warp & 3;          // M-tile, TMEM lane quarter this warp may access
+        // ===== epilogue: group m = the four warps of M-tile m, thread = model =====
+        const int m = (warp - EPI_WARP0) / 4, q = warp & 3;
         const int row = m * 128 + q * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-        int as = 0, k = 0;
-        uint32_t aph = 0;
+        unsigned seq = (unsigned)m;
         unsigned long long evaluated = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
-            const PairParams pp = a.pairs[pair_of(item)];
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int pair = pair_of(item);
+            const PairParams pp = a.pairs[pair];
             const int n = pp.n;
             const int ntiles = (n + NT - 1) / NT;
-            float acc0 = 0.f, acc1 = 0.f;
-            for (int t = 0; t < ntiles; ++t) {
-                mbar_wait(&acc_full[as], aph);
+            float acc0 = 0.f;
+            unsigned long long accA = 0ull, accB = 0ull;   // packed FP32 pairs
+            for (int t = 0; t < ntiles; ++t, seq += MT) {
+                const unsigned slot = seq % SLOTS;
+                mbar_wait(&slot_full[slot], (seq / SLOTS) & 1);
                 tc_fence_after();
-                const uint32_t cC = lane_addr + (uint32_t)(((as * MT + m) * 2) * NT), cT = cC + NT;
+                const uint32_t cC = lane_addr + slot * (2 * NT), cT = cC + NT;
                 const int nv = min(NT, n - t * NT);
+                if (MODE != 2) {
 #pragma unroll
-                for (int h = 0; h < NT / 32; ++h) {
-                    if (MODE == 2) continue;
-                    uint32_t c[32], tt[32];
-                    tmem_ld32(cC + h * 32, c);
-                    tmem_ld32(cT + h * 32, tt);
-                    tmem_ld_wait();
-                    if (MODE == 1) {
-                        acc0 += __uint_as_float(c[0] ^ c[31]) + __uint_as_float(tt[0] ^ tt[31]);
-                        continue;
-                    }
-                    if (a.debug && item == 0) {
+                    for (int h = 0; h < NT; h += 32) {
+                        uint32_t c[32], tt[32];
+                        tmem_ld32(cC + h, c);
+                        tmem_ld32(cT + h, tt);
+                        tmem_ld_wait();
+                        if (a.debug && item == 0) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const int col = t * NT + h * 32 + j;
-                            if (col < a.debug_cols) {
-                                a.debug[((size_t)row * 2 + 0) * a.debug_cols + col] = __uint_as_float(c[j]);
-                                a.debug[((size_t)row * 2 + 1) * a.debug_cols + col] = __uint_as_float(tt[j]);
+                            for (int j = 0; j < 32; ++j) {
+                                const int col = t * NT + h + j;
+                                if (col < a.debug_cols) {
+                                    a.debug[((size_t)row * 2 + 0) * a.debug_cols + col] = __uint_as_float(c[j]);
+                                    a.debug[((size_t)row * 2 + 1) * a.debug_cols + col] = __uint_as_float(tt[j]);
+                                }
                             }
                         }
-                    }
-                    if (nv >= (h + 1) * 32) {
+                        if (MODE == 1) {
+                            acc0 += __uint_as_float(c[0] ^ c[31]) + __uint_as_float(tt[0] ^ tt[31]);
+                        } else if (nv >= h + 32) {
+                            // 1 FFMA.SAT per point-score + 1 packed FADD2 per two; four independent accumulation chains
 #pragma unroll
-                        for (int j = 0; j < 32; j += 2) {
-                            acc0 += fma_sat(__uint_as_float(c[j]), __uint_as_float(c[j]), __uint_as_float(tt[j]));
-                            acc1 += fma_sat(__uint_as_float(c[j + 1]), __uint_as_float(c[j + 1]), __uint_as_float(tt[j + 1]));
+                            for (int j = 0; j < 32; j += 4) {
+                                const float s0 = fma_sat(__uint_as_float(c[j]), __uint_as_float(c[j]), __uint_as_float(tt[j]));
+                                const float s1 = fma_sat(__uint_as_float(c[j + 1]), __uint_as_float(c[j + 1]), __uint_as_float(tt[j + 1]));
+                                const float s2 = fma_sat(__uint_as_float(c[j + 2]), __uint_as_float(c[j + 2]), __uint_as_float(tt[j + 2]));
+                                const float s3 = fma_sat(__uint_as_float(c[j + 3]), __uint_as_float(c[j + 3]), __uint_as_float(tt[j + 3]));
+                                accA = add2(accA, pack2f(s0, s1));
+                                accB = add2(accB, pack2f(s2, s3));
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (h + j < nv) acc0 += fma_sat(__uint_as_float(c[j]), __uint_as_float(c[j]), __uint_as_float(tt[j]));
                         }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (h * 32 + j < nv)
-                                acc0 += fma_sat(__uint_as_float(c[j]), __uint_as_float(c[j]), __uint_as_float(tt[j]));
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_empty[as]);
-                if (++as == ACC_STAGES) { as = 0; aph ^= 1; }
+                if (lane == 0) mbar_arrive(&slot_empty[slot]);
             }
-            // logical model j of the pair -> (segment, index) -> slot
-            const int pair = pair_of(item);
             int j = (item - a.item_prefix[pair]) * TILE_MODELS + row;
             const int *segc = a.seg_count + (size_t)pair * a.nseg;
             for (int seg = 0; seg < a.nseg; ++seg) {
                 const int c = segc[seg];
                 if (j < c) {
+                    float a0, a1, b0, b1;
+                    unpack2f(accA, a0, a1);
+                    unpack2f(accB, b0, b1);
                     // every addend is exactly 0 or 1 (model_row's scaling), so the FP32 sums are exact counts
-                    a.out[((size_t)pair * a.nseg + seg) * (size_t)(4 * SEG) + j] = (int)(acc0 + acc1);
+                    a.out[((size_t)pair * a.nseg + seg) * (size_t)(4 * SEG) + j] = (int)(acc0 + a0 + a1 + b0 + b1);
                     evaluated += (unsigned long long)n;
                     break;
                 }
@@ -441,51 +476,51 @@ __global__ void __launch_bounds__(THREADS, 1) tc_count_kernel(const __grid_const
             if (lane == 0 && evaluated) atomicAdd(a.evaluated, evaluated);
         }
     } else if (warp >= BUILD_WARP0) {
-        // ===== A builder: 64 threads, 4 models each per work item =====
-        const int bt = tid - BUILD_WARP0 * 32;
+        // ===== A builder: four warps = the 128 TMEM lanes; thread = row, MT rows per work item, written with tcgen05.st =====
+        const int q = warp & 3;
+        const uint32_t lane_addr = tmem_a + ((uint32_t)(q * 32) << 16);
         int k = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
             const int pair = pair_of(item);
             const PairParams pp = a.pairs[pair];
             const int ab = k & 1;
             mbar_wait(&a_empty[ab], ((k >> 1) & 1) ^ 1);
+            tc_fence_after();
             const int j0 = (item - a.item_prefix[pair]) * TILE_MODELS;
             const int *segc = a.seg_count + (size_t)pair * a.nseg;
-            for (int r = bt; r < TILE_MODELS; r += BUILD_WARPS * 32) {
-                // logical model j of the pair -> (segment, index) -> pair-relative slot
-                int j = j0 + r, seg = 0, slot = -1;
+#pragma unroll 1
+            for (int m = 0; m < MT; ++m) {
+                int j = j0 + m * 128 + q * 32 + lane, seg = 0, slot = -1;
                 while (seg < a.nseg) {
                     const int c = segc[seg];
                     if (j < c) { slot = seg * (4 * SEG) + j; break; }
                     j -= c;
                     ++seg;
                 }
-                float r0[32], r1[8];
+                float r0[32];
                 if (slot >= 0) {
                     const Model mdl = a.models[((size_t)pair * a.nseg) * (size_t)(4 * SEG) + slot];
                     const M3 E = a.pose ? essential_from_motion(mdl.q, mdl.t) : fundamental_from_model(mdl);
-                    model_row(E, pp.thr, pp.Mmax, pp.mmax, r0, r1);
+                    model_row(E, pp.thr, pp.Mmax, pp.mmax, r0);
                 } else {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) r0[i] = 0.f;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) r1[i] = 0.f;
                 }
-                const int m = r >> 7, rr = r & 127;
-                uint8_t *reg0 = sA + ab * A_BUF_BYTES + (m * 2) * A_REGION_BYTES, *reg1 = reg0 + A_REGION_BYTES;
-#pragma unroll
-                for (int c = 0; c < 8; ++c)
-                    *(float4 *)(reg0 + sw128_off(rr, c)) = make_float4(r0[4 * c], r0[4 * c + 1], r0[4 * c + 2], r0[4 * c + 3]);
-                *(float4 *)(reg1 + sw128_off(rr, 0)) = make_float4(r1[0], r1[1], r1[2], r1[3]);
-                *(float4 *)(reg1 + sw128_off(rr, 1)) = make_float4(r1[4], r1[5], r1[6], r1[7]);
+                const uint32_t ta = lane_addr + (uint32_t)((ab * MT + m) * A_COLS);
+                tmem_st8(ta, r0);
+                tmem_st8(ta + 8, r0 + 8);
+                tmem_st8(ta + 16, r0 + 16);
+                tmem_st8(ta + 24, r0 + 24);
             }
-            fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
-            mbar_arrive(&a_full[ab]);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a_full[ab]);
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
+    if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 #endif  // __CUDACC__
 

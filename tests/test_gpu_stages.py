@@ -59,7 +59,10 @@ def test_solvers_vs_golden_and_oracle(ctx, port, stages, variant):
         assert len(o) == counts[i]
         for a, b in zip(o, got):
             assert np.allclose(model_vec(a), model_vec(b), rtol=1e-9, atol=1e-12, equal_nan=True)
-    limit = 0 if variant in ("calib", "varying") else max(2, len(x1h) // 50)
+    # S1 / S4: none.  S2: the binary's raw roots are imprecise and its 5-step polish then lands on another root, a
+    # duplicate, or a negative-depth solution in 0.45 % of the samples (measured over 40 000 triplets);
+    # S3: duplicated pseudo-solutions from complex eigenvalue pairs in 0.14 % (30 000 triplets).  Budgets: 3x those rates.
+    limit = {"calib": 0, "varying": 0, "calib_shift": max(2, len(x1h) // 75), "shared": max(1, len(x1h) // 250)}[variant]
     assert bad_ref <= limit
 
 

@@ -87,7 +87,8 @@ def test_solvers(ref, port, variant):
             mine = port.solve_shared_focal(x1h, x2h, d1, d2) if variant == "shared" else port.solve_varying_focal(x1h, x2h, d1, d2)
             ok = same_set(dedup(r), dedup(mine))
         bad += not ok
-    limit = 0 if variant in ("calib", "varying") else n_trials // 50
+    # measured quirk rates of the binary's S2 / S3: 0.45 % / 0.14 % of the samples; budgets 3x
+    limit = {"calib": 0, "varying": 0, "calib_shift": n_trials // 75, "shared": n_trials // 250}[variant]
     assert bad <= limit, f"{bad}/{n_trials} solution sets differ"
 
 
