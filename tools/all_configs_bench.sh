@@ -10,8 +10,8 @@ import json, sys
 try:
     d = json.load(open(f"gpurun_out/cfg_{sys.argv[1]}.json"))
     s = d["stage_ms_per_step"]
-    print("%-20s value %8.0f e2e %8.0f pairs/s | solve %.1f score %.1f (bound %.1f) lo %.1f final %.1f total %.1f ms" % (
-        sys.argv[1], d["value"], d["e2e"]["value"], s["solve"], s["score_minimal"], s["bound_kernel"], s["lo_refine"], s["final_refine"], s["device_total"]))
+    print("%-20s value %8.0f e2e %8.0f pairs/s | solve %.1f score %.1f (tc %.1f bound %.1f) lo %.1f final %.1f total %.1f ms" % (
+        sys.argv[1], d["value"], d["e2e"]["value"], s["solve"], s["score_minimal"], s["tc_kernel"], s["bound_kernel"], s["lo_refine"], s["final_refine"], s["device_total"]))
 except Exception as e:
     print(sys.argv[1], "failed", e)
 PY

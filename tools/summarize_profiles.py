@@ -25,7 +25,10 @@ KEYS = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_
         "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
         "smsp__thread_inst_executed_per_inst_executed.ratio", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
-        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed"]
 
 
 def launches(tag):
@@ -45,7 +48,7 @@ def launches(tag):
         a = agg.setdefault(name, [0, 0.0])
         a[0] += 1
         a[1] += v
-    ours = {k: v for k, v in agg.items() if "rp::" in k or "<unnamed>" in k}
+    ours = {k: v for k, v in agg.items() if "rp::" in k or "tc::" in k or "<unnamed>" in k}
     tot = sum(v[1] for k, v in ours.items() if "pipe_kernel" not in k)
     out = [f"# ncu --metrics gpu__time_duration.sum --clock-control none, `python bench.py --steps 1 --warmup 1 --no-cpu-baseline`",
            "# per-launch times are cold-cache and serialised: compare SHARES (pipeline kernels only; the two",
@@ -85,7 +88,7 @@ def main():
         subprocess.run(["cp", os.path.join(GO, f"{tag}_launches.csv"), os.path.join(PR, f"{tag}_launches.csv")])
         parts.append(txt)
     traffic = {}
-    for name in ("bound", "lm", "score_survivors", "solve"):
+    for name in ("tc", "bound", "lm", "score_survivors", "solve"):
         rep = os.path.join(GO, f"{tag}_{name}.ncu-rep")
         if os.path.exists(rep):
             txt, d = ncu_raw(rep)
@@ -98,6 +101,23 @@ def main():
             except Exception:
                 pass
     open(os.path.join(PR, f"{tag}_ncu_summary.txt"), "w").write("\n\n".join(parts) + "\n")
+    # SASS evidence: the Blackwell-only instructions of the shipped library (B200_PROFILING.md "What proves a Blackwell-native kernel")
+    so = os.path.join(ROOT, "mdrp_b200", "librepose_b200.so")
+    if os.path.exists(so):
+        sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
+        import re
+        ops = collections.Counter(m.group(1).split(".")[0] for m in re.finditer(r"^\s+/\*[0-9a-f]+\*/\s+([A-Z0-9_.]+)", sass, re.M))
+        want = ["UTCHMMA", "UTCBAR", "UTCATOMSWS", "LDTM", "STTM", "UTMALDG", "SYNCS", "FFMA2", "FADD2", "FMUL2", "FFMA", "DFMA", "DMUL", "DADD", "HMMA"]
+        lines = ["# cuobjdump -sass mdrp_b200/librepose_b200.so: instruction counts (static) of the opcodes that matter",
+                 "# UTCHMMA = tcgen05.mma, LDTM / STTM = tcgen05.ld / st, UTMALDG = cp.async.bulk.tensor (TMA), UTCBAR = tcgen05.commit,",
+                 "# SYNCS = mbarrier ops, FFMA2 / FADD2 / FMUL2 = packed f32x2 (sm_100 only); HMMA (legacy mma.sync) must be absent"]
+        lines += [f"{k:12s} {ops.get(k, 0)}" for k in want]
+        ex = [l for l in sass.splitlines() if re.search(r"UTCHMMA|LDTM|STTM|UTMALDG|FFMA\.SAT|FADD2", l)][:24]
+        lines += ["", "# excerpt (tc_count_kernel):"] + [l.rstrip()[:150] for l in ex]
+        open(os.path.join(PR, f"{tag}_sass_excerpt.txt"), "w").write("\n".join(lines) + "\n")
+    for f in (f"{tag}_all_configs.txt", f"{tag}_head_sweep.txt"):
+        if os.path.exists(os.path.join(GO, f)):
+            subprocess.run(["cp", os.path.join(GO, f), os.path.join(PR, f)])
     for f in (f"{tag}_bench.json", f"{tag}_bench_reference.json"):
         if os.path.exists(os.path.join(GO, f)):
             subprocess.run(["cp", os.path.join(GO, f), os.path.join(PR, f)])
