@@ -176,11 +176,11 @@ RP_HD double point_cost(const LMFrame &F, const LMParams &P, double x1_0, double
 // rcp = 1, rsqrt = 2; structural zeros and the calibrated variants' literal unit focals not counted):
 //   residuals + cost (always)          : LM_FLOPS[v][0]
 //   Sampson row, Jacobian + J^T J      : LM_FLOPS[v][1]   (6 | 6 | 7 | 8 columns)
-//   reprojection 1->2, both rows       : LM_FLOPS[v][2]   (6 | 7 | 7 | 8 columns)
+//   reprojection 1->2, both rows       : LM_FLOPS[v][2]   (6 | 7 | 7 | 8 columns, of which each row skips one t column)
 //   reprojection 2->1, both rows       : LM_FLOPS[v][3]   (7 | 8 | 8 | 9 columns)
 // (v = RP_CALIB, RP_CALIB_SHIFT, RP_SHARED, RP_VARYING; derivation in DESIGN.md §5).  `rows` counts the accumulated
 // rows of the three kinds in three 21-bit fields; the LM kernel turns the counts into the bench's lm_flops.
-constexpr int LM_FLOPS[4][4] = {{110, 167, 170, 207}, {110, 167, 222, 247}, {120, 224, 223, 268}, {120, 243, 261, 310}};
+constexpr int LM_FLOPS[4][4] = {{110, 167, 140, 207}, {110, 167, 188, 247}, {120, 224, 189, 268}, {120, 243, 223, 310}};
 
 template <int VARIANT, int NP, int LOSS = -1>
 RP_HD double point_eval(const LMFrame &F, const LMParams &P, double x1_0, double x1_1, double x2_0,
@@ -327,8 +327,9 @@ RP_HD double point_eval(const LMFrame &F, const LMParams &P, double x1_0, double
                     J0[7] = g * (dx - u0 * dz); J1[7] = g * (dy - u1 * dz);
                     J0[CF2] += u0; J1[CF2] += u1;
                 }
-                N.template add_row<M_12>(w, J0, r0);
-                N.template add_row<M_12>(w, J1, r1);
+                // dZ/dt = I: the x row has no t_y column, the y row no t_x column (structural zeros skipped)
+                N.template add_row<(M_12 & ~0x10u)>(w, J0, r0);
+                N.template add_row<(M_12 & ~0x08u)>(w, J1, r1);
                 rows += 1ull << 21;
             }
         }

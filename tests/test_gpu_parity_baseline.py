@@ -16,13 +16,16 @@ from mdrp_b200 import _native as nv, synth
 
 pytestmark = pytest.mark.gpu
 
-# (config, pairs, max refinements-only, max different)
+# (config, pairs, max refinements-only, max different).  Measured over 2 048 pairs per config (1 024 for cfg5) against the wheel
+# (profiles/r02_parity_at_size.json): cfg1 / cfg4 / cfg5 identical in every pair; cfg2 2.4 % refinements-only
+# and 0.1 % different; cfg3 1.0 % and 0.15 %.  "different" there means: same final model (1e-6), mask and num_inliers, but
+# the reported model_score (the in-loop best before the final refinement) off by 1e-9..1e-6 relative.  Budgets: ~3x the rates.
 CASES = [
-    ("cfg1_calib_scale", 128, 2, 0),
-    ("cfg2_calib_shift", 64, 2, 2),
-    ("cfg3_shared_focal", 64, 2, 2),
-    ("cfg4_varying_focal", 64, 2, 1),
-    ("cfg5_roma_calib", 32, 1, 0),
+    ("cfg1_calib_scale", 128, 0, 0),
+    ("cfg2_calib_shift", 64, 5, 1),
+    ("cfg3_shared_focal", 64, 3, 1),
+    ("cfg4_varying_focal", 64, 0, 0),
+    ("cfg5_roma_calib", 32, 0, 0),
 ]
 
 
@@ -53,3 +56,5 @@ def test_baseline_size_vs_reference(ctx, ref, cfg, pairs, max_ties, max_diff):
     # even a `different` pair is a valid estimate of the same scene: inlier count within 2 % of the reference's
     for i in np.nonzero(cls == 2)[0]:
         assert abs(int(stats[i]["num_inliers"]) - int(r["stats"][i][2])) <= 0.02 * c["n"], (i, rec)
+    # whatever the class: iterations always agree, and at least all but the budgeted pairs have the reference's mask
+    assert rec["mask_equal"] >= pairs - max_diff
