@@ -1129,6 +1129,42 @@ __global__ void tc_select_kernel(TcSelectArgs a) {
     }
 }
 
+// the same decision after the second pass of the tensor-core tier, over the first pass's list (compacted in place:
+// a batch of 32 entries is read before its survivors are written at or before the batch's first position)
+__global__ void tc_select_list_kernel(TcSelectArgs a) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= a.n_pairs) return;
+    const PairParams pp = a.pairs[warp];
+    const size_t slots_pp = (size_t)a.nseg * (4 * SEG);
+    const size_t pslot = (size_t)warp * slots_pp;
+    const int n = pp.n;
+    const float thr2_lo = __double2float_rd(pp.sq_thr);
+    const int B0 = a.B0[warp];
+    const double S0 = a.S0[warp];
+    const double need_d = fmax((double)(n - B0), S0 < 1e300 ? ceil(S0 / ((double)thr2_lo * (1.0 - 2e-4))) : 4.0e9);
+    const int need_out = need_d > 2.0e9 ? 0x7fffffff : max((int)need_d, 1);
+    const int cnt = a.list_cnt[warp];
+    int ns = 0;
+    for (int base = 0; base < cnt; base += 32) {
+        const int i = base + lane;
+        const int rel = i < cnt ? a.list[pslot + i] : 0;
+        bool keep = false;
+        if (i < cnt) {
+            keep = a.out[pslot + rel] < need_out;
+            if (!keep) { a.ub[pslot + rel] = 0; a.lb[pslot + rel] = INFINITY; }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        __syncwarp();
+        if (keep) a.list[pslot + ns + __popc(m & ((1u << lane) - 1u))] = rel;
+        ns += __popc(m);
+    }
+    if (lane == 0) {
+        a.list_cnt[warp] = ns;
+        if (a.n_selected && ns) atomicAdd(a.n_selected, (unsigned long long)ns);
+    }
+}
+
 // B0 / S0 of a pair: max count and min score over its first `first_cnt` (<= HB) models, scored exactly
 __global__ void pair_bounds_kernel(int n_pairs, int nseg, const int *first_cnt, const double *score, const int *count,
                                    int *B0, double *S0) {

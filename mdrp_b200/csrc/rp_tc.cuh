@@ -253,7 +253,22 @@ struct TcArgs {
     unsigned long long *evaluated;  // optional: point-scores evaluated
     float *debug;                // optional: raw (Cs, Ts) of work item 0, [TILE_MODELS][2][debug_cols]
     int debug_cols;
+    // Two passes over the correspondences (abandonment at the granularity of this tier): pass 0 counts over the first
+    // tc_split(n) correspondences of every model, the caller drops what already has enough certain outliers, pass 1
+    // counts the remaining correspondences for the survivors only (`list`) and adds to `out`.
+    int two_pass;                // 0: one pass over all correspondences; else the first pass covers two_pass/16 of them
+    int pass;                    // 0 / 1
+    const int *list;             // pass 1: pair-relative slots of the models to process, [n_pairs][list_stride]
+    const int *list_cnt;         //         [n_pairs]
+    int list_stride;
 };
+
+// first correspondence of pass 1 (a multiple of the point tile; n itself when the pair is too small to split)
+RP_HD int tc_split(int n, int sixteenths) {
+    if (n < 4 * 64) return n;
+    const int s = (int)(((long long)n * sixteenths / 16 + 63) / 64) * 64;
+    return s < n ? s : n;
+}
 
 // ---- the kernel -------------------------------------------------------------------------------------------------
 constexpr int NT = 64;                                       // points per accumulator tile (MMA N)
@@ -335,14 +350,35 @@ __global__ void __launch_bounds__(THREADS, 1) tc_count_kernel(const __grid_const
         return lo;
     };
 
+    // correspondences [p0, p1) of this pass, as point tiles [t0, t1)
+    auto tile_range = [&](const PairParams &pp, int &t0, int &t1, int &p1) {
+        const int sp = a.two_pass ? tc_split(pp.n, a.two_pass) : pp.n;
+        const int p0 = a.pass ? sp : 0;
+        p1 = a.pass ? pp.n : sp;
+        t0 = p0 / NT;
+        t1 = p1 > p0 ? (p1 + NT - 1) / NT : t0;
+    };
+    // pair-relative slot of logical model j of the pair (or -1)
+    auto slot_of = [&](int pair, int j) -> int {
+        if (a.list) return j < a.list_cnt[pair] ? a.list[(size_t)pair * a.list_stride + j] : -1;
+        const int *segc = a.seg_count + (size_t)pair * a.nseg;
+        for (int seg = 0; seg < a.nseg; ++seg) {
+            const int c = segc[seg];
+            if (j < c) return seg * (4 * SEG) + j;
+            j -= c;
+        }
+        return -1;
+    };
+
     if (warp == 0) {
         // ===== TMA producer =====
         int st = 0;
         uint32_t ph = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const PairParams pp = a.pairs[pair_of(item)];
-            const int ntiles = (pp.n + NT - 1) / NT;
-            for (int t = 0; t < ntiles; ++t) {
+            int t0, t1, p1;
+            tile_range(pp, t0, t1, p1);
+            for (int t = t0; t < t1; ++t) {
                 mbar_wait(&b_empty[st], ph ^ 1);
                 if (elect_one()) {
                     mbar_expect_tx(&b_full[st], B_STAGE_BYTES);
@@ -359,11 +395,14 @@ __global__ void __launch_bounds__(THREADS, 1) tc_count_kernel(const __grid_const
         unsigned seq = 0;   // running (point tile, M-tile) index: slot = seq % SLOTS
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
             const PairParams pp = a.pairs[pair_of(item)];
-            const int ntiles = (pp.n + NT - 1) / NT;
+            int t0, t1, p1;
+            tile_range(pp, t0, t1, p1);
             const int ab = k & 1;
             mbar_wait(&a_full[ab], (k >> 1) & 1);
             tc_fence_after();
-            for (int t = 0; t < ntiles; ++t) {
+            if (t1 == t0 && elect_one()) umma_commit(&a_empty[ab]);   // nothing to do for this item: hand the A buffer back
+            __syncwarp();
+            for (int t = t0; t < t1; ++t) {
                 mbar_wait(&b_full[st], ph);
 #pragma unroll
                 for (int m = 0; m < MT; ++m) {
@@ -385,7 +424,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_count_kernel(const __grid_const
                         umma_commit(&slot_full[slot]);
                         if (m == MT - 1) {
                             umma_commit(&b_empty[st]);
-                            if (t == ntiles - 1) umma_commit(&a_empty[ab]);
+                            if (t == t1 - 1) umma_commit(&a_empty[ab]);
                         }
                     }
                     __syncwarp();
@@ -404,11 +443,11 @@ __global__ void __launch_bounds__(THREADS, 1) tc_count_kernel(const __grid_const
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int pair = pair_of(item);
             const PairParams pp = a.pairs[pair];
-            const int n = pp.n;
-            const int ntiles = (n + NT - 1) / NT;
+            int t0, t1, n;   // n = end of this pass's correspondence range
+            tile_range(pp, t0, t1, n);
             float acc0 = 0.f;
             unsigned long long accA = 0ull, accB = 0ull;   // packed FP32 pairs
-            for (int t = 0; t < ntiles; ++t, seq += MT) {
+            for (int t = t0; t < t1; ++t, seq += MT) {
                 const unsigned slot = seq % SLOTS;
                 mbar_wait(&slot_full[slot], (seq / SLOTS) & 1);
                 tc_fence_after();
@@ -455,20 +494,16 @@ __global__ void __launch_bounds__(THREADS, 1) tc_count_kernel(const __grid_const
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&slot_empty[slot]);
             }
-            int j = (item - a.item_prefix[pair]) * TILE_MODELS + row;
-            const int *segc = a.seg_count + (size_t)pair * a.nseg;
-            for (int seg = 0; seg < a.nseg; ++seg) {
-                const int c = segc[seg];
-                if (j < c) {
-                    float a0, a1, b0, b1;
-                    unpack2f(accA, a0, a1);
-                    unpack2f(accB, b0, b1);
-                    // every addend is exactly 0 or 1 (model_row's scaling), so the FP32 sums are exact counts
-                    a.out[((size_t)pair * a.nseg + seg) * (size_t)(4 * SEG) + j] = (int)(acc0 + a0 + a1 + b0 + b1);
-                    evaluated += (unsigned long long)n;
-                    break;
-                }
-                j -= c;
+            const int rel = slot_of(pair, (item - a.item_prefix[pair]) * TILE_MODELS + row);
+            if (rel >= 0) {
+                float a0, a1, b0, b1;
+                unpack2f(accA, a0, a1);
+                unpack2f(accB, b0, b1);
+                // every addend is exactly 0 or 1 (model_row's scaling), so the FP32 sums are exact counts
+                const int cnt = (int)(acc0 + a0 + a1 + b0 + b1);
+                int *o = a.out + ((size_t)pair * a.nseg) * (size_t)(4 * SEG) + rel;
+                *o = a.pass ? *o + cnt : cnt;
+                evaluated += (unsigned long long)(t1 > t0 ? n - t0 * NT : 0);
             }
         }
         if (a.evaluated) {
@@ -487,16 +522,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc_count_kernel(const __grid_const
             mbar_wait(&a_empty[ab], ((k >> 1) & 1) ^ 1);
             tc_fence_after();
             const int j0 = (item - a.item_prefix[pair]) * TILE_MODELS;
-            const int *segc = a.seg_count + (size_t)pair * a.nseg;
 #pragma unroll 1
             for (int m = 0; m < MT; ++m) {
-                int j = j0 + m * 128 + q * 32 + lane, seg = 0, slot = -1;
-                while (seg < a.nseg) {
-                    const int c = segc[seg];
-                    if (j < c) { slot = seg * (4 * SEG) + j; break; }
-                    j -= c;
-                    ++seg;
-                }
+                const int slot = slot_of(pair, j0 + m * 128 + q * 32 + lane);
                 float r0[32];
                 if (slot >= 0) {
                     const Model mdl = a.models[((size_t)pair * a.nseg) * (size_t)(4 * SEG) + slot];

@@ -313,6 +313,7 @@ def test_pruning_does_not_change_results(cfg, monkeypatch):
     monkeypatch.delenv("RP_NO_PRUNE", raising=False)
     monkeypatch.delenv("RP_NO_WAVES", raising=False)
     monkeypatch.delenv("RP_NO_TC", raising=False)
+    monkeypatch.delenv("RP_TC_ONE_PASS", raising=False)
     pruned_ctx = nv.Context(0)
     a = pruned_ctx.estimate_batch_host(variant, offs, x1, x2, d1, d2, cams, o)
     _, cnt = pruned_ctx.last_timing()
@@ -341,6 +342,15 @@ def test_pruning_does_not_change_results(cfg, monkeypatch):
         assert np.array_equal(a[1][f], t[1][f]), f
     assert np.allclose(a[1]["model_score"], t[1]["model_score"], rtol=1e-12, atol=0)
     notc_ctx.close()
+    # the tensor-core tier in ONE pass over the correspondences instead of two (no mid-way abandonment): same bytes
+    monkeypatch.setenv("RP_TC_ONE_PASS", "1")
+    one_ctx = nv.Context(0)
+    u = one_ctx.estimate_batch_host(variant, offs, x1, x2, d1, d2, cams, o)
+    _, cntu = one_ctx.last_timing()
+    monkeypatch.delenv("RP_TC_ONE_PASS")
+    assert cntu["tc_evaluated"] > cnt["tc_evaluated"] and cntu["tc_selected"] == cnt["tc_selected"]
+    assert a[0].tobytes() == u[0].tobytes() and a[2].tobytes() == u[2].tobytes() and a[1].tobytes() == u[1].tobytes()
+    one_ctx.close()
     monkeypatch.setenv("RP_NO_PRUNE", "1")
     full_ctx = nv.Context(0)
     b = full_ctx.estimate_batch_host(variant, offs, x1, x2, d1, d2, cams, o)
