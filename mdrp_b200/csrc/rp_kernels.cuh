@@ -420,7 +420,7 @@ RP_D Triplet load_triplet(const SolveArgs &a, const PairParams &pp, int pair, in
 }
 
 #ifndef RP_SOLVE2_MIN_BLOCKS
-#define RP_SOLVE2_MIN_BLOCKS 2   // 128 registers: measured 17.8 ms vs 23.1 ms per 10k pairs at 1 block/SM
+#define RP_SOLVE2_MIN_BLOCKS 3   // 85 registers: scale+shift per 10k pairs 23.1 / 17.8 / 16.8 / 17.4 ms at 1 / 2 / 3 / 4 blocks per SM
 #endif
 template <class CAND>
 __global__ void __launch_bounds__(SOLVE_THREADS, RP_SOLVE2_MIN_BLOCKS) solve2_kernel(SolveArgs a) {

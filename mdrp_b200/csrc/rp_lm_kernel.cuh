@@ -4,11 +4,16 @@
 #include "rp_types.cuh"
 #include "rp_lm.cuh"
 
+#ifndef RP_LM_UNROLL
+#define RP_LM_UNROLL 1      // correspondences per thread in flight in the evaluation loop (build knob; measured: 1 is best)
+#endif
 #ifndef RP_LM_MIN_BLOCKS
 #define RP_LM_MIN_BLOCKS 3   // blocks of 128 threads per SM, i.e. 12 warps: 168 registers per thread
 #endif
 
 namespace rp {
+
+constexpr int LM_UNROLL = RP_LM_UNROLL;
 
 // ---------------------------------------------------------------------------------------------
 // lm: lm_impl<> of PoseLib bundle.cc, one block per problem (persistent over the problem list).
@@ -177,6 +182,7 @@ __global__ void __launch_bounds__(THREADS, RP_LM_MIN_BLOCKS * 128 / THREADS) lm_
             const LMFrame F = make_frame(m);
             double c = 0.0;
             N.clear();
+#pragma unroll LM_UNROLL
             for (int i = tid; i < m_work; i += LM_THREADS) {
                 const int k = use_list ? (int)list_s[i] : i;
                 if (!use_list && mask && !mask[k]) continue;

@@ -12,8 +12,8 @@ v = sys.argv[1]
 try:
     d = json.load(open(f"gpurun_out/variant_{v}.json"))
     s = d["stage_ms_per_step"]
-    print(v, "value %.0f e2e %.0f | solve %.1f score %.1f (bound %.1f) lo %.1f final %.1f total %.1f" % (
-        d["value"], d["e2e"]["value"], s["solve"], s["score_minimal"], s["bound_kernel"], s["lo_refine"], s["final_refine"], s["device_total"]))
+    print(v, "value %.0f e2e %.0f | solve %.1f score %.1f (tc %.1f bound %.1f) lo %.1f final %.1f total %.1f" % (
+        d["value"], d["e2e"]["value"], s["solve"], s["score_minimal"], s["tc_kernel"], s["bound_kernel"], s["lo_refine"], s["final_refine"], s["device_total"]))
 except Exception as e:
     print(v, "failed", e)
 PY
