@@ -86,8 +86,8 @@ struct rp_ctx {
     int head = HB;      // models per pair scored exactly before the bound kernel (RP_HEAD=32|64|96|128; measured: 128 best on cfg2/cfg4, 64 marginally better on the 1000-iteration configs)
     bool waves = true;  // survivors of the prune scored in waves (RP_NO_WAVES=1: all at once)
     bool tc = true;     // tensor-core count tier in front of the FP32 bound kernel (RP_NO_TC=1: off)
-    int tc_two_pass = 8;       // that tier in two passes: the first over tc_two_pass/16 of the correspondences (RP_TC_SPLIT=1..15;
-                               // RP_TC_ONE_PASS=1: one pass over all of them)
+    int tc_two_pass = 8;         // that tier in two passes: the first over tc_two_pass/16 of the correspondences (measured best);
+                               // RP_TC_SPLIT=1..15: a fixed share in sixteenths; RP_TC_ONE_PASS=1: one pass over everything
     void *encode_tiled = nullptr;  // cuTensorMapEncodeTiled (driver entry point, resolved at rp_create)
     int ev_cap0 = EV;   // event-list capacity of the first pass (RP_EV_CAP: small values exercise the re-run path)
     std::vector<int32_t> pair_status;  // per pair of the last rp_estimate_batch_* call (rp_pair_status)
@@ -430,7 +430,7 @@ int run_chunk(rp_ctx *ctx, int variant, const rp_options &opt, const ChunkIO &io
             ta.n_pairs = P; ta.nseg = nseg; ta.pairs = pairs; ta.seg_count = seg_count; ta.item_prefix = B[B_TCPFX].as<int>();
             ta.n_items = &sc->n_tc_items; ta.models = models; ta.out = B[B_TCOUT].as<int>(); ta.pose = pose ? 1 : 0;
             ta.evaluated = &sc->tc_evaluated;
-            ta.two_pass = ctx->tc_two_pass; ta.pass = 0;
+            ta.two_pass = ctx->tc_two_pass; ta.pass = 0; ta.B0 = ba.B0; ta.S0 = ba.S0;
             rc = launch_tc(ctx, ta, B[B_FEAT].as<float4>(), N, st);
             if (rc) return rc;
             TcSelectArgs sel;
@@ -943,6 +943,7 @@ int rp_create(int device, rp_ctx **out) {
     if (const char *nw = getenv("RP_NO_WAVES")) ctx->waves = !(nw[0] == '1');
     if (const char *nt = getenv("RP_NO_TC")) ctx->tc = !(nt[0] == '1');
     if (const char *sp = getenv("RP_TC_SPLIT")) { const int v = atoi(sp); if (v >= 1 && v <= 15) ctx->tc_two_pass = v; }
+    if (const char *ap = getenv("RP_TC_ADAPT_PCT")) { const int v = atoi(ap); if (v >= 50 && v <= 200) ctx->tc_two_pass = -v; }
     if (const char *op = getenv("RP_TC_ONE_PASS")) { if (op[0] == '1') ctx->tc_two_pass = 0; }
     if (const char *ec = getenv("RP_EV_CAP")) { const int v = atoi(ec); if (v >= 1 && v <= EV) ctx->ev_cap0 = v; }
     {

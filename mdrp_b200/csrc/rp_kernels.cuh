@@ -1101,12 +1101,7 @@ __global__ void tc_select_kernel(TcSelectArgs a) {
     const size_t slots_pp = (size_t)a.nseg * (4 * SEG);
     const size_t pslot = (size_t)warp * slots_pp;
     const int n = pp.n;
-    // same abandonment threshold as bound_kernel
-    const float thr2_lo = __double2float_rd(pp.sq_thr);
-    const int B0 = a.B0[warp];
-    const double S0 = a.S0[warp];
-    const double need_d = fmax((double)(n - B0), S0 < 1e300 ? ceil(S0 / ((double)thr2_lo * (1.0 - 2e-4))) : 4.0e9);
-    const int need_out = need_d > 2.0e9 ? 0x7fffffff : max((int)need_d, 1);
+    const int need_out = tc::need_outliers(n, pp.sq_thr, a.B0[warp], a.S0[warp]);   // same threshold as bound_kernel
     int ns = 0;
     for (int seg = 0; seg < a.nseg; ++seg) {
         const int cnt = a.seg_count[warp * a.nseg + seg];
@@ -1139,11 +1134,7 @@ __global__ void tc_select_list_kernel(TcSelectArgs a) {
     const size_t slots_pp = (size_t)a.nseg * (4 * SEG);
     const size_t pslot = (size_t)warp * slots_pp;
     const int n = pp.n;
-    const float thr2_lo = __double2float_rd(pp.sq_thr);
-    const int B0 = a.B0[warp];
-    const double S0 = a.S0[warp];
-    const double need_d = fmax((double)(n - B0), S0 < 1e300 ? ceil(S0 / ((double)thr2_lo * (1.0 - 2e-4))) : 4.0e9);
-    const int need_out = need_d > 2.0e9 ? 0x7fffffff : max((int)need_d, 1);
+    const int need_out = tc::need_outliers(n, pp.sq_thr, a.B0[warp], a.S0[warp]);
     const int cnt = a.list_cnt[warp];
     int ns = 0;
     for (int base = 0; base < cnt; base += 32) {

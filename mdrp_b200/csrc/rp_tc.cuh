@@ -256,18 +256,40 @@ struct TcArgs {
     // Two passes over the correspondences (abandonment at the granularity of this tier): pass 0 counts over the first
     // tc_split(n) correspondences of every model, the caller drops what already has enough certain outliers, pass 1
     // counts the remaining correspondences for the survivors only (`list`) and adds to `out`.
-    int two_pass;                // 0: one pass over all correspondences; else the first pass covers two_pass/16 of them
+    int two_pass;                // 0: one pass over all correspondences; > 0: the first pass covers two_pass/16 of them;
+                                 // < 0: adaptive per pair from (B0, S0): -two_pass % of the abandonment threshold
+    const int *B0;               // per pair: best inlier count / score of the exactly scored head (adaptive split)
+    const double *S0;
     int pass;                    // 0 / 1
     const int *list;             // pass 1: pair-relative slots of the models to process, [n_pairs][list_stride]
     const int *list_cnt;         //         [n_pairs]
     int list_stride;
 };
 
-// first correspondence of pass 1 (a multiple of the point tile; n itself when the pair is too small to split)
-RP_HD int tc_split(int n, int sixteenths) {
+// Certain outliers after which a model can neither exceed the best inlier count B0 nor undercut the best score S0 of the
+// pair's exactly scored head (the abandonment threshold of the FP32 bound kernel, shared by every tier)
+RP_HD int need_outliers(int n, double sq_thr, int B0, double S0) {
+#if defined(__CUDA_ARCH__)
+    const float thr2_lo = __double2float_rd(sq_thr);
+#else
+    const float thr2_lo = (float)(sq_thr * (1.0 - 1e-7));
+#endif
+    const double need_d = fmax((double)(n - B0), S0 < 1e300 ? ceil(S0 / ((double)thr2_lo * (1.0 - 2e-4))) : 4.0e9);
+    return need_d > 2.0e9 ? 0x7fffffff : (need_d < 1.0 ? 1 : (int)need_d);
+}
+
+// First correspondence of pass 1 (a multiple of the point tile; n itself = no second pass).  `sixteenths` > 0: a fixed
+// share of the pair.  Otherwise adaptive: a hopeless model collects ~0.97 certain outliers per correspondence, so it can be
+// dropped after need / 0.95 of them; pairs whose threshold sits beyond 85 % of their correspondences (many outliers, a
+// weak head) are not worth a second pass.  Any choice gives the same results — only the amount of work changes.
+RP_HD int tc_split(int n, int sixteenths, int need, int pct = 105) {
     if (n < 4 * 64) return n;
-    const int s = (int)(((long long)n * sixteenths / 16 + 63) / 64) * 64;
-    return s < n ? s : n;
+    long long s;
+    if (sixteenths > 0) s = (long long)n * sixteenths / 16;
+    else if (need > n) return n;
+    else s = (long long)need * pct / 100 + 1;
+    s = (s + 63) / 64 * 64;
+    return s >= (long long)n * 85 / 100 ? n : (int)s;
 }
 
 // ---- the kernel -------------------------------------------------------------------------------------------------
@@ -351,8 +373,10 @@ __global__ void __launch_bounds__(THREADS, 1) tc_count_kernel(const __grid_const
     };
 
     // correspondences [p0, p1) of this pass, as point tiles [t0, t1)
-    auto tile_range = [&](const PairParams &pp, int &t0, int &t1, int &p1) {
-        const int sp = a.two_pass ? tc_split(pp.n, a.two_pass) : pp.n;
+    auto tile_range = [&](int pair, const PairParams &pp, int &t0, int &t1, int &p1) {
+        int sp = pp.n;
+        if (a.two_pass > 0) sp = tc_split(pp.n, a.two_pass, 0);
+        else if (a.two_pass < 0) sp = tc_split(pp.n, 0, need_outliers(pp.n, pp.sq_thr, a.B0[pair], a.S0[pair]), -a.two_pass);
         const int p0 = a.pass ? sp : 0;
         p1 = a.pass ? pp.n : sp;
         t0 = p0 / NT;
@@ -375,9 +399,10 @@ __global__ void __launch_bounds__(THREADS, 1) tc_count_kernel(const __grid_const
         int st = 0;
         uint32_t ph = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const PairParams pp = a.pairs[pair_of(item)];
+            const int pair = pair_of(item);
+            const PairParams pp = a.pairs[pair];
             int t0, t1, p1;
-            tile_range(pp, t0, t1, p1);
+            tile_range(pair, pp, t0, t1, p1);
             for (int t = t0; t < t1; ++t) {
                 mbar_wait(&b_empty[st], ph ^ 1);
                 if (elect_one()) {
@@ -394,9 +419,10 @@ __global__ void __launch_bounds__(THREADS, 1) tc_count_kernel(const __grid_const
         uint32_t ph = 0;
         unsigned seq = 0;   // running (point tile, M-tile) index: slot = seq % SLOTS
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
-            const PairParams pp = a.pairs[pair_of(item)];
+            const int pair = pair_of(item);
+            const PairParams pp = a.pairs[pair];
             int t0, t1, p1;
-            tile_range(pp, t0, t1, p1);
+            tile_range(pair, pp, t0, t1, p1);
             const int ab = k & 1;
             mbar_wait(&a_full[ab], (k >> 1) & 1);
             tc_fence_after();
@@ -444,7 +470,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_count_kernel(const __grid_const
             const int pair = pair_of(item);
             const PairParams pp = a.pairs[pair];
             int t0, t1, n;   // n = end of this pass's correspondence range
-            tile_range(pp, t0, t1, n);
+            tile_range(pair, pp, t0, t1, n);
             float acc0 = 0.f;
             unsigned long long accA = 0ull, accB = 0ull;   // packed FP32 pairs
             for (int t = t0; t < t1; ++t, seq += MT) {

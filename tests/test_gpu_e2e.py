@@ -348,7 +348,7 @@ def test_pruning_does_not_change_results(cfg, monkeypatch):
     u = one_ctx.estimate_batch_host(variant, offs, x1, x2, d1, d2, cams, o)
     _, cntu = one_ctx.last_timing()
     monkeypatch.delenv("RP_TC_ONE_PASS")
-    assert cntu["tc_evaluated"] > cnt["tc_evaluated"] and cntu["tc_selected"] == cnt["tc_selected"]
+    assert cntu["tc_evaluated"] >= cnt["tc_evaluated"] and cntu["tc_selected"] == cnt["tc_selected"]
     assert a[0].tobytes() == u[0].tobytes() and a[2].tobytes() == u[2].tobytes() and a[1].tobytes() == u[1].tobytes()
     one_ctx.close()
     monkeypatch.setenv("RP_NO_PRUNE", "1")
