@@ -85,6 +85,8 @@ struct rp_ctx {
     bool prune = true;  // hypothesis-level pruning (RP_NO_PRUNE=1 scores every minimal model exactly)
     int head = HB;      // models per pair scored exactly before the bound kernel (RP_HEAD=32|64|96|128; measured: 128 best on cfg2/cfg4, 64 marginally better on the 1000-iteration configs)
     bool waves = true;  // survivors of the prune scored in waves (RP_NO_WAVES=1: all at once)
+    int lm_warp = 0xf;  // bit v: the LO refinements of variant v run one warp per LM problem (lm_warp_kernel) instead of one block
+                        // (RP_LM_WARP=mask; 0 = the block-per-problem kernel everywhere)
     bool tc = true;     // tensor-core count tier in front of the FP32 bound kernel (RP_NO_TC=1: off)
     int tc_two_pass = 8;         // that tier in two passes: the first over tc_two_pass/16 of the correspondences (measured best);
                                // RP_TC_SPLIT=1..15: a fixed share in sixteenths; RP_TC_ONE_PASS=1: one pass over everything
@@ -182,6 +184,7 @@ int launch_lm(rp_ctx *ctx, int variant, const LMArgs &a, long long expected_prob
     // problems differ in cost (1..max_iterations LM iterations): blocks draw them from a counter
     LMArgs la = a;
     la.work_counter = &ctx->buf[B_SCALARS].as<Scalars>()->lm_work;
+    la.warp_kernel = (ctx->lm_warp >> variant) & 1;
     CK(cudaMemsetAsync(la.work_counter, 0, sizeof(int), st));
     CK((cudaError_t)launch_lm_kernel(ctx->sms, variant, la, st));
     return RP_OK;
@@ -941,6 +944,7 @@ int rp_create(int device, rp_ctx **out) {
     for (auto &ev : ctx->ev) cudaEventCreate(&ev);
     if (const char *np = getenv("RP_NO_PRUNE")) ctx->prune = !(np[0] == '1');
     if (const char *nw = getenv("RP_NO_WAVES")) ctx->waves = !(nw[0] == '1');
+    if (const char *lw = getenv("RP_LM_WARP")) ctx->lm_warp = atoi(lw) & 0xf;
     if (const char *nt = getenv("RP_NO_TC")) ctx->tc = !(nt[0] == '1');
     if (const char *sp = getenv("RP_TC_SPLIT")) { const int v = atoi(sp); if (v >= 1 && v <= 15) ctx->tc_two_pass = v; }
     if (const char *ap = getenv("RP_TC_ADAPT_PCT")) { const int v = atoi(ap); if (v >= 50 && v <= 200) ctx->tc_two_pass = -v; }

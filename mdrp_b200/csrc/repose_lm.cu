@@ -19,7 +19,11 @@ static int occupancy_grid(int sms, K kernel, int threads) {
 template <int VARIANT, int NP>
 static void launch_variant(int sms, const LMArgs &a, cudaStream_t st) {
     // the LO refinement (use_final = 0) always uses the TRUNCATED loss: compile-time specialisation
-    if (!a.use_final)
+    // (the one-problem-per-pair launches have too few problems for warp granularity: 2-3 per warp leave a long tail)
+    if (a.warp_kernel && a.prob_list && !a.mask && !a.use_final)
+        lm_warp_kernel<VARIANT, NP, RP_LOSS_TRUNCATED>
+            <<<occupancy_grid(sms, lm_warp_kernel<VARIANT, NP, RP_LOSS_TRUNCATED>, LMW_WPB[VARIANT] * 32), LMW_WPB[VARIANT] * 32, 0, st>>>(a);
+    else if (!a.use_final)
         lm_kernel<VARIANT, NP, RP_LM_THREADS, RP_LOSS_TRUNCATED>
             <<<occupancy_grid(sms, lm_kernel<VARIANT, NP, RP_LM_THREADS, RP_LOSS_TRUNCATED>, RP_LM_THREADS), RP_LM_THREADS, 0, st>>>(a);
     else

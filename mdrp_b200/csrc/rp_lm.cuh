@@ -180,7 +180,7 @@ RP_HD double point_cost(const LMFrame &F, const LMParams &P, double x1_0, double
 //   reprojection 2->1, both rows       : LM_FLOPS[v][3]   (7 | 8 | 8 | 9 columns)
 // (v = RP_CALIB, RP_CALIB_SHIFT, RP_SHARED, RP_VARYING; derivation in DESIGN.md §5).  `rows` counts the accumulated
 // rows of the three kinds in three 21-bit fields; the LM kernel turns the counts into the bench's lm_flops.
-constexpr int LM_FLOPS[4][4] = {{110, 167, 140, 207}, {110, 167, 188, 247}, {120, 224, 189, 268}, {120, 243, 223, 310}};
+constexpr int LM_FLOPS[4][4] = {{110, 161, 133, 197}, {110, 161, 179, 237}, {120, 216, 183, 259}, {120, 235, 217, 301}};
 
 template <int VARIANT, int NP, int LOSS = -1>
 RP_HD double point_eval(const LMFrame &F, const LMParams &P, double x1_0, double x1_1, double x2_0,
@@ -223,23 +223,26 @@ RP_HD double point_eval(const LMFrame &F, const LMParams &P, double x1_0, double
         if (w != 0.0) {
 #pragma unroll
             for (int i = 0; i < NP; ++i) J[i] = 0.0;
-            const double k = C * inv * inv * inv;  // = 2 * (0.5 C inv^3): the factor 2 of d(den) folded in
+            // The row is inv * J' with J'_i = dC_i - c2 * D_i (c2 = C inv^2, D_i = half the derivative of the
+            // denominator): J' is accumulated with the weight w inv^2 against the residual rs / inv = C, which is the same
+            // J^T J and J^T r with one multiplication less per column (the FP64 pipe is what bounds this kernel).
+            const double c2 = rs * inv;
             const double a2 = if2sq, a1 = if1sq;
             // rotation: dE = E [e_i]x ;  d(Ep1) = E (e_i x p1),  d(E^T p2) = -(e_i x E^T p2)
             {
                 const double dx = py * E.r0.z - E.r0.y, dy = py * E.r1.z - E.r1.y;
                 const double dC = py * Etp2.z - Etp2.y;
-                J[0] = dC * inv - k * ((Ep1.x * dx + Ep1.y * dy) * a2 + (Etp2.y * Etp2.z) * a1);
+                J[0] = dC - c2 * ((Ep1.x * dx + Ep1.y * dy) * a2 + (Etp2.y * Etp2.z) * a1);
             }
             {
                 const double dx = E.r0.x - px * E.r0.z, dy = E.r1.x - px * E.r1.z;
                 const double dC = Etp2.x - px * Etp2.z;
-                J[1] = dC * inv - k * ((Ep1.x * dx + Ep1.y * dy) * a2 - (Etp2.x * Etp2.z) * a1);
+                J[1] = dC - c2 * ((Ep1.x * dx + Ep1.y * dy) * a2 - (Etp2.x * Etp2.z) * a1);
             }
             {
                 const double dx = px * E.r0.y - py * E.r0.x, dy = px * E.r1.y - py * E.r1.x;
                 const double dC = px * Etp2.y - py * Etp2.x;
-                J[2] = dC * inv - k * ((Ep1.x * dx + Ep1.y * dy) * a2);
+                J[2] = dC - c2 * ((Ep1.x * dx + Ep1.y * dy) * a2);
             }
             // translation: dE = [e_i]x R ;  d(Ep1) = e_i x (R p1),  d(E^T p2) = -R^T (e_i x p2)
             const V3 s = v3(R.r0.x * px + R.r0.y * py + R.r0.z, R.r1.x * px + R.r1.y * py + R.r1.z,
@@ -248,38 +251,40 @@ RP_HD double point_eval(const LMFrame &F, const LMParams &P, double x1_0, double
                 // e_0 x s = (0, -s.z, s.y);  e_0 x p2 = (0, -1, qy) -> d(E^T p2) = row1(R) - qy row2(R)
                 const double tx = R.r1.x - qy * R.r2.x, ty = R.r1.y - qy * R.r2.y;
                 const double dC = s.y - qy * s.z;
-                J[3] = dC * inv - k * ((-Ep1.y * s.z) * a2 + (Etp2.x * tx + Etp2.y * ty) * a1);
+                J[3] = dC - c2 * ((-Ep1.y * s.z) * a2 + (Etp2.x * tx + Etp2.y * ty) * a1);
             }
             {
                 // e_1 x s = (s.z, 0, -s.x);  e_1 x p2 = (1, 0, -qx) -> d(E^T p2) = qx row2(R) - row0(R)
                 const double tx = qx * R.r2.x - R.r0.x, ty = qx * R.r2.y - R.r0.y;
                 const double dC = qx * s.z - s.x;
-                J[4] = dC * inv - k * ((Ep1.x * s.z) * a2 + (Etp2.x * tx + Etp2.y * ty) * a1);
+                J[4] = dC - c2 * ((Ep1.x * s.z) * a2 + (Etp2.x * tx + Etp2.y * ty) * a1);
             }
             {
                 // e_2 x s = (-s.y, s.x, 0);  e_2 x p2 = (-qy, qx, 0) -> d(E^T p2) = qy row0(R) - qx row1(R)
                 const double tx = qy * R.r0.x - qx * R.r1.x, ty = qy * R.r0.y - qx * R.r1.y;
                 const double dC = qy * s.x - qx * s.y;
-                J[5] = dC * inv - k * ((Ep1.y * s.x - Ep1.x * s.y) * a2 + (Etp2.x * tx + Etp2.y * ty) * a1);
+                J[5] = dC - c2 * ((Ep1.y * s.x - Ep1.x * s.y) * a2 + (Etp2.x * tx + Etp2.y * ty) * a1);
             }
             if (FOCAL) {
                 // p1 = (x1/f1, 1): dp1/df1 = -(px, py, 0)/f1 ; den = A/f2^2 + B/f1^2
                 const double dpx = -px * F.if1, dpy = -py * F.if1, dqx = -qx * F.if2, dqy = -qy * F.if2;
                 const double e1x = E.r0.x * dpx + E.r0.y * dpy, e1y = E.r1.x * dpx + E.r1.y * dpy;
                 const double e2x = E.r0.x * dqx + E.r1.x * dqy, e2y = E.r0.y * dqx + E.r1.y * dqy;
-                const double j1 = (Etp2.x * dpx + Etp2.y * dpy) * inv -
-                                  k * ((Ep1.x * e1x + Ep1.y * e1y) * a2 - B * a1 * F.if1);
-                const double j2 = (Ep1.x * dqx + Ep1.y * dqy) * inv -
-                                  k * ((Etp2.x * e2x + Etp2.y * e2y) * a1 - A * a2 * F.if2);
+                const double j1 = (Etp2.x * dpx + Etp2.y * dpy) -
+                                  c2 * ((Ep1.x * e1x + Ep1.y * e1y) * a2 - B * a1 * F.if1);
+                const double j2 = (Ep1.x * dqx + Ep1.y * dqy) -
+                                  c2 * ((Etp2.x * e2x + Etp2.y * e2y) * a1 - A * a2 * F.if2);
                 if (VARIANT == RP_SHARED) J[7] = j1 + j2;
                 else { J[7] = j1; J[CF2] = j2; }
             }
-            N.template add_row<M_S>(w, J, rs);
+            N.template add_row<M_S>(w * (inv * inv), J, C);
             rows += 1ull;
         }
     }
     if (!(P.scale_reproj > 0.0)) return cost;
 
+    // The reprojection rows are g * J' with g = f / z: J' is accumulated with the weight w g^2 against the residual
+    // r / g = r z / f (again one multiplication less per column than scaling every entry by g first).
     // ---- reprojection 1 -> 2 : Z = R (a p1) + t ----
     {
         const double a = d1 + F.shift1;
@@ -295,41 +300,43 @@ RP_HD double point_eval(const LMFrame &F, const LMParams &P, double x1_0, double
                              loss_weight(loss_type, P.loss_scale, P.scale_reproj * (r0 * r0 + r1 * r1));
             if (w != 0.0) {
                 const double g = f2 * iz;
+                const double zg = FOCAL ? Z.z * F.if2 : Z.z;   // 1 / g
                 double J0[NP], J1[NP];
 #pragma unroll
                 for (int i = 0; i < NP; ++i) { J0[i] = 0.0; J1[i] = 0.0; }
-                // dZ/dw_i = R (e_i x P):  Py c2 - Pz c1,  Pz c0 - Px c2,  Px c1 - Py c0  (c_j columns of R)
+                // dZ/dw_i = R (e_i x P) = a R (e_i x p1):  a (py c2 - c1),  a (c0 - px c2),  a (px c1 - py c0)  (c_j columns of R)
                 {
-                    const double dx = Py * R.r0.z - Pz * R.r0.y, dy = Py * R.r1.z - Pz * R.r1.y, dz = Py * R.r2.z - Pz * R.r2.y;
-                    J0[0] = g * (dx - u0 * dz); J1[0] = g * (dy - u1 * dz);
+                    const double dx = py * R.r0.z - R.r0.y, dy = py * R.r1.z - R.r1.y, dz = py * R.r2.z - R.r2.y;
+                    J0[0] = a * (dx - u0 * dz); J1[0] = a * (dy - u1 * dz);
                 }
                 {
-                    const double dx = Pz * R.r0.x - Px * R.r0.z, dy = Pz * R.r1.x - Px * R.r1.z, dz = Pz * R.r2.x - Px * R.r2.z;
-                    J0[1] = g * (dx - u0 * dz); J1[1] = g * (dy - u1 * dz);
+                    const double dx = R.r0.x - px * R.r0.z, dy = R.r1.x - px * R.r1.z, dz = R.r2.x - px * R.r2.z;
+                    J0[1] = a * (dx - u0 * dz); J1[1] = a * (dy - u1 * dz);
                 }
                 {
-                    const double dx = Px * R.r0.y - Py * R.r0.x, dy = Px * R.r1.y - Py * R.r1.x, dz = Px * R.r2.y - Py * R.r2.x;
-                    J0[2] = g * (dx - u0 * dz); J1[2] = g * (dy - u1 * dz);
+                    const double dx = px * R.r0.y - py * R.r0.x, dy = px * R.r1.y - py * R.r1.x, dz = px * R.r2.y - py * R.r2.x;
+                    J0[2] = a * (dx - u0 * dz); J1[2] = a * (dy - u1 * dz);
                 }
                 // dZ/dt = I
-                J0[3] = g; J0[5] = -g * u0;
-                J1[4] = g; J1[5] = -g * u1;
+                J0[3] = 1.0; J0[5] = -u0;
+                J1[4] = 1.0; J1[5] = -u1;
                 if (VARIANT == RP_CALIB_SHIFT) {
                     // dZ/dshift1 = R p1
                     const double dx = R.r0.x * px + R.r0.y * py + R.r0.z, dy = R.r1.x * px + R.r1.y * py + R.r1.z,
                                  dz = R.r2.x * px + R.r2.y * py + R.r2.z;
-                    J0[7] = g * (dx - u0 * dz); J1[7] = g * (dy - u1 * dz);
+                    J0[7] = dx - u0 * dz; J1[7] = dy - u1 * dz;
                 }
                 if (FOCAL) {
-                    // dZ/df1 = R (-a px/f1, -a py/f1, 0) ; d(pi)/df2 = (u0, u1)
+                    // dZ/df1 = R (-a px/f1, -a py/f1, 0) ; d(pi)/df2 = (u0, u1) = g (Z.x, Z.y) / f2^2... kept as (u0, u1) / g
                     const double ex = -Px * F.if1, ey = -Py * F.if1;
                     const double dx = R.r0.x * ex + R.r0.y * ey, dy = R.r1.x * ex + R.r1.y * ey, dz = R.r2.x * ex + R.r2.y * ey;
-                    J0[7] = g * (dx - u0 * dz); J1[7] = g * (dy - u1 * dz);
-                    J0[CF2] += u0; J1[CF2] += u1;
+                    J0[7] = dx - u0 * dz; J1[7] = dy - u1 * dz;
+                    J0[CF2] += Z.x * F.if2; J1[CF2] += Z.y * F.if2;
                 }
                 // dZ/dt = I: the x row has no t_y column, the y row no t_x column (structural zeros skipped)
-                N.template add_row<(M_12 & ~0x10u)>(w, J0, r0);
-                N.template add_row<(M_12 & ~0x08u)>(w, J1, r1);
+                const double sw = w * (g * g);
+                N.template add_row<(M_12 & ~0x10u)>(sw, J0, r0 * zg);
+                N.template add_row<(M_12 & ~0x08u)>(sw, J1, r1 * zg);
                 rows += 1ull << 21;
             }
         }
@@ -350,32 +357,34 @@ RP_HD double point_eval(const LMFrame &F, const LMParams &P, double x1_0, double
                              loss_weight(loss_type, P.loss_scale, P.scale_reproj * (r0 * r0 + r1 * r1));
             if (w != 0.0) {
                 const double g = f1 * iz;
+                const double zg = FOCAL ? Y.z * F.if1 : Y.z;   // 1 / g
                 double J0[NP], J1[NP];
 #pragma unroll
                 for (int i = 0; i < NP; ++i) { J0[i] = 0.0; J1[i] = 0.0; }
                 // dY/dw_i = Y x e_i:  (0, Yz, -Yy), (-Yz, 0, Yx), (Yy, -Yx, 0)
-                J0[0] = g * (u0 * Y.y);          J1[0] = g * (Y.z + u1 * Y.y);
-                J0[1] = g * (-Y.z - u0 * Y.x);   J1[1] = g * (-u1 * Y.x);
-                J0[2] = g * Y.y;                 J1[2] = -g * Y.x;
+                J0[0] = u0 * Y.y;            J1[0] = Y.z + u1 * Y.y;
+                J0[1] = -Y.z - u0 * Y.x;     J1[1] = -u1 * Y.x;
+                J0[2] = Y.y;                 J1[2] = -Y.x;
                 // dY/dt_i = -row_i(R)
-                J0[3] = g * (u0 * R.r0.z - R.r0.x); J1[3] = g * (u1 * R.r0.z - R.r0.y);
-                J0[4] = g * (u0 * R.r1.z - R.r1.x); J1[4] = g * (u1 * R.r1.z - R.r1.y);
-                J0[5] = g * (u0 * R.r2.z - R.r2.x); J1[5] = g * (u1 * R.r2.z - R.r2.y);
+                J0[3] = u0 * R.r0.z - R.r0.x; J1[3] = u1 * R.r0.z - R.r0.y;
+                J0[4] = u0 * R.r1.z - R.r1.x; J1[4] = u1 * R.r1.z - R.r1.y;
+                J0[5] = u0 * R.r2.z - R.r2.x; J1[5] = u1 * R.r2.z - R.r2.y;
                 // dY/dscale = R^T ((d2+v) p2),  dY/dshift2 = R^T (scale p2): both along m = R^T p2
                 const double mx = R.r0.x * qx + R.r1.x * qy + R.r2.x, my = R.r0.y * qx + R.r1.y * qy + R.r2.y,
                              mz = R.r0.z * qx + R.r1.z * qy + R.r2.z;
-                const double m0 = g * (mx - u0 * mz), m1 = g * (my - u1 * mz);
+                const double m0 = mx - u0 * mz, m1 = my - u1 * mz;
                 J0[6] = bb * m0; J1[6] = bb * m1;
                 if (VARIANT == RP_CALIB_SHIFT) { J0[8] = F.scale * m0; J1[8] = F.scale * m1; }
                 if (FOCAL) {
-                    // dY/df2 = R^T (-b qx/f2, -b qy/f2, 0) ; d(pi1)/df1 = (u0, u1)
+                    // dY/df2 = R^T (-b qx/f2, -b qy/f2, 0) ; d(pi1)/df1 = (u0, u1), i.e. (Y.x, Y.y) / f1 in units of g
                     const double ex = -b * qx * F.if2, ey = -b * qy * F.if2;
                     const double dx = R.r0.x * ex + R.r1.x * ey, dy = R.r0.y * ex + R.r1.y * ey, dz = R.r0.z * ex + R.r1.z * ey;
-                    J0[CF2] += g * (dx - u0 * dz); J1[CF2] += g * (dy - u1 * dz);
-                    J0[7] += u0; J1[7] += u1;
+                    J0[CF2] += dx - u0 * dz; J1[CF2] += dy - u1 * dz;
+                    J0[7] += Y.x * F.if1; J1[7] += Y.y * F.if1;
                 }
-                N.template add_row<M_21>(w, J0, r0);
-                N.template add_row<M_21>(w, J1, r1);
+                const double sw = w * (g * g);
+                N.template add_row<M_21>(sw, J0, r0 * zg);
+                N.template add_row<M_21>(sw, J1, r1 * zg);
                 rows += 1ull << 42;
             }
         }
