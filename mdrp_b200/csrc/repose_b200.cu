@@ -50,7 +50,7 @@ enum { B_OFFS, B_PAIRS, B_PTS64, B_PTS32, B_BEAR, B_SAMPLES, B_MODELS, B_HYPITER
        // second staging set (double buffering of the host path)
        B_MASK_B, B_IN_X1_B, B_IN_X2_B, B_IN_D1_B, B_IN_D2_B, B_IN_CAMS_B, B_TMP0_B, B_TMP1_B,
        // tensor-core tier: per-point feature rows, per-model outlier counts, survivor lists
-       B_FEAT, B_TCOUT, B_TCLIST, B_TCLISTCNT, B_TCLISTPFX, B_PAIRCNT, B_TCPFX,
+       B_FEAT, B_TCOUT, B_TCLIST, B_TCLISTCNT, B_TCLISTPFX, B_PAIRCNT, B_TCPFX, B_TCSPLIT,
        // per-pair flags; re-run sub-batches (event-list overflow, early termination that needs more iterations)
        B_PAIRFLAGS, B_SUB_IDX, B_SUB_SRC, B_SUB_DST, B_SUB_X1, B_SUB_X2, B_SUB_D1, B_SUB_D2, B_SUB_CAMS, B_SUB_MODELS,
        B_SUB_STATS, B_SUB_MASK, B_NBUF };
@@ -88,8 +88,8 @@ struct rp_ctx {
     int lm_warp = 0xf;  // bit v: the LO refinements of variant v run one warp per LM problem (lm_warp_kernel) instead of one block
                         // (RP_LM_WARP=mask; 0 = the block-per-problem kernel everywhere)
     bool tc = true;     // tensor-core count tier in front of the FP32 bound kernel (RP_NO_TC=1: off)
-    int tc_two_pass = 8;         // that tier in two passes: the first over tc_two_pass/16 of the correspondences (measured best);
-                               // RP_TC_SPLIT=1..15: a fixed share in sixteenths; RP_TC_ONE_PASS=1: one pass over everything
+    int tc_two_pass = -115;    // that tier in two passes: < 0: the first pass covers -tc_two_pass % of the pair's abandonment threshold
+                               // (RP_TC_ADAPT_PCT); RP_TC_SPLIT=1..15: a fixed share in sixteenths; RP_TC_ONE_PASS=1: one pass over everything
     void *encode_tiled = nullptr;  // cuTensorMapEncodeTiled (driver entry point, resolved at rp_create)
     int ev_cap0 = EV;   // event-list capacity of the first pass (RP_EV_CAP: small values exercise the re-run path)
     std::vector<int32_t> pair_status;  // per pair of the last rp_estimate_batch_* call (rp_pair_status)
@@ -325,6 +325,7 @@ int run_chunk(rp_ctx *ctx, int variant, const rp_options &opt, const ChunkIO &io
         CK(B[B_TCLISTCNT].reserve(sizeof(int) * P));
         CK(B[B_TCLISTPFX].reserve(sizeof(int) * (P + 1)));
         CK(B[B_PAIRCNT].reserve(sizeof(int) * P));
+        CK(B[B_TCSPLIT].reserve(sizeof(int) * P));
         CK(B[B_TCPFX].reserve(sizeof(int) * (P + 1)));
     }
 
@@ -433,7 +434,11 @@ int run_chunk(rp_ctx *ctx, int variant, const rp_options &opt, const ChunkIO &io
             ta.n_pairs = P; ta.nseg = nseg; ta.pairs = pairs; ta.seg_count = seg_count; ta.item_prefix = B[B_TCPFX].as<int>();
             ta.n_items = &sc->n_tc_items; ta.models = models; ta.out = B[B_TCOUT].as<int>(); ta.pose = pose ? 1 : 0;
             ta.evaluated = &sc->tc_evaluated;
-            ta.two_pass = ctx->tc_two_pass; ta.pass = 0; ta.B0 = ba.B0; ta.S0 = ba.S0;
+            ta.two_pass = ctx->tc_two_pass; ta.pass = 0; ta.split = B[B_TCSPLIT].as<int>();
+            if (ctx->tc_two_pass) {
+                tc::tc_split_kernel<<<cdiv(P, 256), 256, 0, st>>>(P, pairs, ba.B0, ba.S0, ctx->tc_two_pass, B[B_TCSPLIT].as<int>());
+                LAUNCHED();
+            }
             rc = launch_tc(ctx, ta, B[B_FEAT].as<float4>(), N, st);
             if (rc) return rc;
             TcSelectArgs sel;

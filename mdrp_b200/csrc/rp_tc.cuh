@@ -256,10 +256,8 @@ struct TcArgs {
     // Two passes over the correspondences (abandonment at the granularity of this tier): pass 0 counts over the first
     // tc_split(n) correspondences of every model, the caller drops what already has enough certain outliers, pass 1
     // counts the remaining correspondences for the survivors only (`list`) and adds to `out`.
-    int two_pass;                // 0: one pass over all correspondences; > 0: the first pass covers two_pass/16 of them;
-                                 // < 0: adaptive per pair from (B0, S0): -two_pass % of the abandonment threshold
-    const int *B0;               // per pair: best inlier count / score of the exactly scored head (adaptive split)
-    const double *S0;
+    int two_pass;                // 0: one pass over all correspondences; else two passes split at split[pair]
+    const int *split;            // per pair: first correspondence of pass 1 (tc_split_kernel), a multiple of the point tile or n
     int pass;                    // 0 / 1
     const int *list;             // pass 1: pair-relative slots of the models to process, [n_pairs][list_stride]
     const int *list_cnt;         //         [n_pairs]
@@ -290,6 +288,15 @@ RP_HD int tc_split(int n, int sixteenths, int need, int pct = 105) {
     else s = (long long)need * pct / 100 + 1;
     s = (s + 63) / 64 * 64;
     return s >= (long long)n * 85 / 100 ? n : (int)s;
+}
+
+// Per pair, once per chunk: the split of the two passes (the kernel's three warp roles only read it; evaluating
+// need_outliers' FP64 division per work item inside them cost 2-4 ms per 10 000 pairs).
+__global__ void tc_split_kernel(int n_pairs, const PairParams *pairs, const int *B0, const double *S0, int two_pass, int *split) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pairs) return;
+    const PairParams pp = pairs[p];
+    split[p] = two_pass > 0 ? tc_split(pp.n, two_pass, 0) : tc_split(pp.n, 0, need_outliers(pp.n, pp.sq_thr, B0[p], S0[p]), -two_pass);
 }
 
 // ---- the kernel -------------------------------------------------------------------------------------------------
@@ -374,9 +381,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_count_kernel(const __grid_const
 
     // correspondences [p0, p1) of this pass, as point tiles [t0, t1)
     auto tile_range = [&](int pair, const PairParams &pp, int &t0, int &t1, int &p1) {
-        int sp = pp.n;
-        if (a.two_pass > 0) sp = tc_split(pp.n, a.two_pass, 0);
-        else if (a.two_pass < 0) sp = tc_split(pp.n, 0, need_outliers(pp.n, pp.sq_thr, a.B0[pair], a.S0[pair]), -a.two_pass);
+        const int sp = a.two_pass ? a.split[pair] : pp.n;
         const int p0 = a.pass ? sp : 0;
         p1 = a.pass ? pp.n : sp;
         t0 = p0 / NT;
