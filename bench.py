@@ -383,7 +383,7 @@ def main():
     # per-row counts of rp_lm.cuh (LM_FLOPS)
     lm_s = (stage_ms["lo_refine"] + stage_ms["final_refine"]) / 1000.0
     if lm_s > 0 and counters.get("lm_flops", 0):
-        entries.append({"kernel": "lm_kernel (Levenberg-Marquardt: LO of every trigger + final refinement)", "bound": "fp64_pipe",
+        entries.append({"kernel": "lm_warp_kernel + lm_kernel (Levenberg-Marquardt: LO of every trigger, one warp per problem; final LO and final refinement, one block per problem)", "bound": "fp64_pipe",
                         "achieved": counters["lm_flops"] / lm_s / 1e12, "peak": fp64_tf, "unit": "TFLOP/s",
                         "frac": counters["lm_flops"] / lm_s / 1e12 / fp64_tf if fp64_tf else None, "peak_source": pipes_src,
                         "work": "device counters: correspondences evaluated, rows accumulated x the FP64 flop table LM_FLOPS (DESIGN.md §5)",

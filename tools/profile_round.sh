@@ -19,7 +19,7 @@ cap() {  # name kernel-regex skip
 }
 cap tc tc_count_kernel 0
 cap bound bound_kernel 0
-cap lm lm_kernel 0
+cap lm lm_warp_kernel 0
 cap score_survivors score_kernel 1
 cap solve solve2_kernel 0
 bash tools/all_configs_bench.sh > gpurun_out/${TAG}_all_configs.txt 2>&1

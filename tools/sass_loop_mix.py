@@ -18,4 +18,4 @@ for r in regions:
         c[t.split()[0].split(".")[0]] += 1
     n = len(r)
     fp64 = sum(c[k] for k in ("DFMA", "DMUL", "DADD", "DSETP", "MUFU"))
-    print(f"loop body: {n} instr, FP64-pipe {fp64} | " + ", ".join(f"{k} {v}" for k, v in c.most_common(14)))
+    print(f"loop body: {n} instr, FP64-pipe {fp64}, LDL {c['LDL']} STL {c['STL']} LDS {c['LDS']} | " + ", ".join(f"{k} {v}" for k, v in c.most_common(10)), flush=True)
