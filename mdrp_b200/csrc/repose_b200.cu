@@ -87,6 +87,9 @@ struct rp_ctx {
     bool waves = true;  // survivors of the prune scored in waves (RP_NO_WAVES=1: all at once)
     int lm_warp = 0xf;  // bit v: the LO refinements of variant v run one warp per LM problem (lm_warp_kernel) instead of one block
                         // (RP_LM_WARP=mask; 0 = the block-per-problem kernel everywhere)
+    int head_small = 32;  // with the tensor-core tier: models per pair scored exactly up front (RP_HEAD_SMALL) ...
+    int mid_end = 256;    // ... and end of the mid stage that replaces the rest of the head (RP_MID_END; 0: no mid stage, head = RP_HEAD)
+    int mid_ends[4] = {256, 0, 0, 0}, n_mid = 1;   // RP_MID_END=a,b,..: several mid stages
     bool tc = true;     // tensor-core count tier in front of the FP32 bound kernel (RP_NO_TC=1: off)
     int tc_two_pass = -115;    // that tier in two passes: < 0: the first pass covers -tc_two_pass % of the pair's abandonment threshold
                                // (RP_TC_ADAPT_PCT); RP_TC_SPLIT=1..15: a fixed share in sixteenths; RP_TC_ONE_PASS=1: one pass over everything
@@ -172,6 +175,7 @@ int launch_score(rp_ctx *ctx, bool pose, bool mask, const ScoreArgs &args, cudaS
 }
 
 int launch_bound(rp_ctx *ctx, bool pose, const BoundArgs &a, cudaStream_t st) {
+    CK(cudaMemsetAsync(a.work_counter, 0, sizeof(int), st));   // (launched twice per chunk: mid stage and bulk)
     if (pose) bound_kernel<true><<<occupancy_grid(ctx, bound_kernel<true>, SCORE_THREADS), SCORE_THREADS, 0, st>>>(a);
     else bound_kernel<false><<<occupancy_grid(ctx, bound_kernel<false>, SCORE_THREADS), SCORE_THREADS, 0, st>>>(a);
     LAUNCHED();
@@ -398,9 +402,15 @@ int run_chunk(rp_ctx *ctx, int variant, const rp_options &opt, const ChunkIO &io
         int rc = launch_score(ctx, pose, false, sa, st);
         if (rc) return rc;
     } else {
-        // 4a. the first ctx->head models of every pair, exactly -> (B0, S0)
+        // 4a. the first `head` models of every pair, exactly -> (B0, S0)
+        // With the tensor-core tier a short head (ctx->head_small) is followed by a MID stage: the models at positions
+        // [head_small, mid_end) of the pair's first segment go through the same cascade as the bulk (one tensor-core
+        // pass, FP32 bound, prune, exact waves) against the short head's bar, which leaves (B0, S0) = the exact best of
+        // everything before mid_end for the bulk at a fraction of the cost of scoring a long head exactly.
+        const bool mid = use_tc && ctx->mid_end > ctx->head_small && ctx->mid_end > 0;
+        const int head = mid ? ctx->head_small : ctx->head;
         int *first_cnt = B[B_FIRSTCNT].as<int>();
-        first_count_kernel<<<cdiv(P, 256), 256, 0, st>>>(P, nseg, seg_count, first_cnt, ctx->head);
+        first_count_kernel<<<cdiv(P, 256), 256, 0, st>>>(P, nseg, seg_count, first_cnt, head);
         LAUNCHED();
         build_items_kernel<<<1, 1024, 0, st>>>(P, first_cnt, B[B_FIRSTPFX].as<int>(), &sc->n_first_items, nullptr);
         LAUNCHED();
@@ -412,101 +422,131 @@ int run_chunk(rp_ctx *ctx, int variant, const rp_options &opt, const ChunkIO &io
         pair_bounds_kernel<<<cdiv((long long)P * 32, 256), 256, 0, st>>>(P, nseg, first_cnt, score, count,
                                                                        B[B_B0].as<int>(), B[B_S0].as<double>());
         LAUNCHED();
-        // 4b. bounds for all later models.  Tensor-core tier first (certain-outlier counts of EVERY model, rp_tc.cuh),
-        // then the FP32 bound kernel only over the models that tier could not drop.
-        BoundArgs ba;
-        ba.n_groups = P * nseg; ba.grp_stride = 4 * SEG; ba.grp_per_pair = nseg; ba.grp_cnt = seg_count;
-        ba.item_prefix = item_prefix; ba.n_items = &sc->n_items; ba.pairs = pairs; ba.models = models; ba.pts32p = B[B_PTS32P].as<ulonglong2>();
-        ba.ub = B[B_UB].as<int>(); ba.lb = B[B_LB].as<float>(); ba.point_scores = &sc->point_scores;
-        ba.B0 = B[B_B0].as<int>(); ba.S0 = B[B_S0].as<double>();
-        ba.evaluated = &sc->evaluated_ps;
-        ba.work_counter = &sc->bound_work; ba.head = ctx->head;
-        ba.slot_list = nullptr; ba.list_stride = 0;
-        CK(cudaEventRecord(ev[20], st));
-        if (use_tc) {
-            pair_total_kernel<<<cdiv(P, 256), 256, 0, st>>>(P, nseg, seg_count, B[B_PAIRCNT].as<int>());
-            LAUNCHED();
-            build_items_kernel<<<1, 1024, 0, st>>>(P, B[B_PAIRCNT].as<int>(), B[B_TCPFX].as<int>(), &sc->n_tc_items, nullptr, tc::TILE_MODELS);
-            LAUNCHED();
-            // pass 0: every model against the first half of its pair's correspondences
-            tc::TcArgs ta;
-            memset(&ta, 0, sizeof ta);
-            ta.n_pairs = P; ta.nseg = nseg; ta.pairs = pairs; ta.seg_count = seg_count; ta.item_prefix = B[B_TCPFX].as<int>();
-            ta.n_items = &sc->n_tc_items; ta.models = models; ta.out = B[B_TCOUT].as<int>(); ta.pose = pose ? 1 : 0;
-            ta.evaluated = &sc->tc_evaluated;
-            ta.two_pass = ctx->tc_two_pass; ta.pass = 0; ta.split = B[B_TCSPLIT].as<int>();
-            if (ctx->tc_two_pass) {
-                tc::tc_split_kernel<<<cdiv(P, 256), 256, 0, st>>>(P, pairs, ba.B0, ba.S0, ctx->tc_two_pass, B[B_TCSPLIT].as<int>());
+        // 4b/4c for the models at positions [start, limit) of the first segment (limit > 0) or [start, end) of the pair
+        // (limit = 0): tensor-core tier (certain-outlier counts, rp_tc.cuh), FP32 bound kernel over what that tier could
+        // not drop, prune, exact scoring of the survivors in bar-raising waves.  (B0, S0) are raised in place.
+        auto cascade = [&](int start, int limit, int two_pass, cudaEvent_t ev_tc, cudaEvent_t ev_bound) -> int {
+            BoundArgs ba;
+            ba.n_groups = P * nseg; ba.grp_stride = 4 * SEG; ba.grp_per_pair = nseg; ba.grp_cnt = seg_count;
+            ba.item_prefix = item_prefix; ba.n_items = &sc->n_items; ba.pairs = pairs; ba.models = models; ba.pts32p = B[B_PTS32P].as<ulonglong2>();
+            ba.ub = B[B_UB].as<int>(); ba.lb = B[B_LB].as<float>(); ba.point_scores = &sc->point_scores;
+            ba.B0 = B[B_B0].as<int>(); ba.S0 = B[B_S0].as<double>();
+            ba.evaluated = &sc->evaluated_ps;
+            ba.work_counter = &sc->bound_work; ba.head = start;
+            ba.slot_list = nullptr; ba.list_stride = 0;
+            if (use_tc) {
+                range_count_kernel<<<cdiv(P, 256), 256, 0, st>>>(P, nseg, seg_count, start, limit, B[B_PAIRCNT].as<int>());
                 LAUNCHED();
-            }
-            rc = launch_tc(ctx, ta, B[B_FEAT].as<float4>(), N, st);
-            if (rc) return rc;
-            TcSelectArgs sel;
-            sel.n_pairs = P; sel.nseg = nseg; sel.head = ctx->head; sel.pairs = pairs; sel.seg_count = seg_count;
-            sel.out = B[B_TCOUT].as<int>(); sel.B0 = ba.B0; sel.S0 = ba.S0; sel.ub = ba.ub; sel.lb = ba.lb;
-            sel.list = B[B_TCLIST].as<int>(); sel.list_cnt = B[B_TCLISTCNT].as<int>();
-            sel.n_selected = ctx->tc_two_pass ? nullptr : &sc->tc_selected;
-            tc_select_kernel<<<cdiv((long long)P * 32, 256), 256, 0, st>>>(sel);
-            LAUNCHED();
-            if (ctx->tc_two_pass) {
-                // pass 1: the second half, only for the models that are not yet certain to be pruned
-                build_items_kernel<<<1, 1024, 0, st>>>(P, B[B_TCLISTCNT].as<int>(), B[B_TCPFX].as<int>(), &sc->n_tc_items, nullptr, tc::TILE_MODELS);
+                build_items_kernel<<<1, 1024, 0, st>>>(P, B[B_PAIRCNT].as<int>(), B[B_TCPFX].as<int>(), &sc->n_tc_items, nullptr, tc::TILE_MODELS);
                 LAUNCHED();
-                ta.pass = 1; ta.list = B[B_TCLIST].as<int>(); ta.list_cnt = B[B_TCLISTCNT].as<int>(); ta.list_stride = (int)slots_pp;
-                rc = launch_tc(ctx, ta, B[B_FEAT].as<float4>(), N, st);
+                // pass 0: every model of the range against the first part of its pair's correspondences (or all of them)
+                tc::TcArgs ta;
+                memset(&ta, 0, sizeof ta);
+                ta.n_pairs = P; ta.nseg = nseg; ta.pairs = pairs; ta.seg_count = seg_count; ta.item_prefix = B[B_TCPFX].as<int>();
+                ta.n_items = &sc->n_tc_items; ta.models = models; ta.out = B[B_TCOUT].as<int>(); ta.pose = pose ? 1 : 0;
+                ta.evaluated = &sc->tc_evaluated; ta.first = start;
+                ta.two_pass = two_pass; ta.pass = 0; ta.split = B[B_TCSPLIT].as<int>();
+                if (two_pass) {
+                    tc::tc_split_kernel<<<cdiv(P, 256), 256, 0, st>>>(P, pairs, ba.B0, ba.S0, two_pass, B[B_TCSPLIT].as<int>());
+                    LAUNCHED();
+                }
+                int rc = launch_tc(ctx, ta, B[B_FEAT].as<float4>(), N, st);
                 if (rc) return rc;
-                sel.n_selected = &sc->tc_selected;
-                tc_select_list_kernel<<<cdiv((long long)P * 32, 256), 256, 0, st>>>(sel);
+                TcSelectArgs sel;
+                sel.n_pairs = P; sel.nseg = nseg; sel.head = start; sel.limit = limit; sel.pairs = pairs; sel.seg_count = seg_count;
+                sel.out = B[B_TCOUT].as<int>(); sel.B0 = ba.B0; sel.S0 = ba.S0; sel.ub = ba.ub; sel.lb = ba.lb;
+                sel.list = B[B_TCLIST].as<int>(); sel.list_cnt = B[B_TCLISTCNT].as<int>();
+                sel.n_selected = two_pass ? nullptr : &sc->tc_selected;
+                tc_select_kernel<<<cdiv((long long)P * 32, 256), 256, 0, st>>>(sel);
                 LAUNCHED();
+                if (two_pass) {
+                    // pass 1: the remaining correspondences, only for the models that are not yet certain to be pruned
+                    build_items_kernel<<<1, 1024, 0, st>>>(P, B[B_TCLISTCNT].as<int>(), B[B_TCPFX].as<int>(), &sc->n_tc_items, nullptr, tc::TILE_MODELS);
+                    LAUNCHED();
+                    ta.pass = 1; ta.first = 0; ta.list = B[B_TCLIST].as<int>(); ta.list_cnt = B[B_TCLISTCNT].as<int>(); ta.list_stride = (int)slots_pp;
+                    rc = launch_tc(ctx, ta, B[B_FEAT].as<float4>(), N, st);
+                    if (rc) return rc;
+                    sel.n_selected = &sc->tc_selected;
+                    tc_select_list_kernel<<<cdiv((long long)P * 32, 256), 256, 0, st>>>(sel);
+                    LAUNCHED();
+                }
+                if (ev_tc) CK(cudaEventRecord(ev_tc, st));
+                build_items_kernel<<<1, 1024, 0, st>>>(P, B[B_TCLISTCNT].as<int>(), B[B_TCLISTPFX].as<int>(), &sc->n_tcsel_items, nullptr);
+                LAUNCHED();
+                ba.n_groups = P; ba.grp_stride = (int)slots_pp; ba.grp_per_pair = 1; ba.grp_cnt = B[B_TCLISTCNT].as<int>();
+                ba.item_prefix = B[B_TCLISTPFX].as<int>(); ba.n_items = &sc->n_tcsel_items;
+                ba.slot_list = B[B_TCLIST].as<int>(); ba.list_stride = (int)slots_pp;
             }
-            CK(cudaEventRecord(ev[22], st));
-            build_items_kernel<<<1, 1024, 0, st>>>(P, B[B_TCLISTCNT].as<int>(), B[B_TCLISTPFX].as<int>(), &sc->n_tcsel_items, nullptr);
-            LAUNCHED();
-            ba.n_groups = P; ba.grp_stride = (int)slots_pp; ba.grp_per_pair = 1; ba.grp_cnt = B[B_TCLISTCNT].as<int>();
-            ba.item_prefix = B[B_TCLISTPFX].as<int>(); ba.n_items = &sc->n_tcsel_items;
-            ba.slot_list = B[B_TCLIST].as<int>(); ba.list_stride = (int)slots_pp;
-        }
-        rc = launch_bound(ctx, pose, ba, st);
-        if (rc) return rc;
-        CK(cudaEventRecord(ev[21], st));
-        // 4c. prune, then score the survivors exactly
-        PruneArgs pa;
-        pa.n_pairs = P; pa.nseg = nseg; pa.seg_count = seg_count; pa.ub = ba.ub; pa.lb = ba.lb;
-        pa.B0 = B[B_B0].as<int>(); pa.S0 = B[B_S0].as<double>(); pa.score = score; pa.count = count; pa.head = ctx->head;
-        pa.surv_list = B[B_SURVLIST].as<int>(); pa.surv_cnt = B[B_SURVCNT].as<int>();
-        pa.n_survivors = ctx->waves ? nullptr : &sc->n_survivors;
-        prune_kernel<<<cdiv((long long)P * 32, 256), 256, 0, st>>>(pa);
-        LAUNCHED();
-        ScoreArgs sv = sa;
-        sv.item_prefix = B[B_SURVPFX].as<int>(); sv.n_items = &sc->n_surv_items;
-        sv.slot_list = pa.surv_list; sv.list_stride = (int)slots_pp; sv.point_scores = nullptr;
-        if (!ctx->waves) {
-            // all survivors at once (RP_NO_WAVES=1: the check that the waves below change nothing)
-            build_items_kernel<<<1, 1024, 0, st>>>(P, pa.surv_cnt, B[B_SURVPFX].as<int>(), &sc->n_surv_items, nullptr);
-            LAUNCHED();
-            sv.grp_cnt = pa.surv_cnt;
-            rc = launch_score(ctx, pose, false, sv, st);
+            int rc = launch_bound(ctx, pose, ba, st);
             if (rc) return rc;
-        } else {
-            // survivors in waves of growing size, each raising the bar for the next (wave_select_kernel)
+            if (ev_bound) CK(cudaEventRecord(ev_bound, st));
+            // prune, then score the survivors exactly
+            PruneArgs pa;
+            pa.n_pairs = P; pa.nseg = nseg; pa.seg_count = seg_count; pa.ub = ba.ub; pa.lb = ba.lb;
+            pa.B0 = B[B_B0].as<int>(); pa.S0 = B[B_S0].as<double>(); pa.score = score; pa.count = count; pa.head = start; pa.limit = limit;
+            pa.surv_list = B[B_SURVLIST].as<int>(); pa.surv_cnt = B[B_SURVCNT].as<int>();
+            pa.n_survivors = ctx->waves ? nullptr : &sc->n_survivors;
+            prune_kernel<<<cdiv((long long)P * 32, 256), 256, 0, st>>>(pa);
+            LAUNCHED();
+            ScoreArgs sv = sa;
+            sv.item_prefix = B[B_SURVPFX].as<int>(); sv.n_items = &sc->n_surv_items;
+            sv.slot_list = pa.surv_list; sv.list_stride = (int)slots_pp; sv.point_scores = nullptr;
             WaveArgs wa;
             wa.n_pairs = P; wa.slots_pp = slots_pp; wa.surv_list = pa.surv_list; wa.surv_cnt = pa.surv_cnt;
             wa.cursor = B[B_WAVECUR].as<int>(); wa.wave_cnt = B[B_WAVECNT].as<int>(); wa.ub = ba.ub; wa.lb = ba.lb;
             wa.B = B[B_B0].as<int>(); wa.S = B[B_S0].as<double>(); wa.score = score; wa.count = count;
             wa.n_exact = &sc->n_survivors;
-            CK(cudaMemsetAsync(wa.cursor, 0, sizeof(int) * P, st));
-            static const int WAVES[] = {8, 16, 32, 64, 0x7fffffff};
-            for (int k = 0; k < 5; ++k) {
-                wa.wave_size = WAVES[k]; wa.first = k == 0;
-                wave_select_kernel<<<cdiv((long long)P * 32, 256), 256, 0, st>>>(wa);
+            if (!ctx->waves) {
+                // all survivors at once (RP_NO_WAVES=1: the check that the waves below change nothing)
+                build_items_kernel<<<1, 1024, 0, st>>>(P, pa.surv_cnt, B[B_SURVPFX].as<int>(), &sc->n_surv_items, nullptr);
                 LAUNCHED();
-                build_items_kernel<<<1, 1024, 0, st>>>(P, wa.wave_cnt, B[B_SURVPFX].as<int>(), &sc->n_surv_items, nullptr);
-                LAUNCHED();
-                sv.grp_cnt = wa.wave_cnt;
+                sv.grp_cnt = pa.surv_cnt;
                 rc = launch_score(ctx, pose, false, sv, st);
                 if (rc) return rc;
+                if (limit) {
+                    // a later stage follows: fold these exact results into (B0, S0)
+                    CK(cudaMemsetAsync(wa.cursor, 0, sizeof(int) * P, st));
+                    CK(cudaMemcpyAsync(wa.wave_cnt, pa.surv_cnt, sizeof(int) * P, cudaMemcpyDeviceToDevice, st));
+                    wa.wave_size = 0; wa.first = 0; wa.n_exact = nullptr;
+                    wave_select_kernel<<<cdiv((long long)P * 32, 256), 256, 0, st>>>(wa);
+                    LAUNCHED();
+                }
+            } else {
+                // survivors in waves of growing size, each raising the bar for the next (wave_select_kernel)
+                CK(cudaMemsetAsync(wa.cursor, 0, sizeof(int) * P, st));
+                static const int WAVES[] = {8, 16, 32, 64, 0x7fffffff};
+                for (int k = 0; k < 5; ++k) {
+                    wa.wave_size = WAVES[k]; wa.first = k == 0;
+                    wave_select_kernel<<<cdiv((long long)P * 32, 256), 256, 0, st>>>(wa);
+                    LAUNCHED();
+                    build_items_kernel<<<1, 1024, 0, st>>>(P, wa.wave_cnt, B[B_SURVPFX].as<int>(), &sc->n_surv_items, nullptr);
+                    LAUNCHED();
+                    sv.grp_cnt = wa.wave_cnt;
+                    rc = launch_score(ctx, pose, false, sv, st);
+                    if (rc) return rc;
+                }
+                if (limit) {
+                    // a later stage follows: fold the last wave's exact results into (B0, S0)
+                    wa.wave_size = 0; wa.first = 0; wa.n_exact = nullptr;
+                    wave_select_kernel<<<cdiv((long long)P * 32, 256), 256, 0, st>>>(wa);
+                    LAUNCHED();
+                }
+            }
+            return RP_OK;
+        };
+        int from = head;
+        if (mid) {
+            // (RP_MID_END=a,b,..: several mid stages, each against the bar the previous one left)
+            for (int k = 0; k < ctx->n_mid; ++k) {
+                if (ctx->mid_ends[k] <= from) continue;
+                rc = cascade(from, ctx->mid_ends[k], 0, nullptr, nullptr);
+                if (rc) return rc;
+                from = ctx->mid_ends[k];
             }
         }
+        CK(cudaEventRecord(ev[20], st));
+        rc = cascade(from, 0, ctx->tc_two_pass, use_tc ? ev[22] : nullptr, ev[21]);
+        if (rc) return rc;
     }
     CK(cudaEventRecord(ev[4], st));
     // 5. scan + LO problem list
@@ -638,7 +678,7 @@ int run_chunk(rp_ctx *ctx, int variant, const rp_options &opt, const ChunkIO &io
     ctx->last_cnt[8] += (int64_t)h_sc.tc_evaluated;
     ctx->last_cnt[9] += (int64_t)h_sc.tc_selected;
     ctx->last_cnt[10] += (int64_t)h_sc.lm_flops;
-    ctx->last_cnt[5] += ctx->prune ? (int64_t)h_sc.n_survivors + std::min<int64_t>(h_sc.n_hyp, (int64_t)P * ctx->head) : h_sc.n_hyp;
+    ctx->last_cnt[5] += ctx->prune ? (int64_t)h_sc.n_survivors + std::min<int64_t>(h_sc.n_hyp, (int64_t)P * ((ctx->tc && ctx->mid_end > ctx->head_small) ? ctx->head_small : ctx->head)) : h_sc.n_hyp;
     ctx->last_cnt[7] = ctx->head;
     flags.assign((size_t)P, 0);
     if (h_sc.any_flag) {
@@ -950,6 +990,19 @@ int rp_create(int device, rp_ctx **out) {
     if (const char *np = getenv("RP_NO_PRUNE")) ctx->prune = !(np[0] == '1');
     if (const char *nw = getenv("RP_NO_WAVES")) ctx->waves = !(nw[0] == '1');
     if (const char *lw = getenv("RP_LM_WARP")) ctx->lm_warp = atoi(lw) & 0xf;
+    if (const char *hs = getenv("RP_HEAD_SMALL")) { const int v = atoi(hs); if (v >= 0 && v <= 256 && v % 32 == 0) ctx->head_small = v; }
+    if (const char *me = getenv("RP_MID_END")) {
+        int n = 0, vals[4] = {0, 0, 0, 0};
+        bool ok = true;
+        for (const char *p = me; *p && n < 4;) {
+            const int v = atoi(p);
+            if (v < 0 || v > SEG || v % 32 != 0 || (n && v <= vals[n - 1])) ok = false;
+            vals[n++] = v;
+            while (*p && *p != ',') ++p;
+            if (*p == ',') ++p;
+        }
+        if (ok && n) { ctx->n_mid = n; for (int k = 0; k < 4; ++k) ctx->mid_ends[k] = vals[k]; ctx->mid_end = vals[n - 1]; }
+    }
     if (const char *nt = getenv("RP_NO_TC")) ctx->tc = !(nt[0] == '1');
     if (const char *sp = getenv("RP_TC_SPLIT")) { const int v = atoi(sp); if (v >= 1 && v <= 15) ctx->tc_two_pass = v; }
     if (const char *ap = getenv("RP_TC_ADAPT_PCT")) { const int v = atoi(ap); if (v >= 50 && v <= 200) ctx->tc_two_pass = -v; }

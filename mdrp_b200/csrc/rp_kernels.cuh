@@ -1074,6 +1074,18 @@ __global__ void pair_total_kernel(int n_pairs, int nseg, const int *seg_count, i
     pair_cnt[i] = c;
 }
 
+// models of a pair at positions [start, limit) of its first segment (limit > 0), or from `start` of the first segment to
+// the end of the pair (limit = 0)
+__global__ void range_count_kernel(int n_pairs, int nseg, const int *seg_count, int start, int limit, int *pair_cnt) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pairs) return;
+    const int c0 = seg_count[i * nseg];
+    if (limit > 0) { pair_cnt[i] = max(min(c0, limit) - start, 0); return; }
+    int c = max(c0 - start, 0);
+    for (int s = 1; s < nseg; ++s) c += seg_count[i * nseg + s];
+    pair_cnt[i] = c;
+}
+
 // tc_select: what the tensor-core tier (rp_tc.cuh) decided.  out[slot] = certain outliers of the model, a rigorous
 // lower bound of N - inlier_count, and thr^2 out of the score.  With (B0, S0) of the exactly scored head, a model with
 //     out >= N - B0   and   thr^2 out >= S0
@@ -1082,6 +1094,7 @@ __global__ void pair_total_kernel(int n_pairs, int nseg, const int *seg_count, i
 // One warp per pair.
 struct TcSelectArgs {
     int n_pairs, nseg, head;
+    int limit;       // > 0: only positions [head, limit) of the first segment (the mid stage); 0: everything from `head` on
     const PairParams *pairs;
     const int *seg_count;
     const int *out;
@@ -1103,8 +1116,8 @@ __global__ void tc_select_kernel(TcSelectArgs a) {
     const int n = pp.n;
     const int need_out = tc::need_outliers(n, pp.sq_thr, a.B0[warp], a.S0[warp]);   // same threshold as bound_kernel
     int ns = 0;
-    for (int seg = 0; seg < a.nseg; ++seg) {
-        const int cnt = a.seg_count[warp * a.nseg + seg];
+    for (int seg = 0; seg < (a.limit > 0 ? 1 : a.nseg); ++seg) {
+        const int cnt = a.limit > 0 ? min(a.seg_count[warp * a.nseg + seg], a.limit) : a.seg_count[warp * a.nseg + seg];
         const int rel0 = seg * (4 * SEG);
         for (int base = (seg == 0 ? a.head : 0); base < cnt; base += 32) {
             const int h = base + lane;
@@ -1199,6 +1212,7 @@ struct PruneArgs {
     int *surv_cnt;    // [n_pairs]
     unsigned long long *n_survivors;
     int head;   // models of segment 0 that were scored exactly (multiple of 32)
+    int limit;  // > 0: only positions [head, limit) of the first segment (the mid stage); 0: everything from `head` on
 };
 
 __global__ void prune_kernel(PruneArgs a) {
@@ -1210,8 +1224,8 @@ __global__ void prune_kernel(PruneArgs a) {
     const int B0 = a.B0[warp];
     const double S0 = a.S0[warp];
     int ns = 0;
-    for (int seg = 0; seg < a.nseg; ++seg) {
-        const int cnt = a.seg_count[warp * a.nseg + seg];
+    for (int seg = 0; seg < (a.limit > 0 ? 1 : a.nseg); ++seg) {
+        const int cnt = a.limit > 0 ? min(a.seg_count[warp * a.nseg + seg], a.limit) : a.seg_count[warp * a.nseg + seg];
         const int rel0 = seg * (4 * SEG);
         for (int base = (seg == 0 ? a.head : 0); base < cnt; base += 32) {
             const int h = base + lane;

@@ -258,6 +258,7 @@ struct TcArgs {
     // counts the remaining correspondences for the survivors only (`list`) and adds to `out`.
     int two_pass;                // 0: one pass over all correspondences; else two passes split at split[pair]
     const int *split;            // per pair: first correspondence of pass 1 (tc_split_kernel), a multiple of the point tile or n
+    int first;                   // without a list: the pair's models start at position `first` of its first segment
     int pass;                    // 0 / 1
     const int *list;             // pass 1: pair-relative slots of the models to process, [n_pairs][list_stride]
     const int *list_cnt;         //         [n_pairs]
@@ -391,6 +392,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_count_kernel(const __grid_const
     auto slot_of = [&](int pair, int j) -> int {
         if (a.list) return j < a.list_cnt[pair] ? a.list[(size_t)pair * a.list_stride + j] : -1;
         const int *segc = a.seg_count + (size_t)pair * a.nseg;
+        j += min(a.first, segc[0]);
         for (int seg = 0; seg < a.nseg; ++seg) {
             const int c = segc[seg];
             if (j < c) return seg * (4 * SEG) + j;
