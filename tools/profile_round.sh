@@ -17,8 +17,8 @@ cap() {  # name kernel-regex skip
   ncu --set full --clock-control none --import-source on -k regex:$2 -s $3 -c 1 -f -o gpurun_out/${TAG}_$1 \
       python bench.py --no-cpu-baseline --steps 1 --warmup 0 --pairs $PAIRS > gpurun_out/${TAG}_$1.log 2>&1
 }
-cap tc tc_count_kernel 0
-cap bound bound_kernel 0
+cap tc tc_count_kernel 1      # launch 0 is the mid stage, 1 the bulk first pass
+cap bound bound_kernel 1   # launch 0 is the mid stage
 cap lm lm_warp_kernel 0
 cap score_survivors score_kernel 1
 cap solve solve2_kernel 0
