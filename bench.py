@@ -74,16 +74,19 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t_timed=None):
+        """Samples that arrived after `t_timed` (the start of the timed region); the sampler is started before the
+        warm-up steps — the same load — so that a short timed region (N ranks each spawning nvidia-smi take ~0.5 s to
+        deliver the first line) still has samples: if none arrived inside it, the warm-up's are reported."""
         if self.proc:
             self.proc.terminate()
             try:
@@ -91,7 +94,9 @@ class ClockSampler:
             except Exception:
                 self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        inside = [ln for t, ln in self.lines if t_timed is None or t >= t_timed]
+        window = "timed region" if inside else "warm-up steps (none arrived inside the timed region)"
+        for ln in (inside or [ln for _, ln in self.lines]):
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -104,7 +109,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 # ---- CPU reference arm --------------------------------------------------------------------------------
@@ -264,16 +269,17 @@ def main():
     fp64_tf, fp32_tf = ctx.measure_pipes()
 
     # ---- value: inputs resident in HBM ------------------------------------------------------------
+    clocks = ClockSampler(local_rank)
+    clocks.start()
     for _ in range(args.warmup):
         step_dev()
     barrier()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
     launches0 = ctx.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stage_ms = {}
     counters = {}
     barrier()
+    t_timed = time.time()
     e0.record(stream)
     for _ in range(args.steps):
         step_dev()
@@ -286,7 +292,7 @@ def main():
     barrier()
     elapsed = e0.elapsed_time(e1) / 1000.0
     launches = ctx.launch_count - launches0
-    clk = clocks.stop()
+    clk = clocks.stop(t_timed)
     t = torch.tensor([elapsed], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
