@@ -72,7 +72,7 @@ struct LMParams {
 // everything about the current model that is constant across points
 struct LMFrame {
     M3 R, E;
-    V3 t;
+    V3 t, Rt;   // Rt = R^T t
     double scale, shift1, shift2, f1, f2, if1, if2, if1sq, if2sq;
 };
 
@@ -81,6 +81,7 @@ RP_HD LMFrame make_frame(const Model &m) {
     F.R = quat_to_rotmat(m.q);
     F.E = essential_from_motion(m.q, m.t);
     F.t = m.t;
+    F.Rt = mulT(F.R, m.t);
     F.scale = m.scale; F.shift1 = m.shift1; F.shift2 = m.shift2;
     F.f1 = m.f1; F.f2 = m.f2;
     F.if1 = 1.0 / m.f1;
@@ -135,25 +136,35 @@ RP_HD double point_cost(const LMFrame &F, const LMParams &P, double x1_0, double
     const V3 p1 = FOCAL_ ? v3(x1_0 * F.if1, x1_1 * F.if1, 1.0) : v3(x1_0, x1_1, 1.0);
     const V3 p2 = FOCAL_ ? v3(x2_0 * F.if2, x2_1 * F.if2, 1.0) : v3(x2_0, x2_1, 1.0);
     double cost = 0.0;
+    const M3 &R = F.R;
+    const M3 &E = F.E;
+    const double px = p1.x, py = p1.y, qx = p2.x, qy = p2.y;
     if (P.weight_sampson > 0.0) {
-        const V3 Ep1 = mul(F.E, p1), Etp2 = mulT(F.E, p2);
-        const double C = dot(p2, Ep1);
+        const V3 Ep1 = v3(fma_(E.r0.x, px, fma_(E.r0.y, py, E.r0.z)), fma_(E.r1.x, px, fma_(E.r1.y, py, E.r1.z)),
+                          fma_(E.r2.x, px, fma_(E.r2.y, py, E.r2.z)));
+        const V3 Etp2 = v3(fma_(E.r0.x, qx, fma_(E.r1.x, qy, E.r2.x)), fma_(E.r0.y, qx, fma_(E.r1.y, qy, E.r2.y)),
+                           fma_(E.r0.z, qx, fma_(E.r1.z, qy, E.r2.z)));
+        const double C = fma_(qx, Ep1.x, fma_(qy, Ep1.y, Ep1.z));
         const double A = Ep1.x * Ep1.x + Ep1.y * Ep1.y, B = Etp2.x * Etp2.x + Etp2.y * Etp2.y;
         const double inv = lm_rsqrt(A * if2sq + B * if1sq);
         const double rs = C * inv;
         cost += P.weight_sampson * loss_eval(loss_type, P.loss_scale, rs * rs);
     }
     if (P.scale_reproj > 0.0) {
+        // Z = R (a p1) + t = a s + t,  Y = R^T (b p2 - t) = b m - R^T t   (s = R p1, m = R^T p2: the forms point_eval uses)
+        const V3 s = v3(fma_(R.r0.x, px, fma_(R.r0.y, py, R.r0.z)), fma_(R.r1.x, px, fma_(R.r1.y, py, R.r1.z)),
+                        fma_(R.r2.x, px, fma_(R.r2.y, py, R.r2.z)));
+        const V3 m = v3(fma_(R.r0.x, qx, fma_(R.r1.x, qy, R.r2.x)), fma_(R.r0.y, qx, fma_(R.r1.y, qy, R.r2.y)),
+                        fma_(R.r0.z, qx, fma_(R.r1.z, qy, R.r2.z)));
         const double a = d1 + F.shift1;
-        V3 Z = mul(F.R, v3(a * p1.x, a * p1.y, a * p1.z));
-        Z = Z + F.t;
+        const V3 Z = v3(fma_(a, s.x, F.t.x), fma_(a, s.y, F.t.y), fma_(a, s.z, F.t.z));
         if (Z.z > 0.0) {
             const double iz = lm_rcp(Z.z);
             const double r0 = f2 * (Z.x * iz) - x2_0, r1 = f2 * (Z.y * iz) - x2_1;
             cost += loss_eval(loss_type, P.loss_scale, P.scale_reproj * (r0 * r0 + r1 * r1));
         }
         const double b = F.scale * (d2 + F.shift2);
-        const V3 Y = mulT(F.R, v3(b * p2.x - F.t.x, b * p2.y - F.t.y, b * p2.z - F.t.z));
+        const V3 Y = v3(fma_(b, m.x, -F.Rt.x), fma_(b, m.y, -F.Rt.y), fma_(b, m.z, -F.Rt.z));
         if (Y.z > 0.0) {
             const double iz = lm_rcp(Y.z);
             const double r0 = f1 * (Y.x * iz) - x1_0, r1 = f1 * (Y.y * iz) - x1_1;
@@ -180,7 +191,7 @@ RP_HD double point_cost(const LMFrame &F, const LMParams &P, double x1_0, double
 //   reprojection 2->1, both rows       : LM_FLOPS[v][3]   (7 | 8 | 8 | 9 columns)
 // (v = RP_CALIB, RP_CALIB_SHIFT, RP_SHARED, RP_VARYING; derivation in DESIGN.md §5).  `rows` counts the accumulated
 // rows of the three kinds in three 21-bit fields; the LM kernel turns the counts into the bench's lm_flops.
-constexpr int LM_FLOPS[4][4] = {{110, 161, 133, 197}, {110, 161, 179, 237}, {120, 216, 183, 259}, {120, 235, 217, 301}};
+constexpr int LM_FLOPS[4][4] = {{104, 146, 131, 182}, {104, 146, 162, 222}, {112, 201, 183, 244}, {112, 220, 217, 286}};
 
 template <int VARIANT, int NP, int LOSS = -1>
 RP_HD double point_eval(const LMFrame &F, const LMParams &P, double x1_0, double x1_1, double x2_0,
@@ -203,14 +214,22 @@ RP_HD double point_eval(const LMFrame &F, const LMParams &P, double x1_0, double
     const M3 &E = F.E;
     double J[NP];
     double cost = 0.0;
+    // s = R p1 and m = R^T p2 serve all three residual blocks: Z = R (a p1) + t = a s + t, Y = R^T (b p2 - t) = b m - R^T t,
+    // the translation columns of the Sampson row, the shift1 column (= s) and the scale / shift2 columns (along m).
+    // Three-term sums are written as nested FMAs: `a*b + c*d + e` contracts to MUL + FMA + ADD, and the FP64 pipe's issue
+    // rate is what bounds this kernel.
+    const V3 s = v3(fma_(R.r0.x, px, fma_(R.r0.y, py, R.r0.z)), fma_(R.r1.x, px, fma_(R.r1.y, py, R.r1.z)),
+                    fma_(R.r2.x, px, fma_(R.r2.y, py, R.r2.z)));
+    const V3 m = v3(fma_(R.r0.x, qx, fma_(R.r1.x, qy, R.r2.x)), fma_(R.r0.y, qx, fma_(R.r1.y, qy, R.r2.y)),
+                    fma_(R.r0.z, qx, fma_(R.r1.z, qy, R.r2.z)));
 
     // ---- Sampson row ----
     if (P.weight_sampson > 0.0) {
-        const V3 Ep1 = v3(E.r0.x * px + E.r0.y * py + E.r0.z, E.r1.x * px + E.r1.y * py + E.r1.z,
-                          E.r2.x * px + E.r2.y * py + E.r2.z);
-        const V3 Etp2 = v3(E.r0.x * qx + E.r1.x * qy + E.r2.x, E.r0.y * qx + E.r1.y * qy + E.r2.y,
-                           E.r0.z * qx + E.r1.z * qy + E.r2.z);
-        const double C = qx * Ep1.x + qy * Ep1.y + Ep1.z;
+        const V3 Ep1 = v3(fma_(E.r0.x, px, fma_(E.r0.y, py, E.r0.z)), fma_(E.r1.x, px, fma_(E.r1.y, py, E.r1.z)),
+                          fma_(E.r2.x, px, fma_(E.r2.y, py, E.r2.z)));
+        const V3 Etp2 = v3(fma_(E.r0.x, qx, fma_(E.r1.x, qy, E.r2.x)), fma_(E.r0.y, qx, fma_(E.r1.y, qy, E.r2.y)),
+                           fma_(E.r0.z, qx, fma_(E.r1.z, qy, E.r2.z)));
+        const double C = fma_(qx, Ep1.x, fma_(qy, Ep1.y, Ep1.z));
         const double A = Ep1.x * Ep1.x + Ep1.y * Ep1.y, B = Etp2.x * Etp2.x + Etp2.y * Etp2.y;
         const double inv = lm_rsqrt(A * if2sq + B * if1sq);
         const double rs = C * inv;
@@ -244,9 +263,7 @@ RP_HD double point_eval(const LMFrame &F, const LMParams &P, double x1_0, double
                 const double dC = px * Etp2.y - py * Etp2.x;
                 J[2] = dC - c2 * ((Ep1.x * dx + Ep1.y * dy) * a2);
             }
-            // translation: dE = [e_i]x R ;  d(Ep1) = e_i x (R p1),  d(E^T p2) = -R^T (e_i x p2)
-            const V3 s = v3(R.r0.x * px + R.r0.y * py + R.r0.z, R.r1.x * px + R.r1.y * py + R.r1.z,
-                            R.r2.x * px + R.r2.y * py + R.r2.z);
+            // translation: dE = [e_i]x R ;  d(Ep1) = e_i x (R p1) = e_i x s,  d(E^T p2) = -R^T (e_i x p2)
             {
                 // e_0 x s = (0, -s.z, s.y);  e_0 x p2 = (0, -1, qy) -> d(E^T p2) = row1(R) - qy row2(R)
                 const double tx = R.r1.x - qy * R.r2.x, ty = R.r1.y - qy * R.r2.y;
@@ -288,9 +305,7 @@ RP_HD double point_eval(const LMFrame &F, const LMParams &P, double x1_0, double
     // ---- reprojection 1 -> 2 : Z = R (a p1) + t ----
     {
         const double a = d1 + F.shift1;
-        const double Px = a * px, Py = a * py, Pz = a;
-        const V3 Z = v3(R.r0.x * Px + R.r0.y * Py + R.r0.z * Pz + F.t.x, R.r1.x * Px + R.r1.y * Py + R.r1.z * Pz + F.t.y,
-                        R.r2.x * Px + R.r2.y * Py + R.r2.z * Pz + F.t.z);
+        const V3 Z = v3(fma_(a, s.x, F.t.x), fma_(a, s.y, F.t.y), fma_(a, s.z, F.t.z));
         if (Z.z > 0.0) {
             const double iz = lm_rcp(Z.z);
             const double u0 = Z.x * iz, u1 = Z.y * iz;
@@ -321,14 +336,12 @@ RP_HD double point_eval(const LMFrame &F, const LMParams &P, double x1_0, double
                 J0[3] = 1.0; J0[5] = -u0;
                 J1[4] = 1.0; J1[5] = -u1;
                 if (VARIANT == RP_CALIB_SHIFT) {
-                    // dZ/dshift1 = R p1
-                    const double dx = R.r0.x * px + R.r0.y * py + R.r0.z, dy = R.r1.x * px + R.r1.y * py + R.r1.z,
-                                 dz = R.r2.x * px + R.r2.y * py + R.r2.z;
-                    J0[7] = dx - u0 * dz; J1[7] = dy - u1 * dz;
+                    // dZ/dshift1 = R p1 = s
+                    J0[7] = s.x - u0 * s.z; J1[7] = s.y - u1 * s.z;
                 }
                 if (FOCAL) {
                     // dZ/df1 = R (-a px/f1, -a py/f1, 0) ; d(pi)/df2 = (u0, u1) = g (Z.x, Z.y) / f2^2... kept as (u0, u1) / g
-                    const double ex = -Px * F.if1, ey = -Py * F.if1;
+                    const double ex = -(a * px) * F.if1, ey = -(a * py) * F.if1;
                     const double dx = R.r0.x * ex + R.r0.y * ey, dy = R.r1.x * ex + R.r1.y * ey, dz = R.r2.x * ex + R.r2.y * ey;
                     J0[7] = dx - u0 * dz; J1[7] = dy - u1 * dz;
                     J0[CF2] += Z.x * F.if2; J1[CF2] += Z.y * F.if2;
@@ -345,9 +358,7 @@ RP_HD double point_eval(const LMFrame &F, const LMParams &P, double x1_0, double
     {
         const double bb = d2 + F.shift2;
         const double b = F.scale * bb;
-        const double Qx = b * qx - F.t.x, Qy = b * qy - F.t.y, Qz = b - F.t.z;
-        const V3 Y = v3(R.r0.x * Qx + R.r1.x * Qy + R.r2.x * Qz, R.r0.y * Qx + R.r1.y * Qy + R.r2.y * Qz,
-                        R.r0.z * Qx + R.r1.z * Qy + R.r2.z * Qz);
+        const V3 Y = v3(fma_(b, m.x, -F.Rt.x), fma_(b, m.y, -F.Rt.y), fma_(b, m.z, -F.Rt.z));
         if (Y.z > 0.0) {
             const double iz = lm_rcp(Y.z);
             const double u0 = Y.x * iz, u1 = Y.y * iz;
@@ -370,9 +381,7 @@ RP_HD double point_eval(const LMFrame &F, const LMParams &P, double x1_0, double
                 J0[4] = u0 * R.r1.z - R.r1.x; J1[4] = u1 * R.r1.z - R.r1.y;
                 J0[5] = u0 * R.r2.z - R.r2.x; J1[5] = u1 * R.r2.z - R.r2.y;
                 // dY/dscale = R^T ((d2+v) p2),  dY/dshift2 = R^T (scale p2): both along m = R^T p2
-                const double mx = R.r0.x * qx + R.r1.x * qy + R.r2.x, my = R.r0.y * qx + R.r1.y * qy + R.r2.y,
-                             mz = R.r0.z * qx + R.r1.z * qy + R.r2.z;
-                const double m0 = mx - u0 * mz, m1 = my - u1 * mz;
+                const double m0 = m.x - u0 * m.z, m1 = m.y - u1 * m.z;
                 J0[6] = bb * m0; J1[6] = bb * m1;
                 if (VARIANT == RP_CALIB_SHIFT) { J0[8] = F.scale * m0; J1[8] = F.scale * m1; }
                 if (FOCAL) {

@@ -473,3 +473,43 @@ def test_lo_kernels_agree(cfg, monkeypatch):
     for f in ("q", "t", "scale", "shift1", "shift2", "f1", "f2"):
         if f in a[0].dtype.names:
             assert np.allclose(a[0][f], b[0][f], rtol=1e-9, atol=1e-9), f
+
+
+@pytest.mark.parametrize("cfg", ["cfg2_calib_shift", "cfg3_shared_focal", "cfg4_varying_focal"])
+def test_pruning_does_not_change_results_at_baseline_size(cfg, monkeypatch):
+    """The same guard as above at BASELINE.json's size (2 000 matches x 10 000 iterations: ten 1 024-iteration segments
+    per pair, mid stage and both tensor-core passes active) on the bench's own generator: the whole cascade against
+    RP_NO_PRUNE=1 (every minimal model scored exactly), bytewise."""
+    c = synth.CONFIGS[cfg]
+    b = synth.make_batch(cfg, 24, seed=4242)
+    variant = {"calib": nv.CALIB_SHIFT if c["shift"] else nv.CALIB, "shared": nv.SHARED, "varying": nv.VARYING}[c["variant"]]
+    o = _options(c["iters"], shift=c["shift"])
+    for k in ("RP_NO_PRUNE", "RP_NO_WAVES", "RP_NO_TC", "RP_TC_ONE_PASS", "RP_MID_END"):
+        monkeypatch.delenv(k, raising=False)
+    ctx = nv.Context(0)
+    a = ctx.estimate_batch_host(variant, b["offsets"], b["x1"], b["x2"], b["d1"], b["d2"], b["cams"], o)
+    _, cnt = ctx.last_timing()
+    ctx.close()
+    assert cnt["exact_models"] < 0.05 * cnt["hypotheses"] and cnt["tc_evaluated"] > 0
+    monkeypatch.setenv("RP_NO_PRUNE", "1")
+    full = nv.Context(0)
+    f = full.estimate_batch_host(variant, b["offsets"], b["x1"], b["x2"], b["d1"], b["d2"], b["cams"], o)
+    _, cntf = full.last_timing()
+    full.close()
+    monkeypatch.delenv("RP_NO_PRUNE")
+    assert cntf["exact_models"] == cntf["hypotheses"]
+    assert a[0].tobytes() == f[0].tobytes() and a[2].tobytes() == f[2].tobytes()
+    for k in ("refinements", "iterations", "num_inliers", "inlier_ratio"):
+        assert np.array_equal(a[1][k], f[1][k]), k
+    assert np.allclose(a[1]["model_score"], f[1]["model_score"], rtol=1e-12, atol=0)
+    # the plain 128-model exact head instead of the short head + mid stage: same bytes
+    monkeypatch.setenv("RP_MID_END", "0")
+    head = nv.Context(0)
+    h = head.estimate_batch_host(variant, b["offsets"], b["x1"], b["x2"], b["d1"], b["d2"], b["cams"], o)
+    _, cnth = head.last_timing()
+    head.close()
+    monkeypatch.delenv("RP_MID_END")
+    assert cnth["exact_models"] > cnt["exact_models"]
+    assert a[0].tobytes() == h[0].tobytes() and a[2].tobytes() == h[2].tobytes()
+    for k in ("refinements", "iterations", "num_inliers", "inlier_ratio"):
+        assert np.array_equal(a[1][k], h[1][k]), k

@@ -4,7 +4,7 @@ cd "$(dirname "$0")/.."
 cp mdrp_b200/librepose_b200.so /tmp/orig.so
 IFS=';' read -ra CF <<< "${CFGS:-cfg2_calib_shift 10000;cfg4_varying_focal 10000;cfg1_calib_scale 20000}"
 for lib in ${LIBS:-cur}; do
-  [ "$lib" = cur ] || cp build_variants/$lib.so mdrp_b200/librepose_b200.so
+  if [ "$lib" = cur ]; then cp /tmp/orig.so mdrp_b200/librepose_b200.so; else cp build_variants/$lib.so mdrp_b200/librepose_b200.so; fi
   for cfg in "${CF[@]}"; do
     set -- $cfg
     for m in ${MASKS:-0 15}; do

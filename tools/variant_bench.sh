@@ -4,7 +4,7 @@
 cd "$(dirname "$0")/.."
 cp mdrp_b200/librepose_b200.so /tmp/orig.so
 for v in "$@"; do
-  [ "$v" = cur ] || cp build_variants/$v.so mdrp_b200/librepose_b200.so   # `cur`: the library as built in-tree
+  if [ "$v" = cur ]; then cp /tmp/orig.so mdrp_b200/librepose_b200.so; else cp build_variants/$v.so mdrp_b200/librepose_b200.so; fi   # `cur`: the library as built in-tree
   python bench.py --no-cpu-baseline --steps 2 --warmup 3 ${BENCH_ARGS} > gpurun_out/variant_$v.json 2> gpurun_out/variant_$v.err
   python - "$v" <<'PY'
 import json, sys
