@@ -66,8 +66,54 @@ RP_HD double lm_rsqrt(double x) {
 
 struct LMParams {
     double scale_reproj, weight_sampson, loss_scale;
+    double inv_t2;      // 1 / loss_scale^2
     int loss_type;
 };
+
+// Cost of the Cauchy losses, sum_k t^2 log1p(r_k^2 / t^2), accumulated as t^2 log(prod_k (1 + r_k^2 / t^2)): one FMA per
+// residual instead of a 45-instruction FP64 log1p (the final refinement evaluates three of them per correspondence per
+// pass).  Two running products (the Sampson terms carry weight_sampson), folded into `acc` every 512 factors
+// (TRUNCATED_CAUCHY: factors <= 2, so the product stays below 2^512) or when a product passes 1e150 (CAUCHY).
+struct LogProd {
+    double ps, pr, acc;
+    int cnt;
+    RP_HD void init() { ps = 1.0; pr = 1.0; acc = 0.0; cnt = 0; }
+    RP_HD void fold(double ws) { acc += ws * log(ps) + log(pr); ps = 1.0; pr = 1.0; cnt = 0; }
+    // the accumulated cost, in units of t^2
+    RP_HD double total(double ws) const { return acc + ws * log(ps) + log(pr); }
+    template <bool SAMPSON>
+    RP_HD void add(int type, double x, double ws) {
+        if (type == RP_LOSS_TRUNCATED_CAUCHY) x = x > 1.0 ? 1.0 : x;   // (a NaN residual stays NaN, as in loss_eval)
+        else if (!(x < 1e100)) { acc += (SAMPSON ? ws : 1.0) * log1p(x); return; }
+        if (SAMPSON) ps = fma_(ps, x, ps); else pr = fma_(pr, x, pr);
+        if (++cnt >= 512 || (type == RP_LOSS_CAUCHY && (ps > 1e150 || pr > 1e150))) fold(ws);
+    }
+};
+
+// one robustified residual of the LM cost: returns its contribution, or parks it in `lp` (device, Cauchy losses)
+template <int LOSS, bool SAMPSON>
+RP_HD double robust_cost(const LMParams &P, int loss_type, double r2, LogProd &lp) {
+#ifdef __CUDA_ARCH__
+    if (LOSS < 0 && (loss_type == RP_LOSS_CAUCHY || loss_type == RP_LOSS_TRUNCATED_CAUCHY)) {
+        lp.template add<SAMPSON>(loss_type, r2 * P.inv_t2, P.weight_sampson);
+        return 0.0;
+    }
+#endif
+    return (SAMPSON ? P.weight_sampson : 1.0) * loss_eval(loss_type, P.loss_scale, r2);
+}
+// IRLS weight; on the device the Cauchy weights 1 / (1 + r^2 / t^2) use the Newton-refined reciprocal instead of two
+// IEEE divisions
+template <int LOSS>
+RP_HD double robust_weight(const LMParams &P, int loss_type, double r2) {
+#ifdef __CUDA_ARCH__
+    if (LOSS < 0 && (loss_type == RP_LOSS_CAUCHY || loss_type == RP_LOSS_TRUNCATED_CAUCHY)) {
+        const double x = r2 * P.inv_t2;
+        if (loss_type == RP_LOSS_TRUNCATED_CAUCHY && x > 1.0) return 0.0;
+        return lm_rcp(1.0 + x);
+    }
+#endif
+    return loss_weight(loss_type, P.loss_scale, r2);
+}
 
 // everything about the current model that is constant across points
 struct LMFrame {
@@ -127,7 +173,7 @@ RP_HD V3 row(const M3 &M, int i) { return i == 0 ? M.r0 : (i == 1 ? M.r1 : M.r2)
 // switch disappears); LOSS < 0 reads it from P.
 template <int VARIANT, int LOSS = -1>
 RP_HD double point_cost(const LMFrame &F, const LMParams &P, double x1_0, double x1_1, double x2_0, double x2_1,
-                        double d1, double d2) {
+                        double d1, double d2, LogProd &lp) {
     constexpr bool FOCAL_ = (VARIANT == RP_SHARED || VARIANT == RP_VARYING);
     const int loss_type = LOSS >= 0 ? LOSS : P.loss_type;
     // calibrated variants carry f1 = f2 = 1: literal ones let the compiler drop the multiplications
@@ -148,7 +194,7 @@ RP_HD double point_cost(const LMFrame &F, const LMParams &P, double x1_0, double
         const double A = Ep1.x * Ep1.x + Ep1.y * Ep1.y, B = Etp2.x * Etp2.x + Etp2.y * Etp2.y;
         const double inv = lm_rsqrt(A * if2sq + B * if1sq);
         const double rs = C * inv;
-        cost += P.weight_sampson * loss_eval(loss_type, P.loss_scale, rs * rs);
+        cost += robust_cost<LOSS, true>(P, loss_type, rs * rs, lp);
     }
     if (P.scale_reproj > 0.0) {
         // Z = R (a p1) + t = a s + t,  Y = R^T (b p2 - t) = b m - R^T t   (s = R p1, m = R^T p2: the forms point_eval uses)
@@ -161,14 +207,14 @@ RP_HD double point_cost(const LMFrame &F, const LMParams &P, double x1_0, double
         if (Z.z > 0.0) {
             const double iz = lm_rcp(Z.z);
             const double r0 = f2 * (Z.x * iz) - x2_0, r1 = f2 * (Z.y * iz) - x2_1;
-            cost += loss_eval(loss_type, P.loss_scale, P.scale_reproj * (r0 * r0 + r1 * r1));
+            cost += robust_cost<LOSS, false>(P, loss_type, P.scale_reproj * (r0 * r0 + r1 * r1), lp);
         }
         const double b = F.scale * (d2 + F.shift2);
         const V3 Y = v3(fma_(b, m.x, -F.Rt.x), fma_(b, m.y, -F.Rt.y), fma_(b, m.z, -F.Rt.z));
         if (Y.z > 0.0) {
             const double iz = lm_rcp(Y.z);
             const double r0 = f1 * (Y.x * iz) - x1_0, r1 = f1 * (Y.y * iz) - x1_1;
-            cost += loss_eval(loss_type, P.loss_scale, P.scale_reproj * (r0 * r0 + r1 * r1));
+            cost += robust_cost<LOSS, false>(P, loss_type, P.scale_reproj * (r0 * r0 + r1 * r1), lp);
         }
     }
     return cost;
@@ -195,7 +241,7 @@ constexpr int LM_FLOPS[4][4] = {{104, 146, 131, 182}, {104, 146, 162, 222}, {112
 
 template <int VARIANT, int NP, int LOSS = -1>
 RP_HD double point_eval(const LMFrame &F, const LMParams &P, double x1_0, double x1_1, double x2_0,
-                        double x2_1, double d1, double d2, NormalEq<NP> &N, unsigned long long &rows) {
+                        double x2_1, double d1, double d2, NormalEq<NP> &N, unsigned long long &rows, LogProd &lp) {
     constexpr bool FOCAL = (VARIANT == RP_SHARED || VARIANT == RP_VARYING);
     const int loss_type = LOSS >= 0 ? LOSS : P.loss_type;
     // calibrated variants carry f1 = f2 = 1: literal ones let the compiler drop the multiplications (and the
@@ -233,12 +279,12 @@ RP_HD double point_eval(const LMFrame &F, const LMParams &P, double x1_0, double
         const double A = Ep1.x * Ep1.x + Ep1.y * Ep1.y, B = Etp2.x * Etp2.x + Etp2.y * Etp2.y;
         const double inv = lm_rsqrt(A * if2sq + B * if1sq);
         const double rs = C * inv;
-        cost += P.weight_sampson * loss_eval(loss_type, P.loss_scale, rs * rs);
+        cost += robust_cost<LOSS, true>(P, loss_type, rs * rs, lp);
         // the reference scales the Sampson residual and its Jacobian row by weight_sampson, so the normal equations
         // carry weight_sampson^2 although the cost carries weight_sampson (verified on the binary; invisible at 1)
         // ... and the focal accumulators evaluate the robust weight at weight_sampson * r^2, the calibrated one at r^2
         const double w = P.weight_sampson * P.weight_sampson *
-                         loss_weight(loss_type, P.loss_scale, FOCAL ? P.weight_sampson * (rs * rs) : rs * rs);
+                         robust_weight<LOSS>(P, loss_type, FOCAL ? P.weight_sampson * (rs * rs) : rs * rs);
         if (w != 0.0) {
 #pragma unroll
             for (int i = 0; i < NP; ++i) J[i] = 0.0;
@@ -310,9 +356,8 @@ RP_HD double point_eval(const LMFrame &F, const LMParams &P, double x1_0, double
             const double iz = lm_rcp(Z.z);
             const double u0 = Z.x * iz, u1 = Z.y * iz;
             const double r0 = f2 * u0 - x2_0, r1 = f2 * u1 - x2_1;
-            cost += loss_eval(loss_type, P.loss_scale, P.scale_reproj * (r0 * r0 + r1 * r1));
-            const double w = P.scale_reproj *
-                             loss_weight(loss_type, P.loss_scale, P.scale_reproj * (r0 * r0 + r1 * r1));
+            cost += robust_cost<LOSS, false>(P, loss_type, P.scale_reproj * (r0 * r0 + r1 * r1), lp);
+            const double w = P.scale_reproj * robust_weight<LOSS>(P, loss_type, P.scale_reproj * (r0 * r0 + r1 * r1));
             if (w != 0.0) {
                 const double g = f2 * iz;
                 const double zg = FOCAL ? Z.z * F.if2 : Z.z;   // 1 / g
@@ -363,9 +408,8 @@ RP_HD double point_eval(const LMFrame &F, const LMParams &P, double x1_0, double
             const double iz = lm_rcp(Y.z);
             const double u0 = Y.x * iz, u1 = Y.y * iz;
             const double r0 = f1 * u0 - x1_0, r1 = f1 * u1 - x1_1;
-            cost += loss_eval(loss_type, P.loss_scale, P.scale_reproj * (r0 * r0 + r1 * r1));
-            const double w = P.scale_reproj *
-                             loss_weight(loss_type, P.loss_scale, P.scale_reproj * (r0 * r0 + r1 * r1));
+            cost += robust_cost<LOSS, false>(P, loss_type, P.scale_reproj * (r0 * r0 + r1 * r1), lp);
+            const double w = P.scale_reproj * robust_weight<LOSS>(P, loss_type, P.scale_reproj * (r0 * r0 + r1 * r1));
             if (w != 0.0) {
                 const double g = f1 * iz;
                 const double zg = FOCAL ? Y.z * F.if1 : Y.z;   // 1 / g
@@ -405,7 +449,9 @@ template <int VARIANT, int NP>
 RP_HD void point_accumulate(const LMFrame &F, const LMParams &P, double x1_0, double x1_1, double x2_0,
                             double x2_1, double d1, double d2, NormalEq<NP> &N) {
     unsigned long long rows = 0;
-    (void)point_eval<VARIANT, NP>(F, P, x1_0, x1_1, x2_0, x2_1, d1, d2, N, rows);
+    LogProd lp;
+    lp.init();
+    (void)point_eval<VARIANT, NP>(F, P, x1_0, x1_1, x2_0, x2_1, d1, d2, N, rows, lp);
 }
 
 // parameter update of lm_impl's problem.step(): R <- R exp([dw]x), everything else additive

@@ -123,6 +123,7 @@ __global__ void __launch_bounds__(THREADS, RP_LM_MIN_BLOCKS * 128 / THREADS) lm_
             P.loss_type = RP_LOSS_TRUNCATED;
             P.loss_scale = pp.lo_loss_scale;
         }
+        P.inv_t2 = 1.0 / (P.loss_scale * P.loss_scale);
         const int max_it = a.use_final ? a.max_iterations : 25;
         const int n = pp.n;
         const Pt64 *pts = a.pts64 + pp.off;
@@ -162,12 +163,15 @@ __global__ void __launch_bounds__(THREADS, RP_LM_MIN_BLOCKS * 128 / THREADS) lm_
         auto block_cost = [&](const Model &m) -> double {
             const LMFrame F = make_frame(m);
             double c = 0.0;
+            LogProd lp;
+            lp.init();
             for (int i = tid; i < m_work; i += LM_THREADS) {
                 const int k = use_list ? (int)list_s[i] : i;
                 if (!use_list && mask && !mask[k]) continue;
                 const Pt64 p = pts[k];
-                c += point_cost<VARIANT, LOSS>(F, P, p.x1_0, p.x1_1, p.x2_0, p.x2_1, d1[k], d2[k]);
+                c += point_cost<VARIANT, LOSS>(F, P, p.x1_0, p.x1_1, p.x2_0, p.x2_1, d1[k], d2[k], lp);
             }
+            if (LOSS < 0) c += P.loss_scale * P.loss_scale * lp.total(P.weight_sampson);
             c = warp_sum(c);
             __syncthreads();
             if (lane == 0) cred[wid] = c;
@@ -183,14 +187,17 @@ __global__ void __launch_bounds__(THREADS, RP_LM_MIN_BLOCKS * 128 / THREADS) lm_
         auto block_eval = [&](const Model &m, NormalEq<NP> &N) -> double {
             const LMFrame F = make_frame(m);
             double c = 0.0;
+            LogProd lp;
+            lp.init();
             N.clear();
 #pragma unroll LM_UNROLL
             for (int i = tid; i < m_work; i += LM_THREADS) {
                 const int k = use_list ? (int)list_s[i] : i;
                 if (!use_list && mask && !mask[k]) continue;
                 const Pt64 p = pts[k];
-                c += point_eval<VARIANT, NP, LOSS>(F, P, p.x1_0, p.x1_1, p.x2_0, p.x2_1, d1[k], d2[k], N, rows);
+                c += point_eval<VARIANT, NP, LOSS>(F, P, p.x1_0, p.x1_1, p.x2_0, p.x2_1, d1[k], d2[k], N, rows, lp);
             }
+            if (LOSS < 0) c += P.loss_scale * P.loss_scale * lp.total(P.weight_sampson);
             c = warp_sum(c);
             __syncthreads();
             if (lane == 0) cred[wid] = c;
@@ -372,6 +379,7 @@ __global__ void __launch_bounds__(LMW_WPB[VARIANT] * 32, LMW_BPS[VARIANT]) lm_wa
             P.loss_type = RP_LOSS_TRUNCATED;
             P.loss_scale = pp.lo_loss_scale;
         }
+        P.inv_t2 = 1.0 / (P.loss_scale * P.loss_scale);
         const int max_it = a.use_final ? a.max_iterations : 25;
         const int n = pp.n;
         const Pt64 *pts = a.pts64 + pp.off;
@@ -399,6 +407,8 @@ __global__ void __launch_bounds__(LMW_WPB[VARIANT] * 32, LMW_BPS[VARIANT]) lm_wa
             constexpr bool jac = decltype(jac_tag)::value;
             const LMFrame F = make_frame(m);
             double c = 0.0;
+            LogProd lp;
+            lp.init();
             if (jac) N.clear();
             fetch(lane, 0);
             fetch(lane + 32, 1);
@@ -408,11 +418,12 @@ __global__ void __launch_bounds__(LMW_WPB[VARIANT] * 32, LMW_BPS[VARIANT]) lm_wa
                 const Slot q = ring[s][lane];
                 int s2 = s + 2; if (s2 >= LMW_SLOTS) s2 -= LMW_SLOTS;
                 fetch(i + 64, s2);
-                if (jac) c += point_eval<VARIANT, NP, LOSS>(F, P, q.x[0], q.x[1], q.x[2], q.x[3], q.d1, q.d2, N, rows);
-                else c += point_cost<VARIANT, LOSS>(F, P, q.x[0], q.x[1], q.x[2], q.x[3], q.d1, q.d2);
+                if (jac) c += point_eval<VARIANT, NP, LOSS>(F, P, q.x[0], q.x[1], q.x[2], q.x[3], q.d1, q.d2, N, rows, lp);
+                else c += point_cost<VARIANT, LOSS>(F, P, q.x[0], q.x[1], q.x[2], q.x[3], q.d1, q.d2, lp);
                 if (++s == LMW_SLOTS) s = 0;
             }
             cp_async_wait<0>();
+            if (LOSS < 0) c += P.loss_scale * P.loss_scale * lp.total(P.weight_sampson);
             return warp_sum(c);
         };
         auto reduce_normal = [&](NormalEq<NP> &N) {
