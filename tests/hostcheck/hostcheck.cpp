@@ -77,10 +77,13 @@ static void accumulate_t(const Model &m, const LMParams &P, const double *x1, co
     NormalEq<NP> N;
     N.clear();
     double c = 0;
+    LogProd lp;   // (only the device path parks Cauchy terms in it; on the host every term comes back through the return value)
+    lp.init();
     for (long k = 0; k < n; ++k) {
         point_accumulate<V, NP>(F, P, x1[2 * k], x1[2 * k + 1], x2[2 * k], x2[2 * k + 1], d1[k], d2[k], N);
-        c += point_cost<V>(F, P, x1[2 * k], x1[2 * k + 1], x2[2 * k], x2[2 * k + 1], d1[k], d2[k]);
+        c += point_cost<V>(F, P, x1[2 * k], x1[2 * k + 1], x2[2 * k], x2[2 * k + 1], d1[k], d2[k], lp);
     }
+    c += P.loss_scale * P.loss_scale * lp.total(P.weight_sampson);
     std::memset(JtJ, 0, 81 * sizeof(double));
     std::memset(Jtr, 0, 9 * sizeof(double));
     for (int i = 0; i < NP; ++i) {
@@ -97,6 +100,7 @@ HC void hc_accumulate(int variant, const rp_model *model, const double *x1, cons
     std::memcpy(&m, model, sizeof(m));
     LMParams P;
     P.scale_reproj = scale_reproj; P.weight_sampson = weight_sampson; P.loss_scale = loss_scale; P.loss_type = loss_type;
+    P.inv_t2 = 1.0 / (loss_scale * loss_scale);
     switch (variant) {
     case RP_CALIB: accumulate_t<RP_CALIB, 7>(m, P, x1, x2, d1, d2, n, JtJ, Jtr, cost); break;
     case RP_CALIB_SHIFT: accumulate_t<RP_CALIB_SHIFT, 9>(m, P, x1, x2, d1, d2, n, JtJ, Jtr, cost); break;
