@@ -81,7 +81,8 @@ struct rp_ctx {
     double last_ms[16] = {0};
     double prev_h2d_ms = 0.0, prev_dev_ms = 0.0;  // upload / kernel time of the previous host-path call (lead-chunk sizing)
     int64_t last_cnt[16] = {0};  // [5] models through the exact kernel, [6] point-scores the bound kernel evaluated
-    size_t workspace_budget = (size_t)32 << 30;  // HBM is 180 GB: big chunks amortise kernel tails
+    size_t workspace_budget = (size_t)80 << 30;  // HBM is 180 GB: big chunks amortise kernel tails and launches (10 000 pairs x 10 000
+                                                 // iterations = one 71 GB chunk; measured 32 -> 80 GB: +3 %); capped at half of the free memory
     bool prune = true;  // hypothesis-level pruning (RP_NO_PRUNE=1 scores every minimal model exactly)
     int head = HB;      // models per pair scored exactly before the bound kernel (RP_HEAD=32|64|96|128; measured: 128 best on cfg2/cfg4, 64 marginally better on the 1000-iteration configs)
     bool waves = true;  // survivors of the prune scored in waves (RP_NO_WAVES=1: all at once)
