@@ -190,6 +190,7 @@ int launch_lm(rp_ctx *ctx, int variant, const LMArgs &a, long long expected_prob
     LMArgs la = a;
     la.work_counter = &ctx->buf[B_SCALARS].as<Scalars>()->lm_work;
     la.warp_kernel = (ctx->lm_warp >> variant) & 1;
+    la.warp_single = (ctx->lm_warp >> 4) & 1;
     CK(cudaMemsetAsync(la.work_counter, 0, sizeof(int), st));
     CK((cudaError_t)launch_lm_kernel(ctx->sms, variant, la, st));
     return RP_OK;
@@ -990,7 +991,7 @@ int rp_create(int device, rp_ctx **out) {
     for (auto &ev : ctx->ev) cudaEventCreate(&ev);
     if (const char *np = getenv("RP_NO_PRUNE")) ctx->prune = !(np[0] == '1');
     if (const char *nw = getenv("RP_NO_WAVES")) ctx->waves = !(nw[0] == '1');
-    if (const char *lw = getenv("RP_LM_WARP")) ctx->lm_warp = atoi(lw) & 0xf;
+    if (const char *lw = getenv("RP_LM_WARP")) ctx->lm_warp = atoi(lw) & 0x1f;
     if (const char *hs = getenv("RP_HEAD_SMALL")) { const int v = atoi(hs); if (v >= 0 && v <= 256 && v % 32 == 0) ctx->head_small = v; }
     if (const char *me = getenv("RP_MID_END")) {
         int n = 0, vals[4] = {0, 0, 0, 0};

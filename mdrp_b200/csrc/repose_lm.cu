@@ -20,7 +20,7 @@ template <int VARIANT, int NP>
 static void launch_variant(int sms, const LMArgs &a, cudaStream_t st) {
     // the LO refinement (use_final = 0) always uses the TRUNCATED loss: compile-time specialisation
     // (the one-problem-per-pair launches have too few problems for warp granularity: 2-3 per warp leave a long tail)
-    if (a.warp_kernel && a.prob_list && !a.mask && !a.use_final)
+    if (a.warp_kernel && (a.prob_list || a.warp_single) && !a.mask && !a.use_final)
         lm_warp_kernel<VARIANT, NP, RP_LOSS_TRUNCATED>
             <<<occupancy_grid(sms, lm_warp_kernel<VARIANT, NP, RP_LOSS_TRUNCATED>, LMW_WPB[VARIANT] * 32), LMW_WPB[VARIANT] * 32, 0, st>>>(a);
     else if (!a.use_final)

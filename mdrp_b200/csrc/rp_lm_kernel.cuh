@@ -40,6 +40,7 @@ struct LMArgs {
     unsigned long long *lm_flops;   // optional: FP64 flops executed (LM_FLOPS table x device counts)
     int *work_counter;           // zeroed before the launch: blocks take problems dynamically
     int warp_kernel;             // unmasked problems: one warp per problem (lm_warp_kernel) instead of one block
+    int warp_single;             // ... also for the one-problem-per-pair launches without a problem list (final LO)
 };
 
 constexpr int LM_LIST_CAP = 16384;  // 32 KB of shared memory per block (3 blocks/SM); indices fit 16 bits
