@@ -26,6 +26,14 @@ static void launch_variant(int sms, const LMArgs &a, cudaStream_t st) {
     else if (!a.use_final)
         lm_kernel<VARIANT, NP, RP_LM_THREADS, RP_LOSS_TRUNCATED>
             <<<occupancy_grid(sms, lm_kernel<VARIANT, NP, RP_LM_THREADS, RP_LOSS_TRUNCATED>, RP_LM_THREADS), RP_LM_THREADS, 0, st>>>(a);
+    // the final refinement with the two losses the reference's drivers and defaults use, fixed at compile time (no loss
+    // switch and no unused loss code in the loop: the launch is sensitive to instruction fetch), any other loss at run time
+    else if (a.loss_type == RP_LOSS_TRUNCATED_CAUCHY)
+        lm_kernel<VARIANT, NP, RP_LM_THREADS, RP_LOSS_TRUNCATED_CAUCHY>
+            <<<occupancy_grid(sms, lm_kernel<VARIANT, NP, RP_LM_THREADS, RP_LOSS_TRUNCATED_CAUCHY>, RP_LM_THREADS), RP_LM_THREADS, 0, st>>>(a);
+    else if (a.loss_type == RP_LOSS_CAUCHY)
+        lm_kernel<VARIANT, NP, RP_LM_THREADS, RP_LOSS_CAUCHY>
+            <<<occupancy_grid(sms, lm_kernel<VARIANT, NP, RP_LM_THREADS, RP_LOSS_CAUCHY>, RP_LM_THREADS), RP_LM_THREADS, 0, st>>>(a);
     else
         lm_kernel<VARIANT, NP, RP_LM_THREADS, -1>
             <<<occupancy_grid(sms, lm_kernel<VARIANT, NP, RP_LM_THREADS, -1>, RP_LM_THREADS), RP_LM_THREADS, 0, st>>>(a);

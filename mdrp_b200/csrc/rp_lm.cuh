@@ -90,11 +90,15 @@ struct LogProd {
     }
 };
 
+// LOSS template argument of the LM code: >= 0 fixes the robust loss at compile time, < 0 reads it from LMParams.  The
+// Cauchy losses (compile-time or run-time) take the log-product path on the device.
+RP_HD constexpr bool lm_loss_may_be_cauchy(int LOSS) { return LOSS < 0 || LOSS == RP_LOSS_CAUCHY || LOSS == RP_LOSS_TRUNCATED_CAUCHY; }
+
 // one robustified residual of the LM cost: returns its contribution, or parks it in `lp` (device, Cauchy losses)
 template <int LOSS, bool SAMPSON>
 RP_HD double robust_cost(const LMParams &P, int loss_type, double r2, LogProd &lp) {
 #ifdef __CUDA_ARCH__
-    if (LOSS < 0 && (loss_type == RP_LOSS_CAUCHY || loss_type == RP_LOSS_TRUNCATED_CAUCHY)) {
+    if (lm_loss_may_be_cauchy(LOSS) && (loss_type == RP_LOSS_CAUCHY || loss_type == RP_LOSS_TRUNCATED_CAUCHY)) {
         lp.template add<SAMPSON>(loss_type, r2 * P.inv_t2, P.weight_sampson);
         return 0.0;
     }
@@ -106,7 +110,7 @@ RP_HD double robust_cost(const LMParams &P, int loss_type, double r2, LogProd &l
 template <int LOSS>
 RP_HD double robust_weight(const LMParams &P, int loss_type, double r2) {
 #ifdef __CUDA_ARCH__
-    if (LOSS < 0 && (loss_type == RP_LOSS_CAUCHY || loss_type == RP_LOSS_TRUNCATED_CAUCHY)) {
+    if (lm_loss_may_be_cauchy(LOSS) && (loss_type == RP_LOSS_CAUCHY || loss_type == RP_LOSS_TRUNCATED_CAUCHY)) {
         const double x = r2 * P.inv_t2;
         if (loss_type == RP_LOSS_TRUNCATED_CAUCHY && x > 1.0) return 0.0;
         return lm_rcp(1.0 + x);

@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(THREADS, RP_LM_MIN_BLOCKS * 128 / THREADS) lm_
         P.weight_sampson = a.weight_sampson;
         P.scale_reproj = a.scale_reproj_override >= 0.0 ? a.scale_reproj_override : pp.scale_reproj;
         if (a.use_final) {
-            P.loss_type = a.loss_type;
+            P.loss_type = LOSS >= 0 ? LOSS : a.loss_type;
             P.loss_scale = a.loss_scale_override > 0.0 ? a.loss_scale_override : pp.final_loss_scale;
         } else {
             P.loss_type = RP_LOSS_TRUNCATED;
@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(THREADS, RP_LM_MIN_BLOCKS * 128 / THREADS) lm_
                 const Pt64 p = pts[k];
                 c += point_cost<VARIANT, LOSS>(F, P, p.x1_0, p.x1_1, p.x2_0, p.x2_1, d1[k], d2[k], lp);
             }
-            if (LOSS < 0) c += P.loss_scale * P.loss_scale * lp.total(P.weight_sampson);
+            if (lm_loss_may_be_cauchy(LOSS)) c += P.loss_scale * P.loss_scale * lp.total(P.weight_sampson);
             c = warp_sum(c);
             __syncthreads();
             if (lane == 0) cred[wid] = c;
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(THREADS, RP_LM_MIN_BLOCKS * 128 / THREADS) lm_
                 const Pt64 p = pts[k];
                 c += point_eval<VARIANT, NP, LOSS>(F, P, p.x1_0, p.x1_1, p.x2_0, p.x2_1, d1[k], d2[k], N, rows, lp);
             }
-            if (LOSS < 0) c += P.loss_scale * P.loss_scale * lp.total(P.weight_sampson);
+            if (lm_loss_may_be_cauchy(LOSS)) c += P.loss_scale * P.loss_scale * lp.total(P.weight_sampson);
             c = warp_sum(c);
             __syncthreads();
             if (lane == 0) cred[wid] = c;
@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(LMW_WPB[VARIANT] * 32, LMW_BPS[VARIANT]) lm_wa
         P.weight_sampson = a.weight_sampson;
         P.scale_reproj = a.scale_reproj_override >= 0.0 ? a.scale_reproj_override : pp.scale_reproj;
         if (a.use_final) {
-            P.loss_type = a.loss_type;
+            P.loss_type = LOSS >= 0 ? LOSS : a.loss_type;
             P.loss_scale = a.loss_scale_override > 0.0 ? a.loss_scale_override : pp.final_loss_scale;
         } else {
             P.loss_type = RP_LOSS_TRUNCATED;
@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(LMW_WPB[VARIANT] * 32, LMW_BPS[VARIANT]) lm_wa
                 if (++s == LMW_SLOTS) s = 0;
             }
             cp_async_wait<0>();
-            if (LOSS < 0) c += P.loss_scale * P.loss_scale * lp.total(P.weight_sampson);
+            if (lm_loss_may_be_cauchy(LOSS)) c += P.loss_scale * P.loss_scale * lp.total(P.weight_sampson);
             return warp_sum(c);
         };
         auto reduce_normal = [&](NormalEq<NP> &N) {
